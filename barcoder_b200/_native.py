@@ -1,0 +1,224 @@
+"""ctypes binding of libbarcoder_b200.so (C ABI: include/barcoder_b200.h).
+
+This is the only compute path of the package.  There is no CPU fallback: if the shared
+library is missing, cannot be loaded, or no CUDA device is usable, the calls raise
+(``NativeLibraryError`` / ``BowtieError`` upstream) instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbarcoder_b200.so")
+
+BC_OK = 0
+BC_PAM_IUPAC = 1
+BC_PAM_GATE = 2
+BC_PARAM_BLOCKS = 1
+BC_PARAM_PATH = 2
+BC_PARAM_COUNT_CANDIDATES = 3
+BC_PARAM_HIT_CAPACITY = 4
+PATH_AUTO, PATH_PROBE, PATH_JOIN = 0, 1, 2
+
+META_PAM_OK = 1 << 3
+META_PAM_FULL = 1 << 4
+META_PAM_AMB = 1 << 5
+
+HIT_DTYPE = np.dtype([("spacer_id", "<u4"), ("gpos", "<u4"), ("mm_mask", "<u4"), ("meta", "<u4")])
+
+EXPORTS = (
+    "bc_abi_version", "bc_create", "bc_destroy", "bc_set_genome", "bc_set_genome_dev", "bc_set_library",
+    "bc_set_library_dev", "bc_set_pam", "bc_set_param", "bc_build_index", "bc_search", "bc_copy_hits",
+    "bc_hits_device", "bc_get_stats", "bc_last_error",
+)
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class BcStats(ctypes.Structure):
+    _fields_ = [
+        ("genome_bases", ctypes.c_uint64), ("library_spacers", ctypes.c_uint64),
+        ("spacer_len", ctypes.c_uint32), ("k", ctypes.c_uint32), ("blocks", ctypes.c_uint32),
+        ("combos", ctypes.c_uint32), ("path", ctypes.c_uint32), ("scan_launches", ctypes.c_uint32),
+        ("hits", ctypes.c_uint64), ("candidates", ctypes.c_uint64), ("probes", ctypes.c_uint64),
+        ("ms_pack_genome", ctypes.c_float), ("ms_pack_library", ctypes.c_float),
+        ("ms_build_index", ctypes.c_float), ("ms_search", ctypes.c_float),
+        ("ms_scan_kernel", ctypes.c_float), ("reserved", ctypes.c_uint32 * 8),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+_lib = None
+
+
+def load():
+    """Load the extension once; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C barcoder_b200/csrc`. barcoder_b200 has no CPU fallback."
+        )
+    try:
+        L = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover - depends on the box
+        raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    vp, u8p, u32, u64, i32, i64 = (ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64,
+                                   ctypes.c_int, ctypes.c_int64)
+    L.bc_abi_version.restype = i32
+    L.bc_create.argtypes = [ctypes.POINTER(vp), i32]
+    L.bc_destroy.argtypes = [vp]
+    L.bc_destroy.restype = None
+    L.bc_set_genome.argtypes = [vp, u8p, vp, u32]
+    L.bc_set_genome_dev.argtypes = [vp, u8p, vp, u32, vp]
+    L.bc_set_library.argtypes = [vp, u8p, u32, u32]
+    L.bc_set_library_dev.argtypes = [vp, u8p, u32, u32, vp]
+    L.bc_set_pam.argtypes = [vp, ctypes.c_char_p, i32, u32]
+    L.bc_set_param.argtypes = [vp, i32, i64]
+    L.bc_build_index.argtypes = [vp, i32]
+    L.bc_search.argtypes = [vp, i32, ctypes.POINTER(u64)]
+    L.bc_copy_hits.argtypes = [vp, vp, u64]
+    L.bc_hits_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
+    L.bc_get_stats.argtypes = [vp, ctypes.POINTER(BcStats)]
+    L.bc_last_error.argtypes = [vp]
+    L.bc_last_error.restype = ctypes.c_char_p
+    for name in EXPORTS:
+        if name not in ("bc_destroy", "bc_last_error"):
+            getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"barcoder_b200 native error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class Searcher:
+    """Thin object wrapper over one bc_ctx (one GPU)."""
+
+    def __init__(self, device=0):
+        self._L = load()
+        self._ctx = ctypes.c_void_p()
+        rc = self._L.bc_create(ctypes.byref(self._ctx), int(device))
+        if rc != BC_OK:
+            msg = self._L.bc_last_error(None)
+            self._ctx = None
+            raise NativeError(rc, (msg or b"").decode())
+        self.device = device
+        self.contig_offsets = None
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.bc_destroy(self._ctx)
+            self._ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != BC_OK:
+            raise NativeError(rc, (self._L.bc_last_error(self._ctx) or b"").decode())
+
+    # -- inputs
+    def set_genome(self, contigs):
+        """contigs: list of str/bytes.  Host buffers; the copy to the device is inside the call."""
+        bs = [c.encode("ascii") if isinstance(c, str) else bytes(c) for c in contigs]
+        off = np.zeros(len(bs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(bs), dtype=np.uint8) if off[-1] else np.zeros(1, np.uint8)
+        self.set_genome_array(blob, off)
+
+    def set_genome_array(self, ascii_u8, offsets_u64):
+        ascii_u8 = np.ascontiguousarray(ascii_u8, dtype=np.uint8)
+        off = np.ascontiguousarray(offsets_u64, dtype=np.uint64)
+        self._check(self._L.bc_set_genome(self._ctx, ascii_u8.ctypes.data, off.ctypes.data, len(off) - 1))
+        self.contig_offsets = off.copy()
+
+    def set_genome_device(self, data_ptr, offsets_u64, stream=0):
+        off = np.ascontiguousarray(offsets_u64, dtype=np.uint64)
+        self._check(self._L.bc_set_genome_dev(self._ctx, data_ptr, off.ctypes.data, len(off) - 1, stream or None))
+        self.contig_offsets = off.copy()
+
+    def set_library(self, spacers):
+        """spacers: list of equal-length str, or a uint8 array [n, L]."""
+        if isinstance(spacers, np.ndarray):
+            arr = np.ascontiguousarray(spacers, dtype=np.uint8)
+            n, L = arr.shape
+        else:
+            spacers = list(spacers)
+            n = len(spacers)
+            L = len(spacers[0]) if n else 1
+            if any(len(s) != L for s in spacers):
+                raise ValueError("all spacers passed to one set_library call must have the same length")
+            arr = np.frombuffer("".join(spacers).encode("ascii"), dtype=np.uint8) if n else np.zeros(1, np.uint8)
+        self._check(self._L.bc_set_library(self._ctx, arr.ctypes.data, n, L))
+        self.n, self.L = n, L
+
+    def set_library_device(self, data_ptr, n, L, stream=0):
+        self._check(self._L.bc_set_library_dev(self._ctx, data_ptr, n, L, stream or None))
+        self.n, self.L = n, L
+
+    def set_pam(self, pam="", direction="downstream", iupac=False, gate=False):
+        d = {"downstream": 0, "upstream": 1}.get(direction)
+        if d is None:
+            raise ValueError("direction must be 'upstream' or 'downstream'")
+        flags = (BC_PAM_IUPAC if iupac else 0) | (BC_PAM_GATE if gate else 0)
+        self._check(self._L.bc_set_pam(self._ctx, pam.upper().encode("ascii"), d, flags))
+
+    def set_param(self, key, value):
+        self._check(self._L.bc_set_param(self._ctx, key, int(value)))
+
+    # -- compute
+    def build_index(self, k):
+        self._check(self._L.bc_build_index(self._ctx, int(k)))
+
+    def search(self, k):
+        n = ctypes.c_uint64()
+        self._check(self._L.bc_search(self._ctx, int(k), ctypes.byref(n)))
+        return n.value
+
+    def hits(self):
+        """Copy the result records of the last search to the host (unordered)."""
+        st = self.stats()
+        out = np.empty(st["hits"], dtype=HIT_DTYPE)
+        if len(out):
+            self._check(self._L.bc_copy_hits(self._ctx, out.ctypes.data, len(out)))
+        return out
+
+    def hits_device(self):
+        ptr, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self._L.bc_hits_device(self._ctx, ctypes.byref(ptr), ctypes.byref(n)))
+        return ptr.value or 0, n.value
+
+    def stats(self):
+        st = BcStats()
+        self._check(self._L.bc_get_stats(self._ctx, ctypes.byref(st)))
+        return st.as_dict()
+
+
+def canonical_sort(hits):
+    """(spacer_id, gpos, strand) order - the order every parity comparison uses."""
+    order = np.lexsort((hits["meta"] & 1, hits["gpos"], hits["spacer_id"]))
+    return hits[order]

@@ -1,0 +1,576 @@
+// bc_api.cu - the C ABI declared in include/barcoder_b200.h: context, device memory,
+// seed-scheme selection and kernel orchestration.  No CPU search path exists in this file:
+// every data-touching step is a kernel launch; the host only plans and moves pointers.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "bc_kernels.h"
+#include "bc_join.h"
+
+struct bc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string err;
+
+    // genome
+    uint64_t G = 0;
+    uint32_t n_contigs = 0, n_pos = 0, n_words = 0;
+    std::vector<uint64_t> coff;
+    uint32_t *d_H = nullptr, *d_L = nullptr, *d_B = nullptr, *d_start_dev = nullptr;
+    bool have_genome = false;
+
+    // library
+    uint32_t n = 0, L = 0;
+    uint32_t *d_qh = nullptr, *d_ql = nullptr, *d_sn = nullptr, *d_any_n = nullptr;
+    uint32_t lib_has_n = 0;
+    bool have_library = false;
+
+    // PAM
+    uint32_t P = 0, pam_dir = 0, pam_flags = 0, pam_sets[8] = {0};
+
+    // params
+    int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0;
+
+    // index
+    bool have_index = false;
+    int index_k = -1;
+    uint32_t b = 0, n_combos = 0;
+    uint32_t block_mask[BC_MAX_BLOCKS] = {0};
+    ComboDesc combo[BC_MAX_COMBOS];
+    uint64_t dir_slots = 0;
+    uint32_t *d_dir = nullptr, *d_cursor = nullptr, *d_scan_tmp = nullptr, *d_ent_id = nullptr;
+    uint2* d_ent_hl = nullptr;
+    uint64_t ent_cap = 0, dir_cap = 0, scan_tmp_cap = 0;
+
+    // join workspace
+    JoinWorkspace join;
+
+    // results
+    bc_hit* d_hits = nullptr;
+    uint64_t hit_cap = 0, n_hits = 0;
+    unsigned long long* d_count = nullptr;
+
+    bc_stats stats;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char buf__[512];                                                                       \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                     __FILE__, __LINE__);                                                          \
+            ctx->err = buf__;                                                                      \
+            return e__ == cudaErrorMemoryAllocation ? BC_ENOMEM : BC_ECUDA;                        \
+        }                                                                                          \
+    } while (0)
+
+static int fail(bc_ctx* ctx, int code, const char* msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+template <class T>
+static void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static thread_local std::string g_create_err;
+
+extern "C" int bc_abi_version(void) { return BC_ABI_VERSION; }
+
+extern "C" int bc_create(bc_ctx** out, int device) {
+    if (!out) return BC_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_err = std::string("no usable CUDA device: ") + cudaGetErrorString(e);
+        return BC_ENODEV;
+    }
+    if (device < 0 || device >= count) {
+        g_create_err = "device ordinal out of range";
+        return BC_EINVAL;
+    }
+    bc_ctx* ctx = new bc_ctx();
+    ctx->device = device;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    memset(ctx->combo, 0, sizeof ctx->combo);
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreate(&ctx->stream) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev2) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev3) != cudaSuccess ||
+        cudaMalloc(&ctx->d_count, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_any_n, sizeof(uint32_t)) != cudaSuccess) {
+        g_create_err = std::string("CUDA context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return BC_ECUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return BC_OK;
+}
+
+extern "C" void bc_destroy(bc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B); dfree(ctx->d_start_dev);
+    dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn); dfree(ctx->d_any_n);
+    dfree(ctx->d_dir); dfree(ctx->d_cursor); dfree(ctx->d_scan_tmp); dfree(ctx->d_ent_id); dfree(ctx->d_ent_hl);
+    dfree(ctx->d_hits); dfree(ctx->d_count);
+    bc_join_free(ctx->join);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* bc_last_error(bc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------- genome
+static int set_genome_common(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* contig_offsets,
+                             uint32_t n_contigs, cudaStream_t st) {
+    uint64_t G = contig_offsets[n_contigs];
+    for (uint32_t c = 0; c < n_contigs; c++)
+        if (contig_offsets[c + 1] < contig_offsets[c]) return fail(ctx, BC_EINVAL, "contig_offsets must be non-decreasing");
+    if (contig_offsets[0] != 0) return fail(ctx, BC_EINVAL, "contig_offsets[0] must be 0");
+    if (G + n_contigs + 64 >= (1ull << 32)) return fail(ctx, BC_ELIMIT, "genome longer than 2^32 - 64 positions");
+    ctx->have_genome = false;
+    ctx->G = G;
+    ctx->n_contigs = n_contigs;
+    ctx->coff.assign(contig_offsets, contig_offsets + n_contigs + 1);
+    ctx->n_pos = (uint32_t)(G + n_contigs);
+    ctx->n_words = (ctx->n_pos + 31) / 32 + 4;  // tail words are all-ambiguous padding
+    dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B); dfree(ctx->d_start_dev);
+    CK(cudaMalloc(&ctx->d_H, (size_t)ctx->n_words * 4));
+    CK(cudaMalloc(&ctx->d_L, (size_t)ctx->n_words * 4));
+    CK(cudaMalloc(&ctx->d_B, (size_t)ctx->n_words * 4));
+    CK(cudaMalloc(&ctx->d_start_dev, (size_t)(n_contigs + 1) * 4));
+    std::vector<uint32_t> start_dev(n_contigs + 1);
+    for (uint32_t c = 0; c <= n_contigs; c++) start_dev[c] = (uint32_t)(contig_offsets[c] + c);
+    uint64_t* d_coff = nullptr;
+    CK(cudaMalloc(&d_coff, (size_t)(n_contigs + 1) * 8));
+    CK(cudaMemcpyAsync(d_coff, contig_offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_start_dev, start_dev.data(), (size_t)(n_contigs + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(bc_launch_pack_genome(d_ascii, d_coff, ctx->d_start_dev, n_contigs, ctx->n_pos, ctx->n_words, ctx->d_H,
+                             ctx->d_L, ctx->d_B, ctx->sm_count, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaStreamSynchronize(st));  // start_dev / d_coff staging must outlive the kernel
+    CK(cudaEventElapsedTime(&ctx->stats.ms_pack_genome, ctx->ev0, ctx->ev1));
+    cudaFree(d_coff);
+    ctx->have_genome = true;
+    ctx->stats.genome_bases = G;
+    return BC_OK;
+}
+
+extern "C" int bc_set_genome_dev(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* contig_offsets,
+                                 uint32_t n_contigs, void* stream) {
+    if (!ctx) return BC_EINVAL;
+    if (!contig_offsets || n_contigs == 0) return fail(ctx, BC_EINVAL, "genome needs at least one contig");
+    if (!d_ascii && contig_offsets[n_contigs] > 0) return fail(ctx, BC_EINVAL, "null genome pointer");
+    CK(cudaSetDevice(ctx->device));
+    return set_genome_common(ctx, d_ascii, contig_offsets, n_contigs, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int bc_set_genome(bc_ctx* ctx, const uint8_t* ascii, const uint64_t* contig_offsets, uint32_t n_contigs) {
+    if (!ctx) return BC_EINVAL;
+    if (!contig_offsets || n_contigs == 0) return fail(ctx, BC_EINVAL, "genome needs at least one contig");
+    uint64_t G = contig_offsets[n_contigs];
+    if (!ascii && G > 0) return fail(ctx, BC_EINVAL, "null genome pointer");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d_ascii = nullptr;
+    CK(cudaMalloc(&d_ascii, G ? G : 1));
+    if (G) CK(cudaMemcpyAsync(d_ascii, ascii, G, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = set_genome_common(ctx, d_ascii, contig_offsets, n_contigs, ctx->stream);
+    cudaFree(d_ascii);
+    return rc;
+}
+
+// --------------------------------------------------------------------------------------- library
+static int set_library_common(bc_ctx* ctx, const uint8_t* d_ascii, uint32_t n, uint32_t L, cudaStream_t st) {
+    if (L < 1 || L > 32) return fail(ctx, BC_ELIMIT, "spacer length must be 1..32");
+    if (n >= (1u << 31)) return fail(ctx, BC_ELIMIT, "too many spacers");
+    ctx->have_library = false;
+    ctx->have_index = false;
+    ctx->n = n;
+    ctx->L = L;
+    dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn);
+    size_t ne = (size_t)2 * n + 1;
+    CK(cudaMalloc(&ctx->d_qh, ne * 4));
+    CK(cudaMalloc(&ctx->d_ql, ne * 4));
+    CK(cudaMalloc(&ctx->d_sn, ((size_t)n + 1) * 4));
+    CK(cudaMemsetAsync(ctx->d_any_n, 0, 4, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(bc_launch_pack_library(d_ascii, n, L, ctx->d_qh, ctx->d_ql, ctx->d_sn, ctx->d_any_n, st));
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(&ctx->lib_has_n, ctx->d_any_n, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_pack_library, ctx->ev0, ctx->ev1));
+    ctx->have_library = true;
+    ctx->stats.library_spacers = n;
+    ctx->stats.spacer_len = L;
+    return BC_OK;
+}
+
+extern "C" int bc_set_library_dev(bc_ctx* ctx, const uint8_t* d_ascii, uint32_t n, uint32_t L, void* stream) {
+    if (!ctx) return BC_EINVAL;
+    if (!d_ascii && n > 0) return fail(ctx, BC_EINVAL, "null library pointer");
+    CK(cudaSetDevice(ctx->device));
+    return set_library_common(ctx, d_ascii, n, L, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int bc_set_library(bc_ctx* ctx, const uint8_t* ascii, uint32_t n, uint32_t L) {
+    if (!ctx) return BC_EINVAL;
+    if (!ascii && n > 0) return fail(ctx, BC_EINVAL, "null library pointer");
+    if (L < 1 || L > 32) return fail(ctx, BC_ELIMIT, "spacer length must be 1..32");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d_ascii = nullptr;
+    size_t bytes = (size_t)n * L;
+    CK(cudaMalloc(&d_ascii, bytes ? bytes : 1));
+    if (bytes) CK(cudaMemcpyAsync(d_ascii, ascii, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = set_library_common(ctx, d_ascii, n, L, ctx->stream);
+    cudaFree(d_ascii);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------- PAM
+static uint32_t iupac_set(char ch, uint32_t flags) {
+    switch (ch) {
+        case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8; case 'N': return 15;
+        default: break;
+    }
+    if (!(flags & BC_PAM_IUPAC)) return 0;  // literal letter: cannot equal an A/C/G/T base
+    switch (ch) {
+        case 'R': return 5; case 'Y': return 10; case 'S': return 6; case 'W': return 9; case 'K': return 12;
+        case 'M': return 3; case 'B': return 14; case 'D': return 13; case 'H': return 11; case 'V': return 7;
+        default: return 0;
+    }
+}
+
+extern "C" int bc_set_pam(bc_ctx* ctx, const char* pam, int direction, uint32_t flags) {
+    if (!ctx) return BC_EINVAL;
+    if (!pam) pam = "";
+    size_t P = strlen(pam);
+    if (P > 8) return fail(ctx, BC_ELIMIT, "PAM longer than 8 letters");
+    if (direction != 0 && direction != 1) return fail(ctx, BC_EINVAL, "direction must be 0 (downstream) or 1 (upstream)");
+    ctx->P = (uint32_t)P;
+    ctx->pam_dir = (uint32_t)direction;
+    ctx->pam_flags = flags;
+    for (size_t i = 0; i < 8; i++) ctx->pam_sets[i] = i < P ? iupac_set(pam[i], flags) : 0;
+    return BC_OK;
+}
+
+extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
+    if (!ctx) return BC_EINVAL;
+    switch (key) {
+        case BC_PARAM_BLOCKS: ctx->par_blocks = value; ctx->have_index = false; return BC_OK;
+        case BC_PARAM_PATH:
+            if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "path must be 0, 1 or 2");
+            ctx->par_path = value; ctx->have_index = false; return BC_OK;
+        case BC_PARAM_COUNT_CANDIDATES: ctx->par_count = value; return BC_OK;
+        case BC_PARAM_HIT_CAPACITY: ctx->par_hit_cap = value; return BC_OK;
+        default: return fail(ctx, BC_EINVAL, "unknown parameter");
+    }
+}
+
+// ----------------------------------------------------------------------------------- seed scheme
+// Generalised pigeonhole: split the L query positions into b blocks.  An alignment with <= k
+// mismatches leaves >= b-k blocks exact, so indexing every (b-k)-subset of blocks ("seed
+// combination") finds every alignment.  b = k+1 is the classic k+1-seed scheme; larger b means
+// more directory look-ups per window but geometrically fewer candidates.
+struct Scheme {
+    uint32_t b, n_combos;
+    uint32_t block_mask[BC_MAX_BLOCKS];
+    ComboDesc combo[BC_MAX_COMBOS];
+    uint64_t dir_slots;
+    double cand_per_window;  // expected candidates per genome window on uniform data
+};
+
+static bool make_scheme(uint32_t L, uint32_t k, uint32_t b, uint32_t key_cap_nt, uint64_t n_entries, Scheme* s) {
+    if (b < k + 1 || b > BC_MAX_BLOCKS || b > L) return false;
+    uint32_t pick = b - k;
+    if (pick > BC_MAX_PIECES) return false;
+    memset(s, 0, sizeof *s);
+    s->b = b;
+    uint32_t bstart[BC_MAX_BLOCKS + 1];
+    for (uint32_t j = 0; j <= b; j++) bstart[j] = (uint32_t)((uint64_t)j * L / b);
+    for (uint32_t j = 0; j < b; j++) {
+        uint32_t len = bstart[j + 1] - bstart[j];
+        s->block_mask[j] = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << bstart[j];
+    }
+    uint64_t slots = 0;
+    double cand = 0;
+    uint32_t nc = 0;
+    for (uint32_t mask = 0; mask < (1u << b); mask++) {  // ascending mask = deterministic combo order
+        if ((uint32_t)__builtin_popcount(mask) != pick) continue;
+        if (nc == BC_MAX_COMBOS) return false;
+        ComboDesc& cd = s->combo[nc];
+        cd.blocks_mask = mask;
+        uint32_t budget = key_cap_nt, np = 0, knt = 0;
+        for (uint32_t j = 0; j < b && budget; j++) {
+            if (!(mask >> j & 1u)) continue;
+            uint32_t len = bstart[j + 1] - bstart[j];
+            if (len > budget) len = budget;
+            cd.start[np] = (uint8_t)bstart[j];
+            cd.len[np] = (uint8_t)len;
+            cd.key_mask |= ((1u << len) - 1u) << bstart[j];
+            budget -= len;
+            knt += len;
+            np++;
+        }
+        cd.n_pieces = (uint8_t)np;
+        cd.key_nt = (uint8_t)knt;
+        if (slots >= (1ull << 32)) return false;
+        cd.dir_off = (uint32_t)slots;
+        slots += 1ull << (2 * knt);
+        cand += (double)n_entries / (double)(1ull << (2 * knt));
+        nc++;
+    }
+    s->n_combos = nc;
+    s->dir_slots = slots + 1;  // +1: end sentinel of the last bucket
+    s->cand_per_window = cand;
+    return slots + 1 < (1ull << 32);
+}
+
+static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_out) {
+    const uint64_t E = 2ull * ctx->n;
+    uint32_t cap = 4;
+    while (cap < BC_KEY_MAX_NT && (1ull << (2 * cap)) < 16 * (E ? E : 1)) cap++;
+    const double windows = (double)(ctx->G ? ctx->G : 1);
+    double best_cost = 0;
+    bool found = false;
+    uint32_t best_path = 1;
+    for (uint32_t b = k + 1; b <= k + 4 && b <= BC_MAX_BLOCKS; b++) {
+        if (ctx->par_blocks && (uint32_t)ctx->par_blocks != b) continue;
+        Scheme s;
+        if (!make_scheme(ctx->L, k, b, cap, E, &s)) continue;
+        // Relative cost model: a directory probe is an L2 round trip
+        // (~8 units), a verified candidate ~1 unit in the probe kernel; the join kernel has no
+        // per-window probes but sorts the windows once per combination (~6 units each) and
+        // verifies candidates from shared memory (~0.35 units).
+        double dir_cost = 6.0 * (double)s.dir_slots;
+        double probe_cost = windows * (8.0 * s.n_combos + 1.0 * s.cand_per_window) + dir_cost;
+        double join_cost = windows * (6.0 * s.n_combos + 0.35 * s.cand_per_window) + dir_cost + 4.0e6 * s.n_combos;
+        for (uint32_t path = 1; path <= 2; path++) {
+            if (ctx->par_path && (uint32_t)ctx->par_path != path) continue;
+            if (path == 2 && !bc_join_supported(s.combo, s.n_combos)) continue;
+            double cost = path == 1 ? probe_cost : join_cost;
+            if (!found || cost < best_cost) {
+                found = true;
+                best_cost = cost;
+                *best = s;
+                best_path = path;
+            }
+        }
+    }
+    if (!found) return fail(ctx, BC_EINVAL, "no feasible seed scheme for this (L, k, blocks, path)");
+    *path_out = best_path;
+    return BC_OK;
+}
+
+extern "C" int bc_build_index(bc_ctx* ctx, int k) {
+    if (!ctx) return BC_EINVAL;
+    if (!ctx->have_library) return fail(ctx, BC_EINVAL, "bc_build_index: no library loaded");
+    if (!ctx->have_genome) return fail(ctx, BC_EINVAL, "bc_build_index: no genome loaded");
+    if (k < 0 || k > 3) return fail(ctx, BC_ELIMIT, "k must be 0..3 (bowtie -v limit)");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_index = false;
+    ctx->index_k = k;
+    ctx->stats.k = (uint32_t)k;
+    if ((uint32_t)k >= ctx->L || ctx->n == 0) {  // reads with L <= k are never aligned (oracle.c rule 7)
+        ctx->n_combos = 0;
+        ctx->b = 0;
+        ctx->have_index = true;
+        ctx->stats.ms_build_index = 0;
+        return BC_OK;
+    }
+    Scheme s;
+    uint32_t path = 1;
+    int rc = choose_scheme(ctx, (uint32_t)k, &s, &path);
+    if (rc != BC_OK) return rc;
+    ctx->b = s.b;
+    ctx->n_combos = s.n_combos;
+    memcpy(ctx->block_mask, s.block_mask, sizeof s.block_mask);
+    memcpy(ctx->combo, s.combo, sizeof s.combo);
+    ctx->dir_slots = s.dir_slots;
+    ctx->stats.blocks = s.b;
+    ctx->stats.combos = s.n_combos;
+    ctx->stats.path = path;
+
+    const uint64_t E = 2ull * ctx->n;
+    const uint64_t ent_needed = E * s.n_combos;
+    if (ent_needed >= (1ull << 32)) return fail(ctx, BC_ELIMIT, "library x combinations exceeds 2^32 index entries");
+    if (ent_needed > ctx->ent_cap) {
+        dfree(ctx->d_ent_hl); dfree(ctx->d_ent_id);
+        ctx->ent_cap = 0;
+        CK(cudaMalloc(&ctx->d_ent_hl, (ent_needed + 1) * sizeof(uint2)));
+        CK(cudaMalloc(&ctx->d_ent_id, (ent_needed + 1) * sizeof(uint32_t)));
+        ctx->ent_cap = ent_needed;
+    }
+    if (s.dir_slots > ctx->dir_cap) {
+        dfree(ctx->d_dir); dfree(ctx->d_cursor);
+        ctx->dir_cap = 0;
+        CK(cudaMalloc(&ctx->d_dir, s.dir_slots * 4));
+        CK(cudaMalloc(&ctx->d_cursor, s.dir_slots * 4));
+        ctx->dir_cap = s.dir_slots;
+    }
+    uint64_t tmp_words = bc_scan_tmp_words(s.dir_slots);
+    if (tmp_words > ctx->scan_tmp_cap) {
+        dfree(ctx->d_scan_tmp);
+        ctx->scan_tmp_cap = 0;
+        CK(cudaMalloc(&ctx->d_scan_tmp, tmp_words * 4));
+        ctx->scan_tmp_cap = tmp_words;
+    }
+    IndexParams ip;
+    ip.qh = ctx->d_qh; ip.ql = ctx->d_ql; ip.sn = ctx->d_sn;
+    ip.n_entries = (uint32_t)E;
+    ip.L = ctx->L;
+    ip.lib_has_n = ctx->lib_has_n;
+    memcpy(ip.combo, ctx->combo, sizeof ip.combo);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_hl,
+                             ctx->d_ent_id, ctx->sm_count, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev0, ctx->ev1));
+    ctx->have_index = true;
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------- search
+static void fill_params(bc_ctx* ctx, SearchParams* p) {
+    memset(p, 0, sizeof *p);
+    p->H = ctx->d_H; p->Lo = ctx->d_L; p->B = ctx->d_B;
+    p->start_dev = ctx->d_start_dev;
+    p->n_pos = ctx->n_pos;
+    p->n_contigs = ctx->n_contigs;
+    p->sn = ctx->d_sn;
+    p->lib_has_n = ctx->lib_has_n;
+    p->L = ctx->L;
+    p->k = (uint32_t)ctx->index_k;
+    p->b = ctx->b;
+    p->n_combos = ctx->n_combos;
+    memcpy(p->block_mask, ctx->block_mask, sizeof p->block_mask);
+    memcpy(p->combo, ctx->combo, sizeof p->combo);
+    p->dir = ctx->d_dir;
+    p->ent_hl = ctx->d_ent_hl;
+    p->ent_id = ctx->d_ent_id;
+    p->P = ctx->P;
+    p->pam_dir = ctx->pam_dir;
+    p->pam_flags = ctx->pam_flags;
+    memcpy(p->pam_sets, ctx->pam_sets, sizeof p->pam_sets);
+    p->hits = ctx->d_hits;
+    p->count = ctx->d_count;
+    p->cap = ctx->hit_cap;
+    p->count_candidates = ctx->par_count ? 1u : 0u;
+}
+
+extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
+    if (!ctx) return BC_EINVAL;
+    if (n_hits_out) *n_hits_out = 0;
+    if (!ctx->have_library || !ctx->have_genome) return fail(ctx, BC_EINVAL, "bc_search: genome and library must be loaded first");
+    if (!ctx->have_index || ctx->index_k != k) {
+        int rc = bc_build_index(ctx, k);
+        if (rc != BC_OK) return rc;
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_hits = 0;
+    ctx->stats.hits = ctx->stats.candidates = ctx->stats.probes = 0;
+    ctx->stats.ms_search = ctx->stats.ms_scan_kernel = 0;
+    ctx->stats.scan_launches = 0;
+    if (ctx->n_combos == 0 || ctx->G < ctx->L) return BC_OK;
+
+    uint64_t want = ctx->par_hit_cap > 0 ? (uint64_t)ctx->par_hit_cap : 8ull * ctx->n;
+    if (ctx->par_hit_cap <= 0) {
+        if (want < (1ull << 20)) want = 1ull << 20;
+        if (want > (1ull << 28)) want = 1ull << 28;
+    }
+    if (ctx->hit_cap < want) {
+        dfree(ctx->d_hits);
+        ctx->hit_cap = 0;
+        CK(cudaMalloc(&ctx->d_hits, want * sizeof(bc_hit)));
+        ctx->hit_cap = want;
+    }
+    float ms_total = 0, ms_scan = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        SearchParams p;
+        fill_params(ctx, &p);
+        CK(cudaMemsetAsync(ctx->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        uint32_t launches = 0;
+        if (ctx->stats.path == 2) {
+            CK(bc_join_search(ctx->join, p, ctx->sm_count, ctx->stream, ctx->ev2, ctx->ev3, &launches));
+        } else {
+            CK(cudaEventRecord(ctx->ev2, ctx->stream));
+            CK(bc_launch_scan_probe(p, ctx->sm_count, ctx->stream));
+            CK(cudaEventRecord(ctx->ev3, ctx->stream));
+            launches = 1;
+        }
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        unsigned long long counts[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(counts, ctx->d_count, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float a = 0, b2 = 0;
+        CK(cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1));
+        if (ctx->stats.path == 2) b2 = ctx->join.ms_join_kernels;
+        else CK(cudaEventElapsedTime(&b2, ctx->ev2, ctx->ev3));
+        ms_total += a;
+        ms_scan += b2;
+        ctx->stats.scan_launches += launches;
+        ctx->stats.candidates = counts[1];
+        ctx->stats.probes = counts[2];
+        if (counts[0] <= ctx->hit_cap) {
+            ctx->n_hits = counts[0];
+            break;
+        }
+        // The buffer was too small: the kernel kept counting, so the exact size is known now.
+        uint64_t need = counts[0] + counts[0] / 16 + 1024;
+        dfree(ctx->d_hits);
+        ctx->hit_cap = 0;
+        CK(cudaMalloc(&ctx->d_hits, need * sizeof(bc_hit)));
+        ctx->hit_cap = need;
+        if (attempt == 2) return fail(ctx, BC_ECUDA, "hit buffer kept overflowing");
+    }
+    ctx->stats.hits = ctx->n_hits;
+    ctx->stats.ms_search = ms_total;
+    ctx->stats.ms_scan_kernel = ms_scan;
+    if (n_hits_out) *n_hits_out = ctx->n_hits;
+    return BC_OK;
+}
+
+extern "C" int bc_copy_hits(bc_ctx* ctx, bc_hit* dst, uint64_t cap) {
+    if (!ctx) return BC_EINVAL;
+    if (cap < ctx->n_hits) return fail(ctx, BC_EINVAL, "bc_copy_hits: destination too small");
+    if (ctx->n_hits == 0) return BC_OK;
+    if (!dst) return fail(ctx, BC_EINVAL, "bc_copy_hits: null destination");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, ctx->d_hits, ctx->n_hits * sizeof(bc_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BC_OK;
+}
+
+extern "C" int bc_hits_device(bc_ctx* ctx, const bc_hit** d_hits, uint64_t* n_hits) {
+    if (!ctx || !d_hits || !n_hits) return BC_EINVAL;
+    *d_hits = ctx->d_hits;
+    *n_hits = ctx->n_hits;
+    return BC_OK;
+}
+
+extern "C" int bc_get_stats(bc_ctx* ctx, bc_stats* out) {
+    if (!ctx || !out) return BC_EINVAL;
+    *out = ctx->stats;
+    return BC_OK;
+}

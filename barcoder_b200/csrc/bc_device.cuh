@@ -1,0 +1,142 @@
+// bc_device.cuh - device-side data layout and the shared hit-emission path.
+//
+// HBM layout:
+//   genome   three 1-bit planes H (code>>1), Lo (code&1), B (1 = not ACGT), one bit per base,
+//            LSB-first in uint32 words; contigs are laid out back to back with ONE separator
+//            base (B=1) after each contig, so a window or PAM that would cross a contig
+//            boundary touches a B bit.  "dev position" = position in this layout;
+//            gpos = dev position - contig index.
+//   library  entry e = 2*spacer + strand; qh/ql hold the QUERY planes (the spacer itself for
+//            '+', its reverse complement for '-'), bit j = base j of the query.
+//   index    for every seed combination c a direct-address directory dir[c][key] into a
+//            key-sorted copy of the entries (ent_hl = {qh,ql}, ent_id = e).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/barcoder_b200.h"
+
+#define BC_MAX_COMBOS 35
+#define BC_MAX_PIECES 4
+#define BC_MAX_BLOCKS 8
+#define BC_KEY_MAX_NT 12
+
+struct ComboDesc {
+    uint32_t blocks_mask;            // which of the b blocks form this seed combination
+    uint32_t key_mask;               // query-position bits covered by the key pieces
+    uint32_t dir_off;                // first directory slot of this combination
+    uint8_t n_pieces;
+    uint8_t start[BC_MAX_PIECES];    // first base of each key piece
+    uint8_t len[BC_MAX_PIECES];      // bases in each key piece
+    uint8_t key_nt;                  // total bases in the key
+    uint8_t pad[2];
+};
+
+struct SearchParams {
+    // genome planes
+    const uint32_t* H;
+    const uint32_t* Lo;
+    const uint32_t* B;
+    const uint32_t* start_dev;  // [n_contigs+1] dev position of each contig start; last = n_pos
+    uint32_t n_pos;             // dev positions (bases + separators)
+    uint32_t n_contigs;
+    // library
+    const uint32_t* sn;         // [n] spacer-orientation mask of non-ACGT spacer characters
+    uint32_t lib_has_n;
+    uint32_t L, k, b, n_combos;
+    uint32_t block_mask[BC_MAX_BLOCKS];
+    ComboDesc combo[BC_MAX_COMBOS];
+    // index
+    const uint32_t* dir;
+    const uint2* ent_hl;
+    const uint32_t* ent_id;
+    // PAM
+    uint32_t P, pam_dir, pam_flags;
+    uint32_t pam_sets[8];       // per PAM position: allowed set over {A=1,C=2,G=4,T=8}
+    // output
+    bc_hit* hits;
+    unsigned long long* count;  // [0] hits, [1] candidates, [2] probes
+    unsigned long long cap;
+    uint32_t count_candidates;
+};
+
+__device__ __forceinline__ uint32_t bc_lmask(uint32_t n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+// L-bit window of a plane starting at dev position pos (needs words pos>>5 and (pos>>5)+1).
+__device__ __forceinline__ uint32_t bc_window(const uint32_t* __restrict__ plane, uint32_t pos) {
+    uint32_t w = pos >> 5;
+    return __funnelshift_r(plane[w], plane[w + 1], pos & 31u);
+}
+
+__device__ __forceinline__ uint32_t bc_combo_key(const ComboDesc& cd, uint32_t h, uint32_t l) {
+    uint32_t key = 0;
+    for (uint32_t i = 0; i < cd.n_pieces; i++) {
+        uint32_t len = cd.len[i], st = cd.start[i], m = (1u << len) - 1u;
+        key = (key << (2 * len)) | (((h >> st) & m) << len) | ((l >> st) & m);
+    }
+    return key;
+}
+
+__device__ __forceinline__ uint32_t bc_rev_bits(uint32_t m, uint32_t L) { return __brev(m) >> (32 - L); }
+
+// Rare path: a (window, entry) pair passed the popcount filter in seed combination `c`.
+// Decides whether this combination owns the hit, annotates the PAM and appends the record.
+//   pos   dev position of the window
+//   e     library entry (2*spacer + strand)
+//   m     mismatch mask in QUERY orientation (bit j = query/window base j differs)
+static __device__ __noinline__ void bc_emit_hit(const SearchParams& p, uint32_t c, uint32_t pos, uint32_t e, uint32_t m) {
+    const uint32_t L = p.L;
+    const uint32_t strand = e & 1u, sid = e >> 1;
+    if (p.lib_has_n) {  // non-ACGT spacer characters mismatch everything (oracle.c rule 6)
+        uint32_t nm = p.sn[sid];
+        if (strand) nm = bc_rev_bits(nm, L);
+        m |= nm;
+        if (__popc(m) > (int)p.k) return;
+    }
+    // Ownership: a hit with <= k mismatches has >= b-k exact blocks; it is reported by the
+    // combination made of its LOWEST b-k exact blocks and by no other.
+    uint32_t need = p.b - p.k, own = 0;
+    for (uint32_t j = 0; j < p.b && need; j++)
+        if (!(m & p.block_mask[j])) { own |= 1u << j; need--; }
+    if (own != p.combo[c].blocks_mask) return;
+
+    // contig of the window
+    uint32_t lo = 0, hi = p.n_contigs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (p.start_dev[mid] <= pos) lo = mid; else hi = mid;
+    }
+    const uint32_t cs = p.start_dev[lo], ce = p.start_dev[lo + 1] - 1;  // [cs, ce) are the contig's bases
+    uint32_t meta = strand | ((uint32_t)__popc(m) << 1) | (p.P << 8);
+    if (p.P == 0) {
+        meta |= BC_META_PAM_OK | BC_META_PAM_FULL;
+    } else {
+        const bool right = (p.pam_dir == 0) == (strand == 0);
+        const long long a = right ? (long long)pos + L : (long long)pos - (long long)p.P;
+        if (a >= (long long)cs && a + (long long)p.P <= (long long)ce) {
+            uint32_t codes = 0, amb = 0, ok = 1;
+            for (uint32_t i = 0; i < p.P; i++) {
+                uint32_t d = (uint32_t)a + (strand ? p.P - 1 - i : i);
+                uint32_t w = d >> 5, s = d & 31u;
+                if ((p.B[w] >> s) & 1u) { amb = 1; continue; }
+                uint32_t code = (((p.H[w] >> s) & 1u) << 1) | ((p.Lo[w] >> s) & 1u);
+                if (strand) code = 3u - code;
+                codes |= code << (2 * i);
+                if (!((p.pam_sets[i] >> code) & 1u)) ok = 0;
+            }
+            meta |= BC_META_PAM_FULL | (codes << 16);
+            if (amb) meta |= BC_META_PAM_AMB;
+            else if (ok) meta |= BC_META_PAM_OK;
+        }
+        if ((p.pam_flags & BC_PAM_GATE) && !(meta & (BC_META_PAM_OK | BC_META_PAM_AMB))) return;
+    }
+    unsigned long long slot = atomicAdd(p.count, 1ull);
+    if (slot < p.cap) {
+        bc_hit h;
+        h.spacer_id = sid;
+        h.gpos = pos - lo;
+        h.mm_mask = strand ? bc_rev_bits(m, L) : m;
+        h.meta = meta;
+        reinterpret_cast<uint4*>(p.hits)[slot] = make_uint4(h.spacer_id, h.gpos, h.mm_mask, h.meta);
+    }
+}

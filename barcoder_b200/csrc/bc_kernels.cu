@@ -1,0 +1,299 @@
+// bc_kernels.cu - sm_100a kernels: genome/library packing (K1/K2), seed-index build (K2),
+// and the probe scan (K3-probe).  The bucket-join scan lives in bc_join.cu.
+#include "bc_kernels.h"
+
+// ------------------------------------------------------------------------------------------ K1
+// ASCII genome -> three bit planes.  One warp produces 32 consecutive plane words: in step i
+// the 32 lanes read the 32 bases of word i (one coalesced 32-byte request), three ballots turn
+// them into the H/Lo/B words, and lane i keeps them, so the final stores are coalesced too.
+// Replaces make_fasta + bowtie-build (BowtieRunner.py:55-62,78-102).
+__device__ __forceinline__ int bc_code_of(uint32_t ch) {
+    ch &= 0xdfu;  // fold case
+    return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1;
+}
+
+__global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ ascii,
+                                                     const uint64_t* __restrict__ coff,
+                                                     const uint32_t* __restrict__ start_dev,
+                                                     uint32_t n_contigs, uint32_t n_pos, uint32_t n_words,
+                                                     uint32_t* __restrict__ H, uint32_t* __restrict__ Lo,
+                                                     uint32_t* __restrict__ B) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t wbase = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; wbase < n_words;
+         wbase += warps * 32u) {
+        uint32_t myH = 0, myL = 0, myB = 0xffffffffu;
+        // contig of this lane's first position
+        uint32_t d = wbase * 32u + lane;
+        uint32_t c = 0;
+        {
+            uint32_t lo = 0, hi = n_contigs;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (start_dev[mid] <= d) lo = mid; else hi = mid;
+            }
+            c = lo;
+        }
+#pragma unroll 4
+        for (uint32_t i = 0; i < 32; i++) {
+            d = (wbase + i) * 32u + lane;
+            int code = -1;
+            if (wbase + i < n_words && d < n_pos) {
+                while (c + 1 < n_contigs && d >= start_dev[c + 1]) c++;
+                uint32_t local = d - start_dev[c];
+                uint64_t cs = coff[c], ce = coff[c + 1];
+                if ((uint64_t)local < ce - cs) code = bc_code_of(ascii[cs + local]);
+            }
+            uint32_t h = __ballot_sync(0xffffffffu, code >= 2);
+            uint32_t l = __ballot_sync(0xffffffffu, code >= 0 && (code & 1));
+            uint32_t b = __ballot_sync(0xffffffffu, code < 0);
+            if (lane == i) { myH = h; myL = l; myB = b; }
+        }
+        if (wbase + lane < n_words) {
+            H[wbase + lane] = myH;
+            Lo[wbase + lane] = myL;
+            B[wbase + lane] = myB;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// ASCII spacers -> query planes for both strands.  Replaces make_fastq (BowtieRunner.py:64-76).
+__global__ void __launch_bounds__(256) k_pack_library(const uint8_t* __restrict__ ascii, uint32_t n, uint32_t L,
+                                                      uint32_t* __restrict__ qh, uint32_t* __restrict__ ql,
+                                                      uint32_t* __restrict__ sn, uint32_t* __restrict__ any_n) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint8_t* src = ascii + (size_t)s * L;
+    uint32_t h = 0, l = 0, nm = 0;
+    for (uint32_t j = 0; j < L; j++) {
+        int code = bc_code_of(src[j]);
+        if (code < 0) nm |= 1u << j;
+        else { h |= (uint32_t)(code >> 1) << j; l |= (uint32_t)(code & 1) << j; }
+    }
+    const uint32_t lm = bc_lmask(L);
+    qh[2 * s] = h;
+    ql[2 * s] = l;
+    // reverse complement: base j of the query = complement of spacer base L-1-j.  Non-ACGT
+    // characters keep code 0 on both strands (their mismatch is forced through sn).
+    uint32_t valid = ~nm & lm;
+    qh[2 * s + 1] = bc_rev_bits(~h & valid, L);
+    ql[2 * s + 1] = bc_rev_bits(~l & valid, L);
+    sn[s] = nm;
+    if (nm) atomicOr(any_n, 1u);
+}
+
+// Seed-index build: histogram of keys per combination, (scan on the host side of this file),
+// then scatter of the entries into key order.
+__global__ void __launch_bounds__(256) k_index_count(IndexParams ip, uint32_t* __restrict__ counts) {
+    const ComboDesc cd = ip.combo[blockIdx.y];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ip.n_entries; e += gridDim.x * blockDim.x) {
+        if (ip.lib_has_n) {
+            uint32_t nm = ip.sn[e >> 1];
+            if (e & 1u) nm = bc_rev_bits(nm, ip.L);
+            if (nm & cd.key_mask) continue;  // a seed containing a non-ACGT base is never exact
+        }
+        atomicAdd(&counts[cd.dir_off + bc_combo_key(cd, ip.qh[e], ip.ql[e])], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_index_scatter(IndexParams ip, uint32_t* __restrict__ cursor,
+                                                       uint2* __restrict__ ent_hl, uint32_t* __restrict__ ent_id) {
+    const ComboDesc cd = ip.combo[blockIdx.y];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ip.n_entries; e += gridDim.x * blockDim.x) {
+        if (ip.lib_has_n) {
+            uint32_t nm = ip.sn[e >> 1];
+            if (e & 1u) nm = bc_rev_bits(nm, ip.L);
+            if (nm & cd.key_mask) continue;
+        }
+        uint32_t h = ip.qh[e], l = ip.ql[e];
+        uint32_t slot = atomicAdd(&cursor[cd.dir_off + bc_combo_key(cd, h, l)], 1u);
+        ent_hl[slot] = make_uint2(h, l);
+        ent_id[slot] = e;
+    }
+}
+
+// ---------------------------------------------------------------------------------- prefix scan
+// Exclusive scan of uint32, 3 phases, used for the directories (up to a few 10^8 slots).
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (uint32_t)o) s += y;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    uint32_t base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint64_t n,
+                                                              uint32_t* __restrict__ sums) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < n) s += in[base + i];
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restrict__ data, uint64_t n,
+                                                             const uint32_t* __restrict__ offsets) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = base + i < n ? data[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(s, &total) + (offsets ? offsets[blockIdx.x] : 0);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) data[base + i] = run;
+        run += v[i];
+    }
+}
+
+// In-place exclusive scan of d_data[0..n).  d_tmp must hold bc_scan_tmp_words(n) words.
+size_t bc_scan_tmp_words(uint64_t n) {
+    size_t total = 0;
+    while (n > SCAN_TILE) {
+        n = (n + SCAN_TILE - 1) / SCAN_TILE;
+        total += n;
+    }
+    return total + 1;
+}
+
+cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t blocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (blocks == 1) {
+        k_scan_apply<<<1, SCAN_THREADS, 0, st>>>(d_data, n, nullptr);
+        return cudaGetLastError();
+    }
+    k_scan_reduce<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(d_data, n, d_tmp);
+    cudaError_t err = bc_exclusive_scan(d_tmp, blocks, d_tmp + blocks, st);
+    if (err != cudaSuccess) return err;
+    k_scan_apply<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(d_data, n, d_tmp);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ K3-probe
+// Streams the genome planes tile by tile through shared memory; every thread owns one window
+// per step, builds the seed keys of each combination, looks the bucket up in the directory and
+// verifies the bucket's entries with XOR + popcount.  Replaces bowtie align
+// (BowtieRunner.py:104-141) for libraries whose buckets are small.
+#define PROBE_THREADS 256
+#define PROBE_STEPS 8
+#define PROBE_TILE_POS (PROBE_THREADS * PROBE_STEPS)  // 2048 windows
+#define PROBE_TILE_WORDS (PROBE_TILE_POS / 32)        // 64 words per plane (+1 halo)
+
+__global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_constant__ SearchParams p,
+                                                              uint32_t n_tiles) {
+    __shared__ uint32_t sH[PROBE_TILE_WORDS + 1], sL[PROBE_TILE_WORDS + 1], sB[PROBE_TILE_WORDS + 1];
+    const uint32_t lm = bc_lmask(p.L);
+    unsigned long long cand = 0, probes = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t w0 = tile * PROBE_TILE_WORDS;
+        __syncthreads();
+        if (threadIdx.x <= PROBE_TILE_WORDS) {  // planes are padded, w0 + 64 is always readable
+            sH[threadIdx.x] = p.H[w0 + threadIdx.x];
+            sL[threadIdx.x] = p.Lo[w0 + threadIdx.x];
+            sB[threadIdx.x] = p.B[w0 + threadIdx.x];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t step = 0; step < PROBE_STEPS; step++) {
+            const uint32_t t = step * PROBE_THREADS + threadIdx.x;
+            const uint32_t pos = tile * PROBE_TILE_POS + t;
+            if (pos >= p.n_pos) continue;
+            if (bc_window(sB, t) & lm) continue;  // window touches a non-ACGT base or a contig end
+            const uint32_t wh = bc_window(sH, t) & lm, wl = bc_window(sL, t) & lm;
+            for (uint32_t c = 0; c < p.n_combos; c++) {
+                const uint32_t slot = p.combo[c].dir_off + bc_combo_key(p.combo[c], wh, wl);
+                uint32_t e = p.dir[slot];
+                const uint32_t e_end = p.dir[slot + 1];
+                probes++;
+                for (; e < e_end; e++) {
+                    const uint2 q = p.ent_hl[e];
+                    const uint32_t m = (wh ^ q.x) | (wl ^ q.y);
+                    cand++;
+                    if (__popc(m) <= (int)p.k) bc_emit_hit(p, c, pos, p.ent_id[e], m);
+                }
+            }
+        }
+    }
+    if (p.count_candidates) {
+        atomicAdd(p.count + 1, cand);
+        atomicAdd(p.count + 2, probes);
+    }
+}
+
+cudaError_t bc_launch_scan_probe(const SearchParams& p, int sm_count, cudaStream_t st) {
+    uint32_t n_tiles = (p.n_pos + PROBE_TILE_POS - 1) / PROBE_TILE_POS;
+    if (n_tiles == 0) return cudaSuccess;
+    uint32_t grid = (uint32_t)sm_count * 8u;
+    if (grid > n_tiles) grid = n_tiles;
+    k_scan_probe<<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t bc_launch_pack_genome(const uint8_t* d_ascii, const uint64_t* d_coff, const uint32_t* d_start_dev,
+                                  uint32_t n_contigs, uint32_t n_pos, uint32_t n_words, uint32_t* H, uint32_t* Lo,
+                                  uint32_t* B, int sm_count, cudaStream_t st) {
+    uint32_t warps_needed = (n_words + 31) / 32;
+    uint32_t blocks = (warps_needed + 7) / 8;
+    uint32_t maxb = (uint32_t)sm_count * 16u;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks == 0) blocks = 1;
+    k_pack_genome<<<blocks, 256, 0, st>>>(d_ascii, d_coff, d_start_dev, n_contigs, n_pos, n_words, H, Lo, B);
+    return cudaGetLastError();
+}
+
+cudaError_t bc_launch_pack_library(const uint8_t* d_ascii, uint32_t n, uint32_t L, uint32_t* qh, uint32_t* ql,
+                                   uint32_t* sn, uint32_t* any_n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_pack_library<<<(n + 255) / 256, 256, 0, st>>>(d_ascii, n, L, qh, ql, sn, any_n);
+    return cudaGetLastError();
+}
+
+cudaError_t bc_launch_index_build(const IndexParams& ip, uint32_t n_combos, uint32_t* d_dir, uint64_t dir_slots,
+                                  uint32_t* d_cursor, uint32_t* d_scan_tmp, uint2* ent_hl, uint32_t* ent_id,
+                                  int sm_count, cudaStream_t st) {
+    cudaError_t err = cudaMemsetAsync(d_dir, 0, dir_slots * sizeof(uint32_t), st);
+    if (err != cudaSuccess) return err;
+    if (ip.n_entries == 0) return cudaSuccess;
+    uint32_t gx = (ip.n_entries + 255) / 256;
+    uint32_t maxb = (uint32_t)sm_count * 8u;
+    if (gx > maxb) gx = maxb;
+    dim3 grid(gx, n_combos);
+    k_index_count<<<grid, 256, 0, st>>>(ip, d_dir);
+    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    if ((err = bc_exclusive_scan(d_dir, dir_slots, d_scan_tmp, st)) != cudaSuccess) return err;
+    err = cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+    if (err != cudaSuccess) return err;
+    k_index_scatter<<<grid, 256, 0, st>>>(ip, d_cursor, ent_hl, ent_id);
+    return cudaGetLastError();
+}

@@ -1,0 +1,148 @@
+/*
+ * barcoder_b200.h - C ABI of the B200-native spacer->genome mismatch search.
+ *
+ * This is the drop-in boundary for ONE path of ryandward/barcoder: the
+ * `bowtie -v k -a` call plus the PAM-adjacency check.  Each entry point cites the
+ * reference interface (file:line under the reference checkout) it replaces.
+ * Plain C: opaque context, raw pointers, sizes, integer return codes.  No torch,
+ * no C++ types.  INTEGRATION.md shows the ctypes stub a reference maintainer adds.
+ *
+ * All functions return BC_OK (0) or a negative BC_E* code; bc_last_error() gives the
+ * text.  There is no CPU fallback: without a usable CUDA device bc_create fails.
+ * A context is bound to one GPU and must be used from one host thread at a time.
+ */
+#ifndef BARCODER_B200_H
+#define BARCODER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BC_ABI_VERSION 1
+
+#define BC_OK 0
+#define BC_EINVAL (-1)   /* bad argument / call order            */
+#define BC_ECUDA (-2)    /* CUDA runtime error                   */
+#define BC_ENODEV (-3)   /* no usable CUDA device                */
+#define BC_ENOMEM (-4)   /* host or device allocation failed     */
+#define BC_ELIMIT (-5)   /* size outside the supported envelope  */
+
+typedef struct bc_ctx bc_ctx;
+
+/*
+ * One alignment.  Replaces one SAM line as consumed by PySamParser.py:26-48
+ * (Chromosome/Start/End/Strand/Barcode/Mismatches) and one parse_sam_output row
+ * (targets.py:354-410: spacer, target, mismatches, chr, tar_start, sp_dir, pam, diff).
+ */
+typedef struct {
+    uint32_t spacer_id; /* index into the array given to bc_set_library            */
+    uint32_t gpos;      /* 0-based leftmost '+'-strand position in the genome given to
+                           bc_set_genome (contigs concatenated, no separators); the
+                           contig is the last one whose offset is <= gpos           */
+    uint32_t mm_mask;   /* bit i = mismatch at spacer position i (0-based, spacer
+                           5'->3' orientation; targets.py:184-190); popcount == NM   */
+    uint32_t meta;      /* BC_META_* below                                          */
+} bc_hit;
+
+#define BC_META_STRAND(m) ((m) & 1u)             /* 0 '+', 1 '-' (SAM flag 16)           */
+#define BC_META_NMM(m) (((m) >> 1) & 3u)         /* mismatches, 0..3 (bowtie -v limit)   */
+#define BC_META_PAM_OK (1u << 3)                 /* PAM full, unambiguous and matching   */
+#define BC_META_PAM_FULL (1u << 4)               /* all PAM bases lie inside the contig  */
+#define BC_META_PAM_AMB (1u << 5)                /* a PAM base is non-ACGT in the genome */
+#define BC_META_PAM_LEN(m) (((m) >> 8) & 15u)    /* PAM length P (0..8)                  */
+#define BC_META_PAM_CODE(m, i) (((m) >> (16 + 2 * (i))) & 3u) /* base i of the PAM in
+                                                    spacer orientation: A0 C1 G2 T3      */
+
+/* bc_set_pam flags */
+#define BC_PAM_IUPAC 1u /* expand IUPAC letters (R,Y,...) in the pattern.  Without it only
+                           N is a wildcard and other letters are literals, exactly like
+                           PAMProcessor.py:7 and targets.py:224.                        */
+#define BC_PAM_GATE 2u  /* report only hits whose PAM matches (plus ambiguous-PAM hits,
+                           which the host resolves).  Off = bowtie's full hit set.      */
+
+/* bc_set_param keys */
+#define BC_PARAM_BLOCKS 1     /* pigeonhole blocks b (k+1 <= b <= k+4); 0 = choose        */
+#define BC_PARAM_PATH 2       /* 0 auto, 1 probe kernel, 2 bucket-join kernel             */
+#define BC_PARAM_COUNT_CANDIDATES 3 /* 1 = count verified candidates into bc_stats        */
+#define BC_PARAM_HIT_CAPACITY 4     /* initial hit-buffer capacity (records)              */
+
+typedef struct {
+    uint64_t genome_bases;    /* G                                                   */
+    uint64_t library_spacers; /* n                                                   */
+    uint32_t spacer_len;      /* L                                                   */
+    uint32_t k;
+    uint32_t blocks;          /* b actually used                                     */
+    uint32_t combos;          /* C(b, k) seed combinations                           */
+    uint32_t path;            /* 1 probe, 2 join                                     */
+    uint32_t scan_launches;   /* kernels launched by the last bc_search              */
+    uint64_t hits;            /* records produced by the last bc_search              */
+    uint64_t candidates;      /* verified (window, entry) pairs, if counting enabled */
+    uint64_t probes;          /* directory look-ups, if counting enabled             */
+    float ms_pack_genome;     /* device time of the last bc_set_genome               */
+    float ms_pack_library;    /* device time of the last bc_set_library              */
+    float ms_build_index;     /* device time of the last bc_build_index              */
+    float ms_search;          /* device time of the last bc_search (all its kernels) */
+    float ms_scan_kernel;     /* device time of the dominant scan kernel(s) only     */
+    uint32_t reserved[8];
+} bc_stats;
+
+int bc_abi_version(void);
+
+/* Replaces `BowtieRunner()` / `__enter__` (BowtieRunner.py:14-20,49-50).  `device` is the
+ * CUDA ordinal; the context owns a stream and all device memory it allocates. */
+int bc_create(bc_ctx** out, int device);
+
+/* Replaces `__exit__` -> temp_dir.cleanup() (BowtieRunner.py:52-53). */
+void bc_destroy(bc_ctx* ctx);
+
+/* Replaces make_fasta + bowtie-build (BowtieRunner.py:55-62,78-102): packs the genome
+ * into 1-bit planes (hi, lo, ambiguity) resident in HBM.  `ascii` = all contigs
+ * concatenated (any case; non-ACGT = ambiguous), `contig_offsets[n_contigs+1]` = start
+ * of each contig and the total length.  The caller may free its buffers on return.
+ * The _dev variant takes a device pointer for `ascii` (offsets stay on the host) and
+ * enqueues on `stream` (a cudaStream_t, or NULL for the context's stream). */
+int bc_set_genome(bc_ctx* ctx, const uint8_t* ascii, const uint64_t* contig_offsets, uint32_t n_contigs);
+int bc_set_genome_dev(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* contig_offsets,
+                      uint32_t n_contigs, void* stream);
+
+/* Replaces make_fastq (BowtieRunner.py:64-76): `ascii_spacers` = n spacers of L
+ * characters each, back to back (1 <= L <= 32).  Non-ACGT characters mismatch
+ * everything.  spacer_id in the results = index into this array. */
+int bc_set_library(bc_ctx* ctx, const uint8_t* ascii_spacers, uint32_t n, uint32_t L);
+int bc_set_library_dev(bc_ctx* ctx, const uint8_t* d_ascii_spacers, uint32_t n, uint32_t L, void* stream);
+
+/* Replaces PAMFinder(records, pam, direction) (PAMProcessor.py:60-63) and the PAM
+ * arguments of targets.py (:864-878).  `pam` up to 8 letters, "" = no PAM.
+ * direction 0 = downstream (3' of the protospacer), 1 = upstream (5'). */
+int bc_set_pam(bc_ctx* ctx, const char* pam, int direction, uint32_t flags);
+
+int bc_set_param(bc_ctx* ctx, int key, int64_t value);
+
+/* Replaces create_index (BowtieRunner.py:78-102) for the library side: builds the
+ * pigeonhole seed index for <= k mismatches on device (0 <= k <= 3). */
+int bc_build_index(bc_ctx* ctx, int k);
+
+/* Replaces align (BowtieRunner.py:104-141): every ungapped end-to-end alignment of every
+ * spacer to both strands with <= k mismatches, PAM annotated in the same pass.  Results
+ * stay on the device until copied.  Builds the index first if bc_build_index(k) was
+ * not called. */
+int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out);
+
+/* Replaces reading the SAM file (PySamParser.py:16-19).  Order is unspecified. */
+int bc_copy_hits(bc_ctx* ctx, bc_hit* dst, uint64_t cap);
+
+/* Device-side view of the result buffer (valid until the next bc_search/bc_destroy),
+ * for callers that gather across GPUs without a host round trip. */
+int bc_hits_device(bc_ctx* ctx, const bc_hit** d_hits, uint64_t* n_hits);
+
+int bc_get_stats(bc_ctx* ctx, bc_stats* out);
+
+/* Replaces BowtieError.message (BowtieRunner.py:144-150). */
+const char* bc_last_error(bc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BARCODER_B200_H */

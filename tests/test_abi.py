@@ -1,0 +1,45 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every
+symbol include/barcoder_b200.h declares.  No compute calls (there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from barcoder_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "barcoder_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bc_[a-z_]+)\s*\(", text)))
+
+
+def test_header_and_loader_agree():
+    assert _declared() == sorted(_native.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_native.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert _native.load().bc_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.NativeError) as ei:
+        _native.Searcher(0)
+    assert ei.value.code in (-2, -3)
+
+
+def test_stats_struct_size_matches_header():
+    # 2*u64 + 6*u32 + 3*u64 + 5*f32 + 8*u32 with natural alignment
+    assert ctypes.sizeof(_native.BcStats) == 16 + 24 + 24 + 20 + 32 + 4

@@ -1,0 +1,162 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bit-exact: the canonical-sorted 16-byte hit records must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from barcoder_b200 import _native, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(genome, off, lib, k, pam="", direction="downstream", iupac=False, gate=False, blocks=0, path=0,
+            hit_cap=0):
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam(pam, direction, iupac=iupac, gate=gate)
+        if blocks:
+            s.set_param(_native.BC_PARAM_BLOCKS, blocks)
+        if path:
+            s.set_param(_native.BC_PARAM_PATH, path)
+        if hit_cap:
+            s.set_param(_native.BC_PARAM_HIT_CAPACITY, hit_cap)
+        n = s.search(k)
+        hits = s.hits()
+        assert len(hits) == n
+        return _native.canonical_sort(hits), s.stats()
+
+
+def run_oracle(genome, off, lib, k, pam="", direction="downstream", iupac=False, gate=False, mode="seeded"):
+    contigs = [bytes(genome[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+    spacers = synth.rows_to_strings(lib)
+    flags = (oracle.PAM_FLAG_IUPAC if iupac else 0) | (oracle.PAM_FLAG_GATE if gate else 0)
+    return oracle.search(contigs, spacers, k, pam=pam, direction=direction, flags=flags, mode=mode)
+
+
+def assert_same(gpu, ref):
+    assert len(gpu) == len(ref), (len(gpu), len(ref))
+    assert gpu.tobytes() == ref.tobytes()
+
+
+def small_case(L, k, seed, n=300, G=60000, n_contigs=4, nfrac=0.01):
+    genome, off = synth.random_genome(G, seed=seed, n_contigs=n_contigs, n_fraction=nfrac, n_run=9)
+    lib = synth.random_library(n, L, seed=seed + 1)
+    synth.plant(lib, genome, 0.5, k, seed=seed + 2)
+    lib[1, L // 3] = ord("N")
+    lib[2, :] = ord("N")
+    lib[5, 0] = ord("a") + (lib[5, 0] - ord("A")) if lib[5, 0] < 97 else lib[5, 0]  # lower-case base
+    return genome, off, lib
+
+
+@pytest.mark.parametrize("L", [1, 2, 5, 12, 19, 20, 21, 31, 32])
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_probe_matches_oracle_all_lengths(L, k):
+    genome, off, lib = small_case(L, k, seed=100 * L + k, n=120, G=20000)
+    ref = run_oracle(genome, off, lib, k, pam="NGG", mode="brute" if L < 4 else "seeded")
+    gpu, st = run_gpu(genome, off, lib, k, pam="NGG", path=1)
+    assert_same(gpu, ref)
+    if L > k:
+        assert st["path"] == 1 and st["scan_launches"] >= 1
+
+
+@pytest.mark.parametrize("k,blocks", [(0, 1), (0, 2), (0, 4), (1, 2), (1, 3), (1, 5), (2, 3), (2, 4), (2, 6),
+                                      (3, 4), (3, 5), (3, 6), (3, 7)])
+@pytest.mark.parametrize("L", [20, 32])
+def test_probe_every_seed_scheme(k, blocks, L):
+    genome, off, lib = small_case(L, k, seed=7 * blocks + k + L)
+    ref = run_oracle(genome, off, lib, k, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, k, pam="NGG", blocks=blocks, path=1)
+    assert st["blocks"] == blocks
+    assert_same(gpu, ref)
+
+
+@pytest.mark.parametrize("direction", ["downstream", "upstream"])
+@pytest.mark.parametrize("pam,iupac", [("NGG", False), ("NGNC", False), ("NNGRRT", True), ("NNGRRT", False),
+                                       ("TTTV", True), ("", False), ("NNNNNNNN", False)])
+def test_pam_modes(direction, pam, iupac):
+    genome, off, lib = small_case(20, 2, seed=len(pam) + 31, n=400, G=40000, nfrac=0.03)
+    for gate in (False, True):
+        ref = run_oracle(genome, off, lib, 2, pam=pam, direction=direction, iupac=iupac, gate=gate)
+        gpu, _ = run_gpu(genome, off, lib, 2, pam=pam, direction=direction, iupac=iupac, gate=gate, path=1)
+        assert_same(gpu, ref)
+
+
+def test_golden_g2_through_abi(plasmids, cn32_spacers, golden_dir):
+    """SURVEY.md 8c G2 through the CUDA path: 869 hits, identical records to the oracle, and the
+    committed canonical tuple list."""
+    ids = list(plasmids)
+    contigs = [str(plasmids[i].seq).encode() for i in ids]
+    genome = np.frombuffer(b"".join(contigs), dtype=np.uint8)
+    off = np.zeros(len(contigs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(c) for c in contigs])
+    lib = np.frombuffer("".join(cn32_spacers).encode(), dtype=np.uint8).reshape(-1, 32)
+    ref = run_oracle(genome, off, lib, 2, pam="NGNC")
+    gpu, _ = run_gpu(genome, off, lib, 2, pam="NGNC")
+    assert len(gpu) == 869
+    assert_same(gpu, ref)
+    tup = []
+    for h in gpu:
+        ci = int((off[1:] <= h["gpos"]).sum())
+        meta = int(h["meta"])
+        pam = "".join("ACGT"[(meta >> (16 + 2 * i)) & 3] for i in range(4)) if meta & 16 else ""
+        tup.append((cn32_spacers[h["spacer_id"]], ids[ci], int(h["gpos"] - off[ci]), "-" if meta & 1 else "+",
+                    (meta >> 1) & 3, pam))
+    text = "\n".join("\t".join(str(x) for x in t) for t in sorted(tup))
+    with open(os.path.join(golden_dir, "g2_known_answer.tsv")) as h:
+        assert h.read().rstrip("\n") == text
+
+
+def test_edge_cases():
+    # empty library, genome shorter than L, contig shorter than L, all-N contig, empty contig
+    genome = np.frombuffer(b"ACGTACGTAC" + b"NNNNNNNNNNNNNNNNNNNNNNNNN" + b"ACG" + b"ACGTTGCAACGTTGCAACGTAAGG", dtype=np.uint8)
+    off = np.array([0, 10, 35, 35, 38, 62], dtype=np.uint64)
+    lib = np.frombuffer(b"ACGTTGCAACGTTGCAACGT" + b"ACGTACGTACACGTACGTAC", dtype=np.uint8).reshape(2, 20)
+    ref = run_oracle(genome, off, lib, 1, pam="NGG", mode="brute")
+    gpu, _ = run_gpu(genome, off, lib, 1, pam="NGG")
+    assert len(ref) >= 1
+    assert_same(gpu, ref)
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(np.zeros((0, 20), dtype=np.uint8))
+        assert s.search(2) == 0
+        s.set_library(lib)
+        assert s.search(0) == len(run_oracle(genome, off, lib, 0))
+        with pytest.raises(_native.NativeError):
+            s.search(4)
+        with pytest.raises(_native.NativeError):
+            s.set_library(np.zeros((1, 33), dtype=np.uint8))
+    with _native.Searcher(0) as s:
+        with pytest.raises(_native.NativeError):
+            s.search(1)  # nothing loaded
+
+
+def test_hit_buffer_overflow_retries():
+    genome, off = synth.random_genome(200000, seed=3)
+    lib = synth.random_library(2000, 12, seed=4)
+    ref = run_oracle(genome, off, lib, 2)
+    assert len(ref) > 5000
+    gpu, st = run_gpu(genome, off, lib, 2, hit_cap=1000)
+    assert st["scan_launches"] == 2
+    assert_same(gpu, ref)
+
+
+def test_palindrome_reported_on_both_strands():
+    genome = np.frombuffer(b"TTTTACGTACGTACGTACGTAAAAGG", dtype=np.uint8)
+    off = np.array([0, len(genome)], dtype=np.uint64)
+    lib = np.frombuffer(b"ACGTACGTACGTACGT", dtype=np.uint8).reshape(1, 16)
+    gpu, _ = run_gpu(genome, off, lib, 0)
+    assert_same(gpu, run_oracle(genome, off, lib, 0, mode="brute"))
+    assert sorted((int(h["gpos"]), int(h["meta"] & 1)) for h in gpu) == [(4, 0), (4, 1), (8, 0), (8, 1)]
+
+
+def test_medium_random_many_contigs():
+    genome, off = synth.random_genome(3_000_000, seed=11, n_contigs=40, n_fraction=0.002)
+    lib = synth.random_library(20000, 20, seed=12)
+    synth.plant(lib, genome, 0.3, 3, seed=13)
+    ref = run_oracle(genome, off, lib, 3, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, 3, pam="NGG")
+    assert_same(gpu, ref)
+    assert len(gpu) > 6000
