@@ -468,6 +468,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->dir = ctx->d_dir;
     p->ent_hl = ctx->d_ent_hl;
     p->ent_id = ctx->d_ent_id;
+    p->dir_entries = 2ull * ctx->n * ctx->n_combos;
     p->P = ctx->P;
     p->pam_dir = ctx->pam_dir;
     p->pam_flags = ctx->pam_flags;
@@ -512,7 +513,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         uint32_t launches = 0;
         if (ctx->stats.path == 2) {
-            CK(bc_join_search(ctx->join, p, ctx->sm_count, ctx->stream, ctx->ev2, ctx->ev3, &launches));
+            CK(bc_join_search(ctx->join, p, ctx->dir_slots, ctx->sm_count, ctx->stream, &launches));
         } else {
             CK(cudaEventRecord(ctx->ev2, ctx->stream));
             CK(bc_launch_scan_probe(p, ctx->sm_count, ctx->stream));

@@ -6,14 +6,14 @@
 struct JoinWorkspace {
     uint32_t* d_gdir = nullptr;     // genome-side directory (same key space as the library's)
     uint32_t* d_gcursor = nullptr;
-    uint32_t* d_gpos = nullptr;     // window positions in key order
+    uint4* d_gwin = nullptr;        // {dev position, wh, wl, 0} window records in key order
     uint32_t* d_scan_tmp = nullptr;
-    uint32_t* d_work = nullptr;     // work-queue counter
-    uint64_t gdir_cap = 0, gpos_cap = 0, scan_tmp_cap = 0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    uint64_t gdir_cap = 0, gwin_cap = 0, scan_tmp_cap = 0;
     float ms_join_kernels = 0;      // device time of the verify kernels of the last search
 };
 
 bool bc_join_supported(const ComboDesc* combo, uint32_t n_combos);
-cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, int sm_count, cudaStream_t st,
-                           cudaEvent_t ev_a, cudaEvent_t ev_b, uint32_t* launches);
+cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, int sm_count,
+                           cudaStream_t st, uint32_t* launches);
 void bc_join_free(JoinWorkspace& ws);

@@ -149,7 +149,7 @@ def test_palindrome_reported_on_both_strands():
     lib = np.frombuffer(b"ACGTACGTACGTACGT", dtype=np.uint8).reshape(1, 16)
     gpu, _ = run_gpu(genome, off, lib, 0)
     assert_same(gpu, run_oracle(genome, off, lib, 0, mode="brute"))
-    assert sorted((int(h["gpos"]), int(h["meta"] & 1)) for h in gpu) == [(4, 0), (4, 1), (8, 0), (8, 1)]
+    assert sorted((int(h["gpos"]), int(h["meta"] & 1)) for h in gpu) == [(4, 0), (4, 1)]
 
 
 def test_medium_random_many_contigs():
@@ -160,3 +160,49 @@ def test_medium_random_many_contigs():
     gpu, st = run_gpu(genome, off, lib, 3, pam="NGG")
     assert_same(gpu, ref)
     assert len(gpu) > 6000
+
+
+# ------------------------------------------------------------------ bucket-join path (K3-join)
+@pytest.mark.parametrize("k,blocks", [(0, 1), (0, 3), (1, 2), (1, 4), (2, 3), (2, 5), (3, 4), (3, 5), (3, 6), (3, 7)])
+@pytest.mark.parametrize("L", [20, 32])
+def test_join_every_seed_scheme(k, blocks, L):
+    genome, off, lib = small_case(L, k, seed=11 * blocks + k + L)
+    ref = run_oracle(genome, off, lib, k, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, k, pam="NGG", blocks=blocks, path=2)
+    assert st["blocks"] == blocks and st["path"] == 2
+    assert_same(gpu, ref)
+
+
+@pytest.mark.parametrize("L", [1, 3, 8, 17, 20, 32])
+@pytest.mark.parametrize("k", [0, 1, 3])
+def test_join_matches_oracle_lengths(L, k):
+    genome, off, lib = small_case(L, k, seed=200 * L + k, n=120, G=20000)
+    ref = run_oracle(genome, off, lib, k, pam="NGNC", mode="brute" if L < 4 else "seeded")
+    gpu, _ = run_gpu(genome, off, lib, k, pam="NGNC", path=2)
+    assert_same(gpu, ref)
+
+
+def test_join_dense_buckets_exceed_shared_tile():
+    """Library buckets larger than the shared-memory tile (1024 entries) and duplicate spacers."""
+    genome, off = synth.random_genome(3000, seed=21, n_contigs=2, n_fraction=0.01, n_run=5)
+    lib = synth.random_library(50000, 6, seed=22, distinct=False)
+    ref = run_oracle(genome, off, lib, 1, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=2)
+    assert len(ref) > 500000
+    assert_same(gpu, ref)
+    gpu2, _ = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=1)
+    assert_same(gpu2, ref)
+
+
+def test_join_medium_both_paths_agree():
+    genome, off = synth.random_genome(2_000_000, seed=31, n_contigs=7, n_fraction=0.002)
+    lib = synth.random_library(100000, 20, seed=32)
+    synth.plant(lib, genome, 0.2, 3, seed=33)
+    ref = run_oracle(genome, off, lib, 3, pam="NGG")
+    for path in (1, 2):
+        gpu, st = run_gpu(genome, off, lib, 3, pam="NGG", path=path)
+        assert st["path"] == path
+        assert_same(gpu, ref)
+    gate_ref = run_oracle(genome, off, lib, 3, pam="NGG", gate=True)
+    gpu, _ = run_gpu(genome, off, lib, 3, pam="NGG", gate=True, path=2)
+    assert_same(gpu, gate_ref)
