@@ -21,6 +21,7 @@ BC_PARAM_BLOCKS = 1
 BC_PARAM_PATH = 2
 BC_PARAM_COUNT_CANDIDATES = 3
 BC_PARAM_HIT_CAPACITY = 4
+BC_PARAM_SPACER_ID_BASE = 5
 PATH_AUTO, PATH_PROBE, PATH_JOIN = 0, 1, 2
 
 META_PAM_OK = 1 << 3
@@ -48,7 +49,8 @@ class BcStats(ctypes.Structure):
         ("hits", ctypes.c_uint64), ("candidates", ctypes.c_uint64), ("probes", ctypes.c_uint64),
         ("ms_pack_genome", ctypes.c_float), ("ms_pack_library", ctypes.c_float),
         ("ms_build_index", ctypes.c_float), ("ms_search", ctypes.c_float),
-        ("ms_scan_kernel", ctypes.c_float), ("reserved", ctypes.c_uint32 * 8),
+        ("ms_scan_kernel", ctypes.c_float), ("ms_genome_bucket", ctypes.c_float),
+        ("index_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 6),
     ]
 
     def as_dict(self):

@@ -36,7 +36,7 @@ struct bc_ctx {
     uint32_t P = 0, pam_dir = 0, pam_flags = 0, pam_sets[8] = {0};
 
     // params
-    int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0;
+    int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
 
     // index
     bool have_index = false;
@@ -282,6 +282,7 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
             ctx->par_path = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_COUNT_CANDIDATES: ctx->par_count = value; return BC_OK;
         case BC_PARAM_HIT_CAPACITY: ctx->par_hit_cap = value; return BC_OK;
+        case BC_PARAM_SPACER_ID_BASE: ctx->par_id_base = value; return BC_OK;
         default: return fail(ctx, BC_EINVAL, "unknown parameter");
     }
 }
@@ -440,12 +441,14 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     ip.L = ctx->L;
     ip.lib_has_n = ctx->lib_has_n;
     memcpy(ip.combo, ctx->combo, sizeof ip.combo);
+    const uint32_t launches0 = bc_launch_counter;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_hl,
                              ctx->d_ent_id, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev0, ctx->ev1));
+    ctx->stats.index_launches = bc_launch_counter - launches0;
     ctx->have_index = true;
     return BC_OK;
 }
@@ -477,6 +480,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->count = ctx->d_count;
     p->cap = ctx->hit_cap;
     p->count_candidates = ctx->par_count ? 1u : 0u;
+    p->spacer_id_base = (uint32_t)ctx->par_id_base;
 }
 
 extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
@@ -490,7 +494,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
     CK(cudaSetDevice(ctx->device));
     ctx->n_hits = 0;
     ctx->stats.hits = ctx->stats.candidates = ctx->stats.probes = 0;
-    ctx->stats.ms_search = ctx->stats.ms_scan_kernel = 0;
+    ctx->stats.ms_search = ctx->stats.ms_scan_kernel = ctx->stats.ms_genome_bucket = 0;
     ctx->stats.scan_launches = 0;
     if (ctx->n_combos == 0 || ctx->G < ctx->L) return BC_OK;
 
@@ -505,7 +509,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         CK(cudaMalloc(&ctx->d_hits, want * sizeof(bc_hit)));
         ctx->hit_cap = want;
     }
-    float ms_total = 0, ms_scan = 0;
+    float ms_total = 0, ms_scan = 0, ms_bucket = 0;
     for (int attempt = 0; attempt < 3; attempt++) {
         SearchParams p;
         fill_params(ctx, &p);
@@ -526,7 +530,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         CK(cudaStreamSynchronize(ctx->stream));
         float a = 0, b2 = 0;
         CK(cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1));
-        if (ctx->stats.path == 2) b2 = ctx->join.ms_join_kernels;
+        if (ctx->stats.path == 2) { b2 = ctx->join.ms_join_kernels; ms_bucket += ctx->join.ms_bucket_kernels; }
         else CK(cudaEventElapsedTime(&b2, ctx->ev2, ctx->ev3));
         ms_total += a;
         ms_scan += b2;
@@ -548,6 +552,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
     ctx->stats.hits = ctx->n_hits;
     ctx->stats.ms_search = ms_total;
     ctx->stats.ms_scan_kernel = ms_scan;
+    ctx->stats.ms_genome_bucket = ms_bucket;
     if (n_hits_out) *n_hits_out = ctx->n_hits;
     return BC_OK;
 }

@@ -59,6 +59,7 @@ struct SearchParams {
     unsigned long long* count;  // [0] hits, [1] candidates, [2] probes
     unsigned long long cap;
     uint32_t count_candidates;
+    uint32_t spacer_id_base;
 };
 
 __device__ __forceinline__ uint32_t bc_lmask(uint32_t n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
@@ -134,7 +135,7 @@ static __device__ __noinline__ void bc_emit_hit(const SearchParams& p, uint32_t 
     unsigned long long slot = atomicAdd(p.count, 1ull);
     if (slot < p.cap) {
         bc_hit h;
-        h.spacer_id = sid;
+        h.spacer_id = sid + p.spacer_id_base;
         h.gpos = pos - lo;
         h.mm_mask = strand ? bc_rev_bits(m, L) : m;
         h.meta = meta;

@@ -8,6 +8,7 @@
 // registers, and one pair costs two LOP3, one POPC and a predicated compare.  Algorithmic HBM
 // traffic is one write + one read of 16 B per (window, combination) plus the index, read once.
 #include "bc_join.h"
+#include "bc_kernels.h"
 
 #define JOIN_THREADS 256
 #define JOIN_WARPS (JOIN_THREADS / 32)
@@ -109,8 +110,6 @@ __global__ void __launch_bounds__(JOIN_THREADS) k_join_verify(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------ host
-cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cudaStream_t st);
-size_t bc_scan_tmp_words(uint64_t n);
 
 bool bc_join_supported(const ComboDesc*, uint32_t n_combos) { return n_combos > 0; }
 
@@ -121,6 +120,7 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
+    if (ws.ev_c) cudaEventDestroy(ws.ev_c);
     ws = JoinWorkspace();
 }
 
@@ -132,10 +132,11 @@ void bc_join_free(JoinWorkspace& ws) {
 
 cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, int sm_count,
                            cudaStream_t st, uint32_t* launches) {
-    *launches = 0;
-    ws.ms_join_kernels = 0;
+    const uint32_t launches0 = bc_launch_counter;
+    ws.ms_join_kernels = ws.ms_bucket_kernels = 0;
     if (!ws.ev_a) JCK(cudaEventCreate(&ws.ev_a));
     if (!ws.ev_b) JCK(cudaEventCreate(&ws.ev_b));
+    if (!ws.ev_c) JCK(cudaEventCreate(&ws.ev_c));
     const uint32_t n_slots = (uint32_t)(dir_slots - 1);
     // chunk the genome so the bucketed window records stay within the workspace budget
     const uint64_t budget_records = (24ull << 30) / sizeof(uint4);
@@ -187,6 +188,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         if (gx > maxb) gx = maxb;
         dim3 grid(gx, p.n_combos);
         JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
+        JCK(cudaEventRecord(ws.ev_c, st));
         k_genome_bucket<0><<<grid, 256, 0, st>>>(gp, ws.d_gdir, nullptr);
         JCK(cudaGetLastError());
         JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
@@ -199,14 +201,15 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         k_join_verify<<<vgrid, JOIN_THREADS, 0, st>>>(p, ws.d_gdir, ws.d_gwin, n_slots);
         JCK(cudaGetLastError());
         JCK(cudaEventRecord(ws.ev_b, st));
-        *launches += 3;
-        if (begin + chunk < p.n_pos || true) {
-            // events are reused per chunk, so read them before the next record
-            JCK(cudaEventSynchronize(ws.ev_b));
-            float ms = 0;
-            JCK(cudaEventElapsedTime(&ms, ws.ev_a, ws.ev_b));
-            ws.ms_join_kernels += ms;
-        }
+        bc_launch_counter += 3;
+        // events are reused per chunk, so read them before the next record
+        JCK(cudaEventSynchronize(ws.ev_b));
+        float ms = 0;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_a, ws.ev_b));
+        ws.ms_join_kernels += ms;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_c, ws.ev_a));
+        ws.ms_bucket_kernels += ms;
     }
+    *launches = bc_launch_counter - launches0;
     return cudaSuccess;
 }

@@ -8,9 +8,10 @@ struct JoinWorkspace {
     uint32_t* d_gcursor = nullptr;
     uint4* d_gwin = nullptr;        // {dev position, wh, wl, 0} window records in key order
     uint32_t* d_scan_tmp = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     uint64_t gdir_cap = 0, gwin_cap = 0, scan_tmp_cap = 0;
     float ms_join_kernels = 0;      // device time of the verify kernels of the last search
+    float ms_bucket_kernels = 0;    // device time of the genome bucketing kernels (count, scan, scatter)
 };
 
 bool bc_join_supported(const ComboDesc* combo, uint32_t n_combos);

@@ -2,6 +2,8 @@
 // and the probe scan (K3-probe).  The bucket-join scan lives in bc_join.cu.
 #include "bc_kernels.h"
 
+thread_local uint32_t bc_launch_counter = 0;
+
 // ------------------------------------------------------------------------------------------ K1
 // ASCII genome -> three bit planes.  One warp produces 32 consecutive plane words: in step i
 // the 32 lanes read the 32 bases of word i (one coalesced 32-byte request), three ballots turn
@@ -191,12 +193,14 @@ cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cud
     uint64_t blocks = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (blocks == 1) {
         k_scan_apply<<<1, SCAN_THREADS, 0, st>>>(d_data, n, nullptr);
+        bc_launch_counter += 1;
         return cudaGetLastError();
     }
     k_scan_reduce<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(d_data, n, d_tmp);
     cudaError_t err = bc_exclusive_scan(d_tmp, blocks, d_tmp + blocks, st);
     if (err != cudaSuccess) return err;
     k_scan_apply<<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(d_data, n, d_tmp);
+    bc_launch_counter += 2;
     return cudaGetLastError();
 }
 
@@ -257,6 +261,7 @@ cudaError_t bc_launch_scan_probe(const SearchParams& p, int sm_count, cudaStream
     uint32_t grid = (uint32_t)sm_count * 8u;
     if (grid > n_tiles) grid = n_tiles;
     k_scan_probe<<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
+    bc_launch_counter += 1;
     return cudaGetLastError();
 }
 
@@ -269,6 +274,7 @@ cudaError_t bc_launch_pack_genome(const uint8_t* d_ascii, const uint64_t* d_coff
     if (blocks > maxb) blocks = maxb;
     if (blocks == 0) blocks = 1;
     k_pack_genome<<<blocks, 256, 0, st>>>(d_ascii, d_coff, d_start_dev, n_contigs, n_pos, n_words, H, Lo, B);
+    bc_launch_counter += 1;
     return cudaGetLastError();
 }
 
@@ -276,6 +282,7 @@ cudaError_t bc_launch_pack_library(const uint8_t* d_ascii, uint32_t n, uint32_t 
                                    uint32_t* sn, uint32_t* any_n, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     k_pack_library<<<(n + 255) / 256, 256, 0, st>>>(d_ascii, n, L, qh, ql, sn, any_n);
+    bc_launch_counter += 1;
     return cudaGetLastError();
 }
 
@@ -295,5 +302,6 @@ cudaError_t bc_launch_index_build(const IndexParams& ip, uint32_t n_combos, uint
     err = cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
     if (err != cudaSuccess) return err;
     k_index_scatter<<<grid, 256, 0, st>>>(ip, d_cursor, ent_hl, ent_id);
+    bc_launch_counter += 2;
     return cudaGetLastError();
 }

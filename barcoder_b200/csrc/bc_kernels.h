@@ -12,6 +12,9 @@ struct IndexParams {
     ComboDesc combo[BC_MAX_COMBOS];
 };
 
+// Every launcher adds the kernels it launched here (bench.py reports gpu_launches from it).
+extern thread_local uint32_t bc_launch_counter;
+
 size_t bc_scan_tmp_words(uint64_t n);
 cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cudaStream_t st);
 

@@ -39,20 +39,35 @@ def random_genome(total_bp, seed, n_contigs=1, n_fraction=0.0, n_run=200):
     return seq, offsets
 
 
+def codes_to_rows(codes, L):
+    """uint64 base-4 codes (base j at bits 2j) -> uint8[n, L] ASCII."""
+    out = np.empty((len(codes), L), dtype=np.uint8)
+    for j in range(L):
+        out[:, j] = _ACGT[((codes >> np.uint64(2 * j)) & np.uint64(3)).astype(np.uint8)]
+    return out
+
+
 def random_library(n, L, seed, distinct=True):
-    """-> uint8[n, L] of uniform random spacers (distinct rows by default)."""
+    """-> uint8[n, L] of uniform random spacers (distinct rows by default).  Drawn as base-4
+    integers so that 10^7 rows dedupe with one integer sort."""
     rng = rng_for(seed)
-    lib = random_bases(n * L, rng).reshape(n, L)
+    hi = (1 << (2 * L)) - 1
+    if distinct and L <= 12 and n > hi + 1:
+        distinct = False  # more rows requested than distinct spacers exist
+    if distinct and n > 1 and L <= 12 and n > (hi + 1) // 4:
+        codes = rng.permutation(np.arange(hi + 1, dtype=np.uint64))[:n]
+        return np.ascontiguousarray(codes_to_rows(codes, L))
+    codes = rng.integers(0, hi, size=n, dtype=np.uint64, endpoint=True)
     if distinct and n > 1:
-        for _ in range(8):
-            view = np.ascontiguousarray(lib).view(np.dtype((np.void, L))).ravel()
-            _, first = np.unique(view, return_index=True)
-            if len(first) == n:
+        for _ in range(16):
+            codes = np.sort(codes)
+            codes = codes[np.concatenate([[True], codes[1:] != codes[:-1]])]
+            if len(codes) == n or len(codes) > hi:
                 break
-            dup = np.ones(n, dtype=bool)
-            dup[first] = False
-            lib[dup] = random_bases(int(dup.sum()) * L, rng).reshape(-1, L)
-    return lib
+            extra = rng.integers(0, hi, size=n - len(codes), dtype=np.uint64, endpoint=True)
+            codes = np.concatenate([codes, extra])
+        codes = rng.permutation(codes[:n])
+    return np.ascontiguousarray(codes_to_rows(codes, L))
 
 
 def revcomp_rows(rows):

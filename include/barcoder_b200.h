@@ -67,6 +67,7 @@ typedef struct {
 #define BC_PARAM_PATH 2       /* 0 auto, 1 probe kernel, 2 bucket-join kernel             */
 #define BC_PARAM_COUNT_CANDIDATES 3 /* 1 = count verified candidates into bc_stats        */
 #define BC_PARAM_HIT_CAPACITY 4     /* initial hit-buffer capacity (records)              */
+#define BC_PARAM_SPACER_ID_BASE 5   /* added to every spacer_id (global ids of a library shard) */
 
 typedef struct {
     uint64_t genome_bases;    /* G                                                   */
@@ -84,8 +85,10 @@ typedef struct {
     float ms_pack_library;    /* device time of the last bc_set_library              */
     float ms_build_index;     /* device time of the last bc_build_index              */
     float ms_search;          /* device time of the last bc_search (all its kernels) */
-    float ms_scan_kernel;     /* device time of the dominant scan kernel(s) only     */
-    uint32_t reserved[8];
+    float ms_scan_kernel;     /* device time of the verify kernel(s) only            */
+    float ms_genome_bucket;   /* join path: device time of the genome bucketing kernels */
+    uint32_t index_launches;  /* kernels launched by the last bc_build_index          */
+    uint32_t reserved[6];
 } bc_stats;
 
 int bc_abi_version(void);
