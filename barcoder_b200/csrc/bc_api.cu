@@ -358,16 +358,21 @@ static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_o
         if (ctx->par_blocks && (uint32_t)ctx->par_blocks != b) continue;
         Scheme s;
         if (!make_scheme(ctx->L, k, b, cap, E, &s)) continue;
-        // Relative cost model: a directory probe is an L2 round trip
-        // (~8 units), a verified candidate ~1 unit in the probe kernel; the join kernel has no
-        // per-window probes but sorts the windows once per combination (~6 units each) and
-        // verifies candidates from shared memory (~0.35 units).
-        double dir_cost = 6.0 * (double)s.dir_slots;
-        double probe_cost = windows * (8.0 * s.n_combos + 1.0 * s.cand_per_window) + dir_cost;
-        double join_cost = windows * (6.0 * s.n_combos + 0.35 * s.cand_per_window) + dir_cost + 4.0e6 * s.n_combos;
+        // Cost model in units of one verified candidate of the join kernel (~0.45 ps of chip time
+        // on B200; constants fitted to measurements):
+        //   probe path: a directory probe is a dependent pair of random sector reads (~25 units
+        //               while the directory is L2-resident, ~90 from HBM); candidates are 8-byte
+        //               uncoalesced reads (~8 units);
+        //   join path : partitioning costs ~85 units per (window, combination) (two atomics and a
+        //               16-byte scattered write), candidates cost 1, plus a fixed launch/scan floor.
+        const double dir_bytes = 4.0 * (double)s.dir_slots;
+        const double dir_cost = 12.0 * (double)s.dir_slots;
+        const double c_probe = dir_bytes < 64e6 ? 25.0 : 90.0;
+        double probe_cost = windows * (c_probe * s.n_combos + 8.0 * s.cand_per_window) + dir_cost;
+        double join_cost = windows * (85.0 * s.n_combos + 1.0 * s.cand_per_window) + dir_cost + 4.0e8;
         for (uint32_t path = 1; path <= 2; path++) {
             if (ctx->par_path && (uint32_t)ctx->par_path != path) continue;
-            if (path == 2 && !bc_join_supported(s.combo, s.n_combos)) continue;
+            if (path == 2 && !bc_join_supported(s.combo, s.n_combos, E)) continue;
             double cost = path == 1 ? probe_cost : join_cost;
             if (!found || cost < best_cost) {
                 found = true;
