@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(PJ_THREADS) k_part_join(const __grid_constant_
     uint32_t* s_fdir = reinterpret_cast<uint32_t*>(s_lib + PJ_LIB_CAP);    // PJ_MAX_FINE + 1
     uint32_t* s_cnt = s_fdir + PJ_MAX_FINE + 1;                            // PJ_MAX_FINE
     uint32_t* s_warp = s_cnt + PJ_MAX_FINE;                                // PJ_THREADS / 32
+    __shared__ HitStage stage;
+    if (threadIdx.x == 0) stage.n = 0;
     const uint32_t tid = threadIdx.x;
     const int k = (int)p.k;
     unsigned long long cand = 0;
@@ -165,15 +167,39 @@ __global__ void __launch_bounds__(PJ_THREADS) k_part_join(const __grid_constant_
                 for (uint32_t i = tid; i < nw; i += PJ_THREADS) {
                     const uint4 w = s_win[i];
                     const uint32_t a = max(s_fdir[w.w], lt), bnd = min(s_fdir[w.w + 1], lt + tile_n);
-                    if (a < bnd) cand += bnd - a;
-#pragma unroll 4
-                    for (uint32_t e = a; e < bnd; e++) {
-                        const uint2 q = s_lib[e - lt];
+                    if (a >= bnd) continue;
+                    cand += bnd - a;
+                    const uint2* lib = s_lib + (a - lt);
+                    const uint32_t n_e = bnd - a;
+                    uint32_t e = 0;
+                    // branch-free batches of 4: the popcounts are min-reduced and only a batch
+                    // that contains a hit is re-examined entry by entry
+                    for (; e + 4 <= n_e; e += 4) {
+                        const uint2 q0 = lib[e], q1 = lib[e + 1], q2 = lib[e + 2], q3 = lib[e + 3];
+                        const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
+                        const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
+                        const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
+                        const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
+                        if (min(min(c0, c1), min(c2, c3)) <= k) {
+                            for (uint32_t j = e; j < e + 4; j++) {
+                                const uint2 q = lib[j];
+                                const uint32_t m = (w.y ^ q.x) | (w.z ^ q.y);
+                                uint4 rec;
+                                if (__popc(m) <= k && bc_make_hit(p, c, w.x, p.ent_id[ls + a + j], m, &rec))
+                                    bc_stage_hit(p, &stage, rec);
+                            }
+                        }
+                    }
+                    for (; e < n_e; e++) {
+                        const uint2 q = lib[e];
                         const uint32_t m = (w.y ^ q.x) | (w.z ^ q.y);
-                        if (__popc(m) <= k) bc_emit_hit(p, c, w.x, p.ent_id[ls + e], m);
+                        uint4 rec;
+                        if (__popc(m) <= k && bc_make_hit(p, c, w.x, p.ent_id[ls + a + e], m, &rec))
+                            bc_stage_hit(p, &stage, rec);
                     }
                 }
             }
+            bc_flush_hits(p, &stage);
             __syncthreads();  // before the next chunk reuses s_win / s_cnt
         }
     }

@@ -217,6 +217,8 @@ cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cud
 __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_constant__ SearchParams p,
                                                               uint32_t n_tiles) {
     __shared__ uint32_t sH[PROBE_TILE_WORDS + 1], sL[PROBE_TILE_WORDS + 1], sB[PROBE_TILE_WORDS + 1];
+    __shared__ HitStage stage;
+    if (threadIdx.x == 0) stage.n = 0;
     const uint32_t lm = bc_lmask(p.L);
     unsigned long long cand = 0, probes = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -244,10 +246,14 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
                     const uint2 q = p.ent_hl[e];
                     const uint32_t m = (wh ^ q.x) | (wl ^ q.y);
                     cand++;
-                    if (__popc(m) <= (int)p.k) bc_emit_hit(p, c, pos, p.ent_id[e], m);
+                    if (__popc(m) <= (int)p.k) {
+                        uint4 rec;
+                        if (bc_make_hit(p, c, pos, p.ent_id[e], m, &rec)) bc_stage_hit(p, &stage, rec);
+                    }
                 }
             }
         }
+        bc_flush_hits(p, &stage);
     }
     if (p.count_candidates) {
         atomicAdd(p.count + 1, cand);
