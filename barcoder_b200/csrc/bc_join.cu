@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 }
 
 #define MV_THREADS 256
-#define MV_ITEMS 4
+#define MV_ITEMS 2
 #define MV_TILE (MV_THREADS * MV_ITEMS)
 
 // Slow path of the verify kernel: entry e of the index is within k mismatches of window w.
@@ -67,17 +67,31 @@ static __device__ __noinline__ void mv_report(const SearchParams& p, HitStage* s
     if (bc_make_hit(p, c, w.x, p.ent_id[e], m, &rec)) bc_stage_hit(p, stage, rec);
 }
 
+// Candidates that pass the popcount filter are not resolved where they are found: a single lane
+// walking the slow path (dependent loads of the entry id, contig table and PAM bases) would stall
+// its whole warp for microseconds, and cfg 4 has ~0.6 hits per window.  They are queued in shared
+// memory as (record index, entry) and resolved after the tile by all threads at once.
+#define MV_QCAP 2048
+
 __global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_constant__ SearchParams p,
                                                              const uint4* __restrict__ gwin,
                                                              const uint32_t* __restrict__ n_rec_ptr) {
     __shared__ HitStage stage;
-    if (threadIdx.x == 0) stage.n = 0;
+    __shared__ uint2 s_q[MV_QCAP];
+    __shared__ uint32_t s_qn;
+    if (threadIdx.x == 0) { stage.n = 0; s_qn = 0; }
     __syncthreads();
     const uint32_t n_rec = *n_rec_ptr;
     const uint32_t n_tiles = (n_rec + MV_TILE - 1) / MV_TILE;
     const int k = (int)p.k;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
+#define MV_CANDIDATE(E)                                              \
+    do {                                                             \
+        const uint32_t qs = atomicAdd(&s_qn, 1u);                    \
+        if (qs < MV_QCAP) s_q[qs] = make_uint2(i, (E));              \
+        else mv_report(p, &stage, w, (E));                           \
+    } while (0)
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int it = 0; it < MV_ITEMS; it++) {
@@ -87,8 +101,8 @@ __global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_consta
             const uint32_t ls = __ldg(p.dir + w.w), le = __ldg(p.dir + w.w + 1);
             cand += le - ls;
             uint32_t e = ls;
-            // branch-free batches of 4: popcounts are min-reduced, only a batch containing a hit
-            // is re-examined entry by entry
+            // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
+            // candidate is re-examined entry by entry
             for (; e + 4 <= le; e += 4) {
                 const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
                             q3 = __ldg(ent + e + 3);
@@ -97,19 +111,28 @@ __global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_consta
                 const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
                 const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
                 if (min(min(c0, c1), min(c2, c3)) <= k) {
-                    if (c0 <= k) mv_report(p, &stage, w, e);
-                    if (c1 <= k) mv_report(p, &stage, w, e + 1);
-                    if (c2 <= k) mv_report(p, &stage, w, e + 2);
-                    if (c3 <= k) mv_report(p, &stage, w, e + 3);
+                    if (c0 <= k) MV_CANDIDATE(e);
+                    if (c1 <= k) MV_CANDIDATE(e + 1);
+                    if (c2 <= k) MV_CANDIDATE(e + 2);
+                    if (c3 <= k) MV_CANDIDATE(e + 3);
                 }
             }
             for (; e < le; e++) {
                 const uint2 q = __ldg(ent + e);
-                if (__popc((w.y ^ q.x) | (w.z ^ q.y)) <= k) mv_report(p, &stage, w, e);
+                if (__popc((w.y ^ q.x) | (w.z ^ q.y)) <= k) MV_CANDIDATE(e);
             }
         }
-        bc_flush_hits(p, &stage);
+        __syncthreads();
+        const uint32_t nq = min(s_qn, (uint32_t)MV_QCAP);
+        for (uint32_t j = threadIdx.x; j < nq; j += MV_THREADS) {
+            const uint2 qe = s_q[j];
+            mv_report(p, &stage, gwin[qe.x], qe.y);
+        }
+        bc_flush_hits(p, &stage);  // barriers inside
+        if (threadIdx.x == 0) s_qn = 0;
+        __syncthreads();
     }
+#undef MV_CANDIDATE
     if (p.count_candidates) atomicAdd(p.count + 1, cand);
 }
 
