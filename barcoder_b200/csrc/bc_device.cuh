@@ -81,6 +81,16 @@ __device__ __forceinline__ uint32_t bc_combo_key(const ComboDesc& cd, uint32_t h
 
 __device__ __forceinline__ uint32_t bc_rev_bits(uint32_t m, uint32_t L) { return __brev(m) >> (32 - L); }
 
+// Ownership: a hit with <= k mismatches has >= b-k exact blocks; it is reported by the seed
+// combination made of its LOWEST b-k exact blocks and by no other, so every alignment is emitted
+// exactly once although several combinations find it.  m = mismatch mask in QUERY orientation.
+__device__ __forceinline__ bool bc_owns(const SearchParams& p, uint32_t c, uint32_t m) {
+    uint32_t need = p.b - p.k, own = 0;
+    for (uint32_t j = 0; j < p.b && need; j++)
+        if (!(m & p.block_mask[j])) { own |= 1u << j; need--; }
+    return own == p.combo[c].blocks_mask;
+}
+
 // Rare path: a (window, entry) pair passed the popcount filter in seed combination `c`.
 // Decides whether this combination owns the hit and annotates the PAM.  Returns false when the
 // pair is not to be reported from here.
@@ -97,12 +107,7 @@ static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t 
         m |= nm;
         if (__popc(m) > (int)p.k) return false;
     }
-    // Ownership: a hit with <= k mismatches has >= b-k exact blocks; it is reported by the
-    // combination made of its LOWEST b-k exact blocks and by no other.
-    uint32_t need = p.b - p.k, own = 0;
-    for (uint32_t j = 0; j < p.b && need; j++)
-        if (!(m & p.block_mask[j])) { own |= 1u << j; need--; }
-    if (own != p.combo[c].blocks_mask) return false;
+    if (!bc_owns(p, c, m)) return false;
 
     // contig of the window
     uint32_t lo = 0, hi = p.n_contigs;

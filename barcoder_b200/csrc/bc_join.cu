@@ -56,91 +56,102 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 #define MV_THREADS 256
 #define MV_ITEMS 4
 #define MV_TILE (MV_THREADS * MV_ITEMS)
-
-// Slow path of the verify kernel: entry e of the index is within k mismatches of window w.
-static __device__ __noinline__ void mv_report(const SearchParams& p, HitStage* stage, const uint4 w, uint32_t e) {
-    const uint2 q = p.ent_hl[e];
-    const uint32_t m = (w.y ^ q.x) | (w.z ^ q.y);
-    uint32_t c = 0;  // combination that owns directory slot w.w
-    while (c + 1 < p.n_combos && p.combo[c + 1].dir_off <= w.w) c++;
-    uint4 rec;
-    if (bc_make_hit(p, c, w.x, p.ent_id[e], m, &rec)) bc_stage_hit(p, stage, rec);
-}
-
+#define MV_TILES_PER_ROUND 4  // tiles verified between two resolve/flush phases
 // Candidates that pass the popcount filter are not resolved where they are found: a single lane
 // walking the slow path (dependent loads of the entry id, contig table and PAM bases) would stall
-// its whole warp for microseconds, and cfg 4 has ~0.6 hits per window.  They are queued in shared
-// memory as (record index, entry) and resolved after the tile by all threads at once.
-#define MV_QCAP 2048
+// its whole warp for microseconds.  Candidates that this combination owns are queued in shared
+// memory as {dev position, mismatch mask, index entry, combination} and resolved once per round
+// by all threads at once.
+#define MV_QCAP 1024
+
+__device__ __forceinline__ uint32_t mv_combo_of_slot(const SearchParams& p, uint32_t slot) {
+    uint32_t c = 0;
+    while (c + 1 < p.n_combos && p.combo[c + 1].dir_off <= slot) c++;
+    return c;
+}
 
 __global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_constant__ SearchParams p,
                                                              const uint4* __restrict__ gwin,
                                                              const uint32_t* __restrict__ n_rec_ptr) {
     __shared__ HitStage stage;
-    __shared__ uint2 s_q[MV_QCAP];
+    __shared__ uint4 s_q[MV_QCAP];
     __shared__ uint32_t s_qn;
     if (threadIdx.x == 0) { stage.n = 0; s_qn = 0; }
     __syncthreads();
     const uint32_t n_rec = *n_rec_ptr;
     const uint32_t n_tiles = (n_rec + MV_TILE - 1) / MV_TILE;
+    const uint32_t n_rounds = (n_tiles + MV_TILES_PER_ROUND - 1) / MV_TILES_PER_ROUND;
     const int k = (int)p.k;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
-#define MV_CANDIDATE(E)                                              \
-    do {                                                             \
-        const uint32_t qs = atomicAdd(&s_qn, 1u);                    \
-        if (qs < MV_QCAP) s_q[qs] = make_uint2(i, (E));              \
-        else mv_report(p, &stage, w, (E));                           \
+    // entry E of the index is within k mismatches of window w
+#define MV_CANDIDATE(E, Q)                                                            \
+    do {                                                                              \
+        const uint32_t m_ = (w.y ^ (Q).x) | (w.z ^ (Q).y);                            \
+        const uint32_t c_ = mv_combo_of_slot(p, w.w);                                 \
+        if (p.lib_has_n || bc_owns(p, c_, m_)) {                                      \
+            const uint32_t qs = atomicAdd(&s_qn, 1u);                                 \
+            if (qs < MV_QCAP) s_q[qs] = make_uint4(w.x, m_, (E), c_);                 \
+            else {                                                                    \
+                uint4 rec_;                                                           \
+                if (bc_make_hit(p, c_, w.x, p.ent_id[(E)], m_, &rec_)) bc_stage_hit(p, &stage, rec_); \
+            }                                                                         \
+        }                                                                             \
     } while (0)
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // Issue the loads of all MV_ITEMS records, then of their directory entries, before any
-        // dependent work: three memory latencies per tile instead of three per record.
-        uint4 wv[MV_ITEMS];
-        uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
+    for (uint32_t round = blockIdx.x; round < n_rounds; round += gridDim.x) {
+#pragma unroll 1
+        for (uint32_t tr = 0; tr < MV_TILES_PER_ROUND; tr++) {
+            const uint32_t tile = round * MV_TILES_PER_ROUND + tr;
+            if (tile >= n_tiles) break;
+            // Issue the loads of all MV_ITEMS records, then of their directory entries, before
+            // any dependent work: three memory latencies per tile instead of three per record.
+            uint4 wv[MV_ITEMS];
+            uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
 #pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) {
-            const uint32_t i = tile * MV_TILE + it * MV_THREADS + threadIdx.x;
-            wv[it] = __ldcs(gwin + min(i, n_rec - 1));
-        }
-#pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) {
-            const uint32_t i = tile * MV_TILE + it * MV_THREADS + threadIdx.x;
-            lsv[it] = __ldg(p.dir + wv[it].w);
-            lev[it] = i < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
-        }
-#pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) {
-            const uint32_t i = tile * MV_TILE + it * MV_THREADS + threadIdx.x;
-            const uint4 w = wv[it];
-            const uint32_t ls = lsv[it], le = lev[it];
-            cand += le - ls;
-            uint32_t e = ls;
-            // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
-            // candidate is re-examined entry by entry
-            for (; e + 4 <= le; e += 4) {
-                const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
-                            q3 = __ldg(ent + e + 3);
-                const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
-                const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
-                const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
-                const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
-                if (min(min(c0, c1), min(c2, c3)) <= k) {
-                    if (c0 <= k) MV_CANDIDATE(e);
-                    if (c1 <= k) MV_CANDIDATE(e + 1);
-                    if (c2 <= k) MV_CANDIDATE(e + 2);
-                    if (c3 <= k) MV_CANDIDATE(e + 3);
-                }
+            for (int it = 0; it < MV_ITEMS; it++) {
+                const uint32_t i = tile * MV_TILE + it * MV_THREADS + threadIdx.x;
+                wv[it] = __ldcs(gwin + min(i, n_rec - 1));
             }
-            for (; e < le; e++) {
-                const uint2 q = __ldg(ent + e);
-                if (__popc((w.y ^ q.x) | (w.z ^ q.y)) <= k) MV_CANDIDATE(e);
+#pragma unroll
+            for (int it = 0; it < MV_ITEMS; it++) {
+                const uint32_t i = tile * MV_TILE + it * MV_THREADS + threadIdx.x;
+                lsv[it] = __ldg(p.dir + wv[it].w);
+                lev[it] = i < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
+            }
+#pragma unroll
+            for (int it = 0; it < MV_ITEMS; it++) {
+                const uint4 w = wv[it];
+                const uint32_t ls = lsv[it], le = lev[it];
+                cand += le - ls;
+                uint32_t e = ls;
+                // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
+                // candidate is re-examined entry by entry
+                for (; e + 4 <= le; e += 4) {
+                    const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
+                                q3 = __ldg(ent + e + 3);
+                    const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
+                    const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
+                    const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
+                    const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
+                    if (min(min(c0, c1), min(c2, c3)) <= k) {
+                        if (c0 <= k) MV_CANDIDATE(e, q0);
+                        if (c1 <= k) MV_CANDIDATE(e + 1, q1);
+                        if (c2 <= k) MV_CANDIDATE(e + 2, q2);
+                        if (c3 <= k) MV_CANDIDATE(e + 3, q3);
+                    }
+                }
+                for (; e < le; e++) {
+                    const uint2 q = __ldg(ent + e);
+                    if (__popc((w.y ^ q.x) | (w.z ^ q.y)) <= k) MV_CANDIDATE(e, q);
+                }
             }
         }
         __syncthreads();
         const uint32_t nq = min(s_qn, (uint32_t)MV_QCAP);
         for (uint32_t j = threadIdx.x; j < nq; j += MV_THREADS) {
-            const uint2 qe = s_q[j];
-            mv_report(p, &stage, gwin[qe.x], qe.y);
+            const uint4 qe = s_q[j];
+            uint4 rec;
+            if (bc_make_hit(p, qe.w, qe.x, p.ent_id[qe.z], qe.y, &rec)) bc_stage_hit(p, &stage, rec);
         }
         bc_flush_hits(p, &stage);  // barriers inside
         if (threadIdx.x == 0) s_qn = 0;

@@ -1,0 +1,102 @@
+"""Minimal PyRanges stand-in: the subset the path uses (`pr.PyRanges(df)`, `.df`, `.join`).
+
+The reference wraps its hit frame and its feature frame in pyranges objects and joins them
+(PySamParser.py:50-52, GenBankParser.py:101-103, testing_grounds.py:38).  pyranges/ncls are not
+part of this build; the overlap join below is a sorted-interval sweep in numpy.
+
+Join semantics follow pyranges 0.0.129 `PyRanges.join(other)` with default arguments: inner
+join on overlapping intervals of the same Chromosome (half-open, overlap >= 1 bp), the other
+frame's Start/End/Strand get the suffix "_b", its remaining columns keep their names.
+Strandedness: the pinned pyranges cannot be imported here, so its `strandedness=None` default
+is an unverifiable corner (SURVEY.md 8c iv); None ignores strand, "same"/"opposite" are offered.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+
+class PyRanges:
+    def __init__(self, df=None):
+        if df is None:
+            df = pd.DataFrame(columns=["Chromosome", "Start", "End"])
+        df = df.copy()
+        if len(df) and "Chromosome" in df.columns:
+            df = df[df["Chromosome"].notna()]  # pyranges groups by Chromosome; null keys vanish
+        self._df = df.reset_index(drop=True)
+
+    @property
+    def df(self):
+        return self._df
+
+    def as_df(self):
+        return self._df
+
+    def __len__(self):
+        return len(self._df)
+
+    @property
+    def columns(self):
+        return self._df.columns
+
+    @property
+    def stranded(self):
+        return "Strand" in self._df.columns and set(self._df["Strand"].unique()) <= {"+", "-"}
+
+    def __repr__(self):
+        return f"PyRanges({len(self._df)} intervals)\n{self._df.head(8)!r}"
+
+    def join(self, other, strandedness=None, how=None, suffix="_b", **_ignored):
+        a, b = self._df, other._df if isinstance(other, PyRanges) else other
+        if strandedness not in (None, False, "same", "opposite"):
+            raise ValueError("strandedness must be None, False, 'same' or 'opposite'")
+        left_idx, right_idx = overlap_pairs(a, b)
+        if strandedness in ("same", "opposite") and len(left_idx):
+            sa = a["Strand"].to_numpy()[left_idx]
+            sb = b["Strand"].to_numpy()[right_idx]
+            keep = (sa == sb) if strandedness == "same" else (
+                ((sa == "+") & (sb == "-")) | ((sa == "-") & (sb == "+")))
+            left_idx, right_idx = left_idx[keep], right_idx[keep]
+        out = a.iloc[left_idx].reset_index(drop=True)
+        bb = b.iloc[right_idx].reset_index(drop=True).drop(columns=["Chromosome"])
+        bb = bb.rename(columns={c: c + suffix for c in bb.columns if c in out.columns})
+        return PyRanges(pd.concat([out, bb], axis=1))
+
+
+def overlap_pairs(a, b):
+    """All (i, j) with a.Chromosome[i] == b.Chromosome[j] and the half-open intervals overlapping.
+    Sweep per chromosome: b sorted by Start; candidates are b rows with Start < a.End, filtered
+    by End > a.Start through a running maximum of b's interval lengths."""
+    if len(a) == 0 or len(b) == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    li, ri = [], []
+    a_chr = a["Chromosome"].to_numpy()
+    b_chr = b["Chromosome"].to_numpy()
+    a_s, a_e = a["Start"].to_numpy(dtype=np.int64), a["End"].to_numpy(dtype=np.int64)
+    b_s, b_e = b["Start"].to_numpy(dtype=np.int64), b["End"].to_numpy(dtype=np.int64)
+    for chrom in pd.unique(a_chr):
+        ia = np.nonzero(a_chr == chrom)[0]
+        ib = np.nonzero(b_chr == chrom)[0]
+        if len(ib) == 0:
+            continue
+        order = np.argsort(b_s[ib], kind="stable")
+        ib = ib[order]
+        bs, be = b_s[ib], b_e[ib]
+        max_len = int((be - bs).max()) if len(ib) else 0
+        # b rows that can overlap a row: Start in (a.Start - max_len, a.End)
+        lo = np.searchsorted(bs, a_s[ia] - max_len, side="right")
+        hi = np.searchsorted(bs, a_e[ia], side="left")
+        counts = np.maximum(hi - lo, 0)
+        if counts.sum() == 0:
+            continue
+        rep_a = np.repeat(np.arange(len(ia)), counts)
+        offs = np.arange(counts.sum()) - np.repeat(np.cumsum(counts) - counts, counts)
+        cand_b = np.repeat(lo, counts) + offs
+        ok = (be[cand_b] > a_s[ia][rep_a]) & (bs[cand_b] < a_e[ia][rep_a])
+        li.append(ia[rep_a[ok]])
+        ri.append(ib[cand_b[ok]])
+    if not li:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    li, ri = np.concatenate(li), np.concatenate(ri)
+    order = np.lexsort((ri, li))
+    return li[order], ri[order]
