@@ -1,0 +1,278 @@
+"""BowtieRunner - the reference's aligner front-end, backed by the CUDA search instead of bowtie.
+
+Public surface kept from BowtieRunner.py:13-150 of the reference:
+
+    with BowtieRunner() as bowtie:
+        bowtie.make_fasta(records)        # dict id -> record with .id/.seq/.description
+        bowtie.make_fastq(barcodes)       # iterable of spacer strings; calls accumulate (:67 append mode)
+        bowtie.create_index()             # BowtieError if no genome was written (:79-80)
+        bowtie.align(num_mismatches=1, num_threads=12)
+        sam = PySamParser(bowtie.sam_path)
+
+plus the properties index_path / fasta_path / fastq_path / sam_path and BowtieError(message).
+
+What happens instead of the two subprocesses (BowtieRunner.py:87-97,111-136):
+  make_fasta    keeps the contigs in memory (and writes the FASTA file, as the reference does)
+  create_index  bc_create + bc_set_genome: H2D copy and 2-bit/ambiguity packing on the GPU
+  align         per spacer length: bc_set_library, bc_build_index(k), bc_search(k), bc_copy_hits;
+                `bowtie -a -v k` semantics (every alignment, both strands), PAM fused when known
+The result is kept as a hit table (`.hits`, `.frame`) registered under `sam_path`, so
+PySamParser(bowtie.sam_path).ranges needs no text round trip; a bowtie-style SAM file is also
+written to `sam_path` (always when write_sam=True, by default only up to SAM_AUTO_LIMIT lines).
+
+`num_threads` is accepted for compatibility and ignored (the search runs on one GPU).
+There is no CPU fallback: any native error surfaces as BowtieError.
+"""
+from __future__ import annotations
+
+import os
+import tempfile
+
+import numpy as np
+import pandas as pd
+
+from . import _native, samio
+from .Logger import Logger
+from .seqio import reverse_complement, write_fasta
+
+SAM_AUTO_LIMIT = 2_000_000
+
+# sam_path -> BowtieRunner result, consulted by PySamParser (see PySamParser.py)
+RESULTS = {}
+# most recently constructed PAMFinder: lets align() fuse the PAM check (see PAMProcessor.py)
+ACTIVE_PAM = {"finder": None}
+
+
+class BowtieError(Exception):
+    """Raised for any failure of the search path; `.message` explains it (BowtieRunner.py:144-150)."""
+
+    def __init__(self, message):
+        super().__init__(message)
+        self.message = message
+
+
+class BowtieRunner(Logger):
+    def __init__(self, device=0, write_sam="auto", write_files=True):
+        super().__init__()
+        self.temp_dir = tempfile.TemporaryDirectory()
+        self.device = device
+        self.write_sam = write_sam
+        self.write_files = write_files
+        self._index_path = None
+        self._contig_ids, self._contigs = [], []
+        self._reads = []
+        self._searcher = None
+        self._pam = None  # (pam, direction) set explicitly through set_pam()
+        self.hits = None
+        self.frame = None
+        self.stats = []
+
+    # ---- paths (same names as the reference; files live in the temp dir)
+    @property
+    def index_path(self):
+        if self._index_path is None:
+            fd, self._index_path = tempfile.mkstemp(dir=self.temp_dir.name)
+            os.close(fd)
+        return self._index_path
+
+    @property
+    def fasta_path(self):
+        return self.index_path + ".fasta"
+
+    @property
+    def fastq_path(self):
+        return self.index_path + ".fastq"
+
+    @property
+    def sam_path(self):
+        return self.index_path + ".sam"
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        self.close()
+
+    def close(self):
+        RESULTS.pop(self.sam_path, None)
+        if self._searcher is not None:
+            self._searcher.close()
+            self._searcher = None
+        self.temp_dir.cleanup()
+
+    # ---- inputs
+    def make_fasta(self, records):
+        self.info(f"Writing FASTA file {self.fasta_path} ...")
+        try:
+            recs = list(records.values())
+            self._contig_ids = [r.id for r in recs]
+            self._contigs = [str(r.seq) for r in recs]
+            if self.write_files:
+                with open(self.fasta_path, "w") as handle:
+                    write_fasta(recs, handle)
+        except Exception as exc:
+            raise BowtieError("Failed to write FASTA file") from exc
+
+    def make_fastq(self, barcodes):
+        self.info(f"Writing FASTQ file {self.fastq_path} ...")
+        try:
+            new = [str(b) for b in barcodes]
+            self._reads.extend(new)
+            if self.write_files:
+                with open(self.fastq_path, "a") as handle:
+                    for s in new:  # Q40 for every base, unnamed records (BowtieRunner.py:68-74)
+                        handle.write(f"@{samio.READ_NAME} <unknown description>\n{s}\n+\n{'I' * len(s)}\n")
+        except Exception as exc:
+            raise BowtieError("Failed to write FASTQ file") from exc
+
+    def set_pam(self, pam, direction="downstream"):
+        """Optional: tell the aligner which PAM to check in the same pass.  Without it, align()
+        uses the most recently constructed PAMFinder, if any."""
+        self._pam = (pam, direction)
+
+    # ---- compute
+    def create_index(self):
+        if not self._contigs or sum(len(c) for c in self._contigs) == 0:
+            raise BowtieError("BowtieRunner.fasta_path does not exist or is an empty")
+        self.info(f"Creating index on CUDA device {self.device} ...")
+        try:
+            if self._searcher is None:
+                self._searcher = _native.Searcher(self.device)
+            self._searcher.set_genome(self._contigs)
+        except (_native.NativeError, _native.NativeLibraryError) as exc:
+            raise BowtieError("Failed to index") from exc
+        st = self._searcher.stats()
+        self.subproc(f"packed {st['genome_bases']} bases in {st['ms_pack_genome']:.3f} ms")
+
+    def _pam_setting(self):
+        if self._pam is not None:
+            return self._pam
+        finder = ACTIVE_PAM["finder"]
+        if finder is not None and finder.device_checkable:
+            # the class API slices the 3' side for both directions (PAMProcessor.py:69-87)
+            return (finder.raw_pam, "downstream")
+        return None
+
+    def align(self, num_mismatches=0, num_threads=os.cpu_count()):
+        if self._searcher is None:
+            raise BowtieError("bowtie failed: create_index() has not been called")
+        k = int(num_mismatches)
+        self.info(f"Performing alignment on CUDA device {self.device} ...")
+        self.json(["bc_search", "-a", f"-v{k}", f"reads={len(self._reads)}"])
+        pam = self._pam_setting()
+        reads = self._reads
+        upper = [r.upper() for r in reads]
+        by_len = {}
+        for i, r in enumerate(upper):
+            by_len.setdefault(len(r), []).append(i)
+        parts, self.stats = [], []
+        try:
+            self._searcher.set_pam(pam[0] if pam else "", pam[1] if pam else "downstream")
+            for L, idx in sorted(by_len.items()):
+                if L == 0 or L > 32:
+                    if L > 32:
+                        raise BowtieError(f"spacers longer than 32 nt are not supported (got {L})")
+                    continue
+                idx = np.asarray(idx, dtype=np.int64)
+                self._searcher.set_library([upper[i] for i in idx])
+                self._searcher.search(k)
+                h = self._searcher.hits()
+                h["spacer_id"] = idx[h["spacer_id"]].astype(np.uint32)  # back to read order
+                parts.append(h)
+                self.stats.append(self._searcher.stats())
+        except (_native.NativeError, _native.NativeLibraryError) as exc:
+            raise BowtieError(f"bc_search failed: {exc}") from exc
+        hits = np.concatenate(parts) if parts else np.zeros(0, dtype=_native.HIT_DTYPE)
+        # bowtie --best: per read, fewest mismatches first; then by position for determinism
+        order = np.lexsort((hits["meta"] & 1, hits["gpos"], (hits["meta"] >> 1) & 3, hits["spacer_id"]))
+        self.hits = hits[order]
+        self._pam_used = pam
+        self.frame = self._build_frame()
+        RESULTS[self.sam_path] = self
+        n_lines = len(self.frame)
+        if self.write_sam is True or (self.write_sam == "auto" and n_lines <= SAM_AUTO_LIMIT):
+            samio.write_sam(self.sam_path, self)
+        for st in self.stats:
+            self.subproc(f"L={st['spacer_len']} k={st['k']}: {st['hits']} alignments of {st['library_spacers']} "
+                         f"reads, search {st['ms_search']:.3f} ms (index {st['ms_build_index']:.3f} ms)")
+
+    # ---- result views
+    def contig_of(self, gpos):
+        off = self._searcher.contig_offsets if self._searcher is not None else self._offsets
+        return np.searchsorted(off[1:], gpos, side="right")
+
+    def _build_frame(self):
+        """Hit table with the columns PySamParser.ranges produces (PySamParser.py:38-46), one row
+        per alignment plus one unmapped row per read without alignments, and - when a PAM was
+        fused - `PAM` / `Targeting` columns (CRISPRiLibrary.py:16-21)."""
+        hits, reads = self.hits, self._reads
+        off = np.asarray(self._searcher.contig_offsets, dtype=np.int64)
+        self._offsets = off
+        L = np.fromiter((len(r) for r in reads), dtype=np.int64, count=len(reads))
+        sid = hits["spacer_id"].astype(np.int64)
+        ci = np.searchsorted(off[1:], hits["gpos"].astype(np.int64), side="right")
+        start = hits["gpos"].astype(np.int64) - off[ci]
+        ids = np.asarray(self._contig_ids, dtype=object)
+        barcode = np.asarray([r.upper() for r in reads], dtype=object)
+        df = pd.DataFrame({
+            "Chromosome": ids[ci] if len(hits) else np.zeros(0, dtype=object),
+            "Start": start,
+            "End": start + L[sid] if len(hits) else start,
+            "Mapped": np.ones(len(hits), dtype=bool),
+            "Strand": np.where(hits["meta"] & 1, "-", "+"),
+            "Barcode": barcode[sid] if len(hits) else np.zeros(0, dtype=object),
+            "Mismatches": ((hits["meta"] >> 1) & 3).astype(np.int64),
+        })
+        if self._pam_used:
+            pam_str, targeting = self._pam_columns(ci, start, L[sid] if len(hits) else L[:0])
+            df["PAM"] = pam_str
+            df["Targeting"] = targeting
+            df.attrs["pam_key"] = (self._pam_used[0].upper(), "class-api")
+        aligned = np.zeros(len(reads), dtype=bool)
+        aligned[sid] = True
+        missing = np.nonzero(~aligned)[0]
+        if len(missing):  # flag-4 SAM lines: PySamParser reports them with Mismatches "0" (:45)
+            um = pd.DataFrame({
+                "Chromosome": None, "Start": -1, "End": None, "Mapped": False, "Strand": "+",
+                "Barcode": barcode[missing], "Mismatches": "0",
+            })
+            if self._pam_used:
+                um["PAM"] = ""
+                um["Targeting"] = False
+            attrs = dict(df.attrs)
+            df = pd.concat([df.astype({"Mismatches": object, "End": object}), um], ignore_index=True)
+            df.attrs.update(attrs)
+        return df
+
+    def _pam_columns(self, ci, start, lens):
+        """PAM strings and match flags.  Full, unambiguous PAMs come decoded from the kernel's
+        2-bit codes; truncated or ambiguous ones (contig ends, N in the genome) and lower-case
+        genomes are resolved with the reference's own string rule (PAMProcessor.py:65-97)."""
+        import re
+        hits = self.hits
+        pam = self._pam_used[0].upper()
+        P = len(pam)
+        meta = hits["meta"]
+        codes = (meta >> 16).astype(np.uint32)
+        letters = np.frombuffer(b"ACGT", dtype="S1")
+        chars = np.empty((len(hits), P), dtype="S1")
+        for i in range(P):
+            chars[:, i] = letters[(codes >> (2 * i)) & 3]
+        pam_str = np.array([b"".join(row).decode() for row in chars], dtype=object) if P else \
+            np.full(len(hits), "", dtype=object)
+        targeting = (meta & _native.META_PAM_OK) != 0
+        lower = any(c != c.upper() for c in self._contigs) if not hasattr(self, "_has_lower") else self._has_lower
+        self._has_lower = lower
+        slow = ((meta & _native.META_PAM_FULL) == 0) | ((meta & _native.META_PAM_AMB) != 0)
+        if lower:
+            slow = np.ones(len(hits), dtype=bool)
+        if slow.any():
+            pattern = re.compile(pam.replace("N", "[ATCG]"))
+            minus = (meta & 1) != 0
+            for j in np.nonzero(slow)[0]:
+                seq = self._contigs[ci[j]]
+                s0, e0 = int(start[j]), int(start[j] + lens[j])
+                s = reverse_complement(seq[s0 - P:s0]) if minus[j] else seq[e0:e0 + P]
+                pam_str[j] = s
+                targeting[j] = bool(pattern.search(s))
+        return pam_str, targeting

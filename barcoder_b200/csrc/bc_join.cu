@@ -54,15 +54,9 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 }
 
 #define MV_THREADS 256
-#define MV_ITEMS 4
-#define MV_TILE (MV_THREADS * MV_ITEMS)
-#define MV_TILES_PER_ROUND 4  // tiles verified between two resolve/flush phases
-// Candidates that pass the popcount filter are not resolved where they are found: a single lane
-// walking the slow path (dependent loads of the entry id, contig table and PAM bases) would stall
-// its whole warp for microseconds.  Candidates that this combination owns are queued in shared
-// memory as {dev position, mismatch mask, index entry, combination} and resolved once per round
-// by all threads at once.
-#define MV_QCAP 1024
+#define MV_WARPS (MV_THREADS / 32)
+#define MV_ITEMS 4    // records per lane per warp-tile
+#define MV_WQ 128     // per-warp candidate queue (entries)
 
 __device__ __forceinline__ uint32_t mv_combo_of_slot(const SearchParams& p, uint32_t slot) {
     uint32_t c = 0;
@@ -70,94 +64,120 @@ __device__ __forceinline__ uint32_t mv_combo_of_slot(const SearchParams& p, uint
     return c;
 }
 
+// Resolve up to 32 queued candidates {dev position, mismatch mask, index entry, directory slot}
+// with all lanes of the warp: ownership, PAM annotation, then ONE global atomic for the whole
+// batch and a coalesced store of the surviving records.
+static __device__ __noinline__ void mv_resolve(const SearchParams& p, const uint4* q, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint4 rec;
+    bool ok = false;
+    if (lane < n) {
+        const uint4 qe = q[lane];
+        ok = bc_make_hit(p, mv_combo_of_slot(p, qe.w), qe.x, p.ent_id[qe.z], qe.y, &rec);
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+    if (ballot == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(p.count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) {
+        const unsigned long long dst = base + __popc(ballot & ((1u << lane) - 1u));
+        if (dst < p.cap) reinterpret_cast<uint4*>(p.hits)[dst] = rec;
+    }
+}
+
+// Verify kernel, warp-autonomous (no block barriers): each warp owns warp-tiles of 32*MV_ITEMS
+// sorted records.  Candidates that pass the popcount filter are NOT resolved where they are found
+// - a single lane walking the slow path (dependent loads of the entry id, contig table and PAM
+// bases) would stall its warp for microseconds, and ncu showed 11.6 active lanes per instruction
+// when it did - they are pushed to a per-warp shared-memory queue and resolved 32 at a time.
 __global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_constant__ SearchParams p,
                                                              const uint4* __restrict__ gwin,
                                                              const uint32_t* __restrict__ n_rec_ptr) {
-    __shared__ HitStage stage;
-    __shared__ uint4 s_q[MV_QCAP];
-    __shared__ uint32_t s_qn;
-    if (threadIdx.x == 0) { stage.n = 0; s_qn = 0; }
-    __syncthreads();
+    __shared__ uint4 s_q[MV_WARPS][MV_WQ];
+    __shared__ uint32_t s_qn[MV_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint4* q = s_q[warp];
+    uint32_t* qn = &s_qn[warp];
+    if (lane == 0) *qn = 0;
+    __syncwarp();
     const uint32_t n_rec = *n_rec_ptr;
-    const uint32_t n_tiles = (n_rec + MV_TILE - 1) / MV_TILE;
-    const uint32_t n_rounds = (n_tiles + MV_TILES_PER_ROUND - 1) / MV_TILES_PER_ROUND;
+    const uint32_t wtile = 32 * MV_ITEMS;
+    const uint32_t n_wtiles = (n_rec + wtile - 1) / wtile;
+    const uint32_t n_warps = gridDim.x * MV_WARPS;
     const int k = (int)p.k;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
-    // entry E of the index is within k mismatches of window w
-#define MV_CANDIDATE(E, Q)                                                            \
-    do {                                                                              \
-        const uint32_t m_ = (w.y ^ (Q).x) | (w.z ^ (Q).y);                            \
-        const uint32_t c_ = mv_combo_of_slot(p, w.w);                                 \
-        if (p.lib_has_n || bc_owns(p, c_, m_)) {                                      \
-            const uint32_t qs = atomicAdd(&s_qn, 1u);                                 \
-            if (qs < MV_QCAP) s_q[qs] = make_uint4(w.x, m_, (E), c_);                 \
-            else {                                                                    \
-                uint4 rec_;                                                           \
-                if (bc_make_hit(p, c_, w.x, p.ent_id[(E)], m_, &rec_)) bc_stage_hit(p, &stage, rec_); \
-            }                                                                         \
-        }                                                                             \
+    // entry E (words Q) of the index is within k mismatches of window w
+#define MV_CANDIDATE(E, Q)                                                                      \
+    do {                                                                                        \
+        const uint32_t m_ = (w.y ^ (Q).x) | (w.z ^ (Q).y);                                      \
+        const uint32_t qs = atomicAdd(qn, 1u);                                                  \
+        if (qs < MV_WQ) q[qs] = make_uint4(w.x, m_, (E), w.w);                                  \
+        else {                                                                                  \
+            uint4 rec_;                                                                         \
+            if (bc_make_hit(p, mv_combo_of_slot(p, w.w), w.x, p.ent_id[(E)], m_, &rec_)) {      \
+                const unsigned long long g_ = atomicAdd(p.count, 1ull);                         \
+                if (g_ < p.cap) reinterpret_cast<uint4*>(p.hits)[g_] = rec_;                    \
+            }                                                                                   \
+        }                                                                                       \
     } while (0)
-    for (uint32_t round = blockIdx.x; round < n_rounds; round += gridDim.x) {
-#pragma unroll 1
-        for (uint32_t tr = 0; tr < MV_TILES_PER_ROUND; tr++) {
-            const uint32_t tile = round * MV_TILES_PER_ROUND + tr;
-            if (tile >= n_tiles) break;
-            // Issue the loads of all MV_ITEMS records, then of their directory entries, before
-            // any dependent work: three memory latencies per tile instead of three per record.
-            uint4 wv[MV_ITEMS];
-            uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
+    for (uint32_t wt = blockIdx.x * MV_WARPS + warp; wt < n_wtiles; wt += n_warps) {
+        // Issue the loads of all MV_ITEMS records, then of their directory entries, before any
+        // dependent work: three memory latencies per warp-tile instead of three per record.
+        uint4 wv[MV_ITEMS];
+        uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
 #pragma unroll
-            for (int it = 0; it < MV_ITEMS; it++) {
-                const uint32_t i = tile * MV_TILE + it * MV_THREADS + threadIdx.x;
-                wv[it] = __ldcs(gwin + min(i, n_rec - 1));
-            }
+        for (int it = 0; it < MV_ITEMS; it++) {
+            const uint32_t i = wt * wtile + it * 32 + lane;
+            wv[it] = __ldcs(gwin + min(i, n_rec - 1));
+        }
 #pragma unroll
-            for (int it = 0; it < MV_ITEMS; it++) {
-                const uint32_t i = tile * MV_TILE + it * MV_THREADS + threadIdx.x;
-                lsv[it] = __ldg(p.dir + wv[it].w);
-                lev[it] = i < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
-            }
+        for (int it = 0; it < MV_ITEMS; it++) {
+            const uint32_t i = wt * wtile + it * 32 + lane;
+            lsv[it] = __ldg(p.dir + wv[it].w);
+            lev[it] = i < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
+        }
 #pragma unroll
-            for (int it = 0; it < MV_ITEMS; it++) {
-                const uint4 w = wv[it];
-                const uint32_t ls = lsv[it], le = lev[it];
-                cand += le - ls;
-                uint32_t e = ls;
-                // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
-                // candidate is re-examined entry by entry
-                for (; e + 4 <= le; e += 4) {
-                    const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
-                                q3 = __ldg(ent + e + 3);
-                    const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
-                    const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
-                    const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
-                    const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
-                    if (min(min(c0, c1), min(c2, c3)) <= k) {
-                        if (c0 <= k) MV_CANDIDATE(e, q0);
-                        if (c1 <= k) MV_CANDIDATE(e + 1, q1);
-                        if (c2 <= k) MV_CANDIDATE(e + 2, q2);
-                        if (c3 <= k) MV_CANDIDATE(e + 3, q3);
-                    }
-                }
-                for (; e < le; e++) {
-                    const uint2 q = __ldg(ent + e);
-                    if (__popc((w.y ^ q.x) | (w.z ^ q.y)) <= k) MV_CANDIDATE(e, q);
+        for (int it = 0; it < MV_ITEMS; it++) {
+            const uint4 w = wv[it];
+            const uint32_t ls = lsv[it], le = lev[it];
+            cand += le - ls;
+            uint32_t e = ls;
+            // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
+            // candidate is re-examined entry by entry
+            for (; e + 4 <= le; e += 4) {
+                const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
+                            q3 = __ldg(ent + e + 3);
+                const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
+                const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
+                const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
+                const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
+                if (min(min(c0, c1), min(c2, c3)) <= k) {
+                    if (c0 <= k) MV_CANDIDATE(e, q0);
+                    if (c1 <= k) MV_CANDIDATE(e + 1, q1);
+                    if (c2 <= k) MV_CANDIDATE(e + 2, q2);
+                    if (c3 <= k) MV_CANDIDATE(e + 3, q3);
                 }
             }
+            for (; e < le; e++) {
+                const uint2 qq = __ldg(ent + e);
+                if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+            }
+            __syncwarp();
+            uint32_t nq = min(*qn, (uint32_t)MV_WQ);  // warp-uniform: written before the syncwarp
+            while (nq >= 32) {
+                mv_resolve(p, q + (nq - 32), 32);
+                nq -= 32;
+            }
+            __syncwarp();
+            if (lane == 0) *qn = nq;
+            __syncwarp();
         }
-        __syncthreads();
-        const uint32_t nq = min(s_qn, (uint32_t)MV_QCAP);
-        for (uint32_t j = threadIdx.x; j < nq; j += MV_THREADS) {
-            const uint4 qe = s_q[j];
-            uint4 rec;
-            if (bc_make_hit(p, qe.w, qe.x, p.ent_id[qe.z], qe.y, &rec)) bc_stage_hit(p, &stage, rec);
-        }
-        bc_flush_hits(p, &stage);  // barriers inside
-        if (threadIdx.x == 0) s_qn = 0;
-        __syncthreads();
     }
 #undef MV_CANDIDATE
+    const uint32_t nq = min(*qn, (uint32_t)MV_WQ);
+    if (nq) mv_resolve(p, q, nq);
     if (p.count_candidates) atomicAdd(p.count + 1, cand);
 }
 
