@@ -32,15 +32,12 @@ import numpy as np
 import pandas as pd
 
 from . import _native, samio
+from ._state import ACTIVE_PAM, RESULTS
 from .Logger import Logger
 from .seqio import reverse_complement, write_fasta
 
 SAM_AUTO_LIMIT = 2_000_000
 
-# sam_path -> BowtieRunner result, consulted by PySamParser (see PySamParser.py)
-RESULTS = {}
-# most recently constructed PAMFinder: lets align() fuse the PAM check (see PAMProcessor.py)
-ACTIVE_PAM = {"finder": None}
 
 
 class BowtieError(Exception):

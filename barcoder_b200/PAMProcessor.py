@@ -13,6 +13,7 @@ frame arrives with `PAM` and `Targeting` already filled (see CRISPRiLibrary._ann
 """
 import re
 
+from ._state import ACTIVE_PAM
 from .seqio import reverse_complement
 
 _STRAND_WORDS = {"+": 1, "1": 1, "+1": 1, "fwd": 1, "forward": 1, "-": -1, "-1": -1, "rev": -1, "reverse": -1}
@@ -70,8 +71,7 @@ class PAMFinder(PAMProcessor):
     def __init__(self, records, pam, direction):
         super().__init__(records, pam, direction)
         self.pam_length = len(pam)
-        from . import BowtieRunner as _runner
-        _runner.ACTIVE_PAM["finder"] = self
+        ACTIVE_PAM["finder"] = self
 
     @property
     def device_checkable(self):

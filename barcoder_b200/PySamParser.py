@@ -12,6 +12,7 @@ with the text reader in samio.py, row by row like the reference does.
 import pandas as pd
 
 from . import samio
+from ._state import RESULTS
 from .ranges import PyRanges
 from .seqio import reverse_complement
 
@@ -45,7 +46,6 @@ class PySamParser:
     @property
     def ranges(self):
         if self._ranges is None:
-            from .BowtieRunner import RESULTS
             runner = RESULTS.get(self.filename)
             df = runner.frame if runner is not None and runner.frame is not None else self._rows_from_text()
             pr = PyRanges(df)

@@ -209,6 +209,10 @@ class Searcher:
             self._check(self._L.bc_copy_hits(self._ctx, out.ctypes.data, len(out)))
         return out
 
+    def hits_into(self, host_ptr, cap_records):
+        """Copy the records into caller-owned host memory (e.g. a pinned buffer)."""
+        self._check(self._L.bc_copy_hits(self._ctx, host_ptr, int(cap_records)))
+
     def hits_device(self):
         ptr, n = ctypes.c_void_p(), ctypes.c_uint64()
         self._check(self._L.bc_hits_device(self._ctx, ctypes.byref(ptr), ctypes.byref(n)))

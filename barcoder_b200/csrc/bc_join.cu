@@ -138,6 +138,49 @@ __global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_consta
             lsv[it] = __ldg(p.dir + wv[it].w);
             lev[it] = i < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
         }
+        // Dense buckets (cfg 4 at b=5: ~300 entries x ~1500 windows per slot): when the whole
+        // warp-tile lies in ONE slot, walk the bucket once and test every entry against all
+        // MV_ITEMS windows of the lane - one broadcast load per MV_ITEMS candidates and
+        // MV_ITEMS independent LOP3/POPC chains per entry.
+        const uint32_t slot0 = __shfl_sync(0xffffffffu, wv[0].w, 0);
+        const bool full_tile = (wt + 1) * wtile <= n_rec;
+        bool uniform = full_tile;
+#pragma unroll
+        for (int it = 0; it < MV_ITEMS; it++) uniform = uniform && (wv[it].w == slot0);
+        if (__all_sync(0xffffffffu, uniform)) {
+            const uint32_t ls = lsv[0], le = lev[0];
+            cand += (unsigned long long)(le - ls) * MV_ITEMS;
+            for (uint32_t e0 = ls; e0 < le; e0 += 32) {
+                const uint32_t e1 = min(e0 + 32, le);
+#pragma unroll 2
+                for (uint32_t e = e0; e < e1; e++) {
+                    const uint2 qq = __ldg(ent + e);
+                    int best = 33;
+#pragma unroll
+                    for (int it = 0; it < MV_ITEMS; it++)
+                        best = min(best, __popc((wv[it].y ^ qq.x) | (wv[it].z ^ qq.y)));
+                    if (best <= k) {
+#pragma unroll
+                        for (int it = 0; it < MV_ITEMS; it++) {
+                            const uint4 w = wv[it];
+                            if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+                        }
+                    }
+                }
+                // drain the queue every 32 entries: at most 32*MV_ITEMS new candidates per lane
+                // group, so the queue (MV_WQ) cannot overflow in the common case
+                __syncwarp();
+                uint32_t nq = min(*qn, (uint32_t)MV_WQ);
+                while (nq >= 32) {
+                    mv_resolve(p, q + (nq - 32), 32);
+                    nq -= 32;
+                }
+                __syncwarp();
+                if (lane == 0) *qn = nq;
+                __syncwarp();
+            }
+            continue;
+        }
 #pragma unroll
         for (int it = 0; it < MV_ITEMS; it++) {
             const uint4 w = wv[it];

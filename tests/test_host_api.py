@@ -1,0 +1,211 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU needed)."""
+import os
+import types
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from barcoder_b200 import (BarCodeLibrary, BowtieError, BowtieRunner, CRISPRiLibrary, GenBankParser, GuideFinder,
+                           PAMFinder, PySamParser, samio, seqio)
+from barcoder_b200.ranges import PyRanges, overlap_pairs
+from oracle import oracle
+
+
+def test_genbank_reader_golden_plasmids(golden_dir, plasmids):
+    assert list(plasmids) == ["CP023716.1", "CP023717.1", "CP023718.1", "CP023719.1"]
+    assert [len(r.seq) for r in plasmids.values()] == [32791, 33006, 36494, 39266]
+    gb = GenBankParser(os.path.join(golden_dir, "zmo_plasmids.gb"))
+    assert set(gb.topologies.values()) == {"circular"}
+    assert gb.overhangs["CP023716.1"] == 100_000
+    assert list(gb.num_genes.values()) == [31, 40, 52, 37]
+    assert gb.seq_lens["CP023719.1"] == 39266
+    assert "Zymomonas" in gb.organisms["CP023716.1"]
+    df = gb.ranges.df
+    assert set(df.columns) == {"Chromosome", "Start", "End", "Strand", "Locus_Tag", "Gene", "Type"}
+    assert (df["Type"] == "source").sum() == 4
+    # origin-spanning gene 36440..284 becomes two parts
+    parts = df[df["Locus_Tag"] == "ZMO1_ZMOp36x053"]
+    assert sorted(zip(parts["Start"], parts["End"])) == [(0, 284), (36439, 36494)]
+    assert gb.find_gene_name_for_locus("ZMO1_ZMOp36x053") == "ZMO1_ZMOp36x053"
+    assert gb.find_gene_name_for_locus("nope") is None
+
+
+def test_genbank_roundtrip_and_locations(tmp_path):
+    rec = seqio.SeqRecord(seqio.Seq("ACGTNNACGT" * 30), id="X1.2", name="X1", description="test contig")
+    rec.annotations.update(topology="linear", organism="Testus maximus")
+    rec.features = [
+        seqio.SeqFeature(seqio.SimpleLocation(0, 300, 1), "source", {"organism": ["Testus maximus"]}),
+        seqio.SeqFeature(seqio.SimpleLocation(9, 50, -1), "gene", {"locus_tag": ["T_1"], "gene": ["abc"]}),
+        seqio.SeqFeature(seqio.CompoundLocation([seqio.SimpleLocation(60, 70, 1), seqio.SimpleLocation(80, 99, 1)]),
+                         "gene", {"locus_tag": ["T_2"]}),
+    ]
+    path = tmp_path / "x.gb"
+    seqio.write_genbank([rec], str(path))
+    back = seqio.genbank_to_dict(str(path))["X1.2"]
+    assert str(back.seq) == str(rec.seq) and back.annotations["topology"] == "linear"
+    assert back.annotations["organism"] == "Testus maximus"
+    g1, g2 = [f for f in back.features if f.type == "gene"]
+    assert (g1.location.start, g1.location.end, g1.location.strand) == (9, 50, -1)
+    assert [(p.start, p.end) for p in g2.location.parts] == [(60, 70), (80, 99)]
+    loc = seqio._parse_location("complement(join(5..10,20..30))")
+    assert [(p.start, p.end, p.strand) for p in loc.parts] == [(19, 30, -1), (4, 10, -1)]
+    assert seqio.Seq("AACG").reverse_complement() == "CGTT"
+
+
+def test_overlap_join_matches_bruteforce():
+    rng = np.random.default_rng(0)
+    a = pd.DataFrame({"Chromosome": rng.choice(["c1", "c2"], 200), "Start": rng.integers(0, 1000, 200)})
+    a["End"] = a["Start"] + rng.integers(1, 40, 200)
+    a["Strand"] = rng.choice(["+", "-"], 200)
+    b = pd.DataFrame({"Chromosome": rng.choice(["c1", "c2", "c3"], 60), "Start": rng.integers(0, 1000, 60)})
+    b["End"] = b["Start"] + rng.integers(1, 300, 60)
+    b["Strand"] = rng.choice(["+", "-"], 60)
+    b["Type"] = "gene"
+    li, ri = overlap_pairs(a, b)
+    want = sorted((i, j) for i in range(200) for j in range(60)
+                  if a.Chromosome[i] == b.Chromosome[j] and a.Start[i] < b.End[j] and b.Start[j] < a.End[i])
+    assert sorted(zip(li.tolist(), ri.tolist())) == want
+    joined = PyRanges(a).join(PyRanges(b)).df
+    assert len(joined) == len(want)
+    assert {"Start_b", "End_b", "Strand_b", "Type"} <= set(joined.columns)
+    same = PyRanges(a).join(PyRanges(b), strandedness="same").df
+    assert (same["Strand"] == same["Strand_b"]).all() and len(same) < len(joined)
+
+
+def test_sam_writer_reader_roundtrip(tmp_path):
+    contigs = ["ACGTACGTAAGGTTTTCCCCGGGGAAAATTTT", "TTTTGGGGACGTACGTAAGG"]
+    runner = types.SimpleNamespace(
+        _reads=["ACGTACGTAA", "CCTTACGTAC", "GGGGGGGGGG"], _contigs=contigs, _contig_ids=["c1", "c2"],
+        _offsets=np.array([0, 32, 52]),
+        hits=np.array([(0, 0, 0, 0), (0, 40, 0b100, (1 << 1)), (1, 0, 0, 1), (1, 40, 0b10000000, 1 | (1 << 1))],
+                      dtype=[("spacer_id", "<u4"), ("gpos", "<u4"), ("mm_mask", "<u4"), ("meta", "<u4")]))
+    path = str(tmp_path / "x.sam")
+    samio.write_sam(path, runner)
+    reads = list(samio.read_sam(path))
+    assert [r.flag for r in reads] == [0, 256, 16, 272, 4]
+    assert reads[0].reference_name == "c1" and reads[0].reference_start == 0 and reads[0].reference_end == 10
+    assert reads[1].get_tag("NM") == 1 and reads[1].get_tag("MD") == "2G7"
+    assert reads[1].get_reference_sequence() == "ACgTACGTAA"
+    assert reads[2].is_reverse and reads[2].query_sequence == "GTACGTAAGG"
+    assert reads[3].get_tag("MD") == "2G7"  # spacer position 7 on '-' is window position 2
+    assert reads[4].is_unmapped and reads[4].reference_name is None and not reads[4].has_tag("NM")
+    df = PySamParser(path).ranges.df
+    assert list(df["Barcode"]) == ["ACGTACGTAA", "ACGTACGTAA", "CCTTACGTAC", "CCTTACGTAC"]
+    assert list(df["Strand"]) == ["+", "+", "-", "-"] and list(df["Start"]) == [0, 8, 0, 8]
+
+
+def test_pam_finder_string_rules(plasmids):
+    recs = {"c": seqio.SeqRecord(seqio.Seq("AAACCCGGGTTTAGGCATCGATCGTTAGCCCTA"), id="c")}
+    pf = PAMFinder(recs, "NGG", "downstream")
+    row = types.SimpleNamespace(Chromosome="c", Start=2, End=12, Strand="+")
+    assert pf.get_pam_seq(row) == "AGG" and pf.pam_matches("AGG")
+    row = types.SimpleNamespace(Chromosome="c", Start=31, End=33, Strand="+")
+    assert pf.get_pam_seq(row) == "" and not pf.pam_matches("")
+    row = types.SimpleNamespace(Chromosome="c", Start=9, End=19, Strand="-")
+    assert pf.get_pam_seq(row) == "CCC" and not pf.pam_matches("CCC")
+    row = types.SimpleNamespace(Chromosome="c", Start=2, End=12, Strand="-")  # negative slice start -> ""
+    assert pf.get_pam_seq(row) == ""
+    up = PAMFinder(recs, "NGG", "upstream")  # same slice as downstream (reference quirk)
+    row = types.SimpleNamespace(Chromosome="c", Start=2, End=12, Strand="+")
+    assert up.get_pam_seq(row) == "AGG"
+    assert not PAMFinder(recs, "NGR", "downstream").pam_matches("AGG")  # R is a literal
+    assert pf.get_strand("fwd") == 1 and pf.get_strand(-1) == -1
+    with pytest.raises(ValueError):
+        pf.get_strand("sideways")
+    for s, (st, en, strand) in {"x": (2, 12, "+"), "y": (9, 19, "-")}.items():
+        got = pf.get_pam_seq(types.SimpleNamespace(Chromosome="c", Start=st, End=en, Strand=strand))
+        assert got == oracle.py_pam_class_api(str(recs["c"].seq), st, en, strand, "NGG")[0]
+
+
+def test_guide_finder():
+    recs = {"c": seqio.SeqRecord(seqio.Seq("TTGGACGTACGTAGGCC"), id="c")}
+    down = GuideFinder(recs, "NGG", "downstream", 5).find_guides_from_pam()
+    # forward matches: TGG@1 (guide 'T', truncated), AGG@12; reverse strand GGCCTACGTACGTCCAA: none with NGG? 'TGG'...
+    fwd = "TTGGACGTACGTAGGCC"
+    import re
+    want = []
+    for text in (fwd, oracle.revcomp(fwd)):
+        for m in re.finditer("[ATCG]GG", text):
+            want.append(text[max(0, m.start() - 5):m.start()])
+    assert down == want and "T" in down
+    up = GuideFinder(recs, "NGG", "upstream", 5).find_guides_from_pam()
+    assert all(len(g) <= 5 for g in up)
+    with pytest.raises(ValueError):
+        GuideFinder(recs, "NGG", "sideways", 5).find_guides_from_pam()
+
+
+def test_barcode_library(tmp_path):
+    tsv = tmp_path / "lib.tsv"
+    tsv.write_text("name\tspacer\nx\tACGT\ny\tACGT\nz\tTTTT\n")
+    lib = BarCodeLibrary(str(tsv), column="spacer")
+    assert lib.barcodes == {"ACGT", "TTTT"} and lib.size == 2
+    fa = tmp_path / "lib.fasta"
+    fa.write_text(">a\nACGT\n>b\nGGGG\nCC\n")
+    assert BarCodeLibrary(str(fa)).barcodes == {"ACGT", "GGGGCC"}
+    lib2 = BarCodeLibrary()
+    lib2.load_from_list(["A", "A", "C"])
+    lib2.add("G")
+    lib2.remove("A")
+    assert lib2.barcodes == {"C", "G"}
+    from barcoder_b200 import BarCodeLibraryError
+    with pytest.raises(BarCodeLibraryError):
+        BarCodeLibrary(str(tsv), column="nope")
+    with pytest.raises(BarCodeLibraryError):
+        BarCodeLibrary(str(tsv))
+    with pytest.raises(BarCodeLibraryError):
+        BarCodeLibrary(str(tmp_path / "lib.txt"))
+
+
+def test_crispri_library_tables():
+    recs = {"c": seqio.SeqRecord(seqio.Seq("A" * 100), id="c")}
+    pf = PAMFinder(recs, "NGG", "downstream")
+    rows = [
+        # barcode b1: one site, source + one gene on '+'
+        dict(Chromosome="c", Start=10, End=30, Mapped=True, Strand="+", Barcode="b1", Mismatches=0, PAM="AGG",
+             Targeting=True, Start_b=0, End_b=100, Strand_b="+", Type="source", Locus_Tag=None, Gene=None),
+        dict(Chromosome="c", Start=10, End=30, Mapped=True, Strand="+", Barcode="b1", Mismatches=0, PAM="AGG",
+             Targeting=True, Start_b=5, End_b=25, Strand_b="+", Type="gene", Locus_Tag="g1", Gene="a"),
+        # barcode b2: two sites -> not source-unique after the first
+        dict(Chromosome="c", Start=40, End=60, Mapped=True, Strand="-", Barcode="b2", Mismatches=1, PAM="TGG",
+             Targeting=True, Start_b=0, End_b=100, Strand_b="+", Type="source", Locus_Tag=None, Gene=None),
+        dict(Chromosome="c", Start=40, End=60, Mapped=True, Strand="-", Barcode="b2", Mismatches=1, PAM="TGG",
+             Targeting=True, Start_b=50, End_b=90, Strand_b="-", Type="gene", Locus_Tag="g2", Gene="b"),
+        dict(Chromosome="c", Start=70, End=90, Mapped=True, Strand="+", Barcode="b2", Mismatches=0, PAM="TTT",
+             Targeting=False, Start_b=50, End_b=90, Strand_b="-", Type="gene", Locus_Tag="g2", Gene="b"),
+    ]
+    df = pd.DataFrame(rows)
+    df.attrs["pam_key"] = ("NGG", "class-api")
+    lib = CRISPRiLibrary(df, pf)
+    assert list(lib.source_unique_targets["Barcode"]) == ["b1", "b2"]
+    mt = lib.mapped_targets
+    assert list(mt["Locus_Tag"]) == ["g1", "g2"]
+    assert list(mt["Offset"]) == [5, 30] and list(mt["Overlap"]) == [15, 10]
+    assert list(lib.unique_targets["Barcode"]) == ["b1", "b2"]
+    assert len(lib.unambiguous_targets) == 2
+    # without fused columns the finder's string functions are used
+    df2 = df.drop(columns=["PAM", "Targeting"])
+    lib2 = CRISPRiLibrary(df2, pf)
+    assert not lib2.targets_df["Targeting"].any()  # the record is all 'A': no NGG anywhere
+
+
+def test_bowtie_runner_call_order_errors(plasmids):
+    with BowtieRunner() as b:
+        with pytest.raises(BowtieError) as ei:
+            b.create_index()
+        assert "fasta_path" in ei.value.message
+        with pytest.raises(BowtieError):
+            b.align(1)
+        b.make_fasta(plasmids)
+        assert os.path.getsize(b.fasta_path) > 140000
+        b.make_fastq(["ACGT", "TTTT"])
+        b.make_fastq(["GGGG"])
+        assert b._reads == ["ACGT", "TTTT", "GGGG"]
+        assert open(b.fastq_path).read().count("\n") == 12
+        assert b.sam_path.endswith(".sam") and b.index_path in b.sam_path
+        import torch
+        if not torch.cuda.is_available():
+            with pytest.raises(BowtieError) as ei:
+                b.create_index()  # no CPU fallback
+            assert ei.value.message == "Failed to index"
+    assert not os.path.exists(b.fasta_path)  # temp dir removed on exit
