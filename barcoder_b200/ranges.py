@@ -20,10 +20,12 @@ class PyRanges:
     def __init__(self, df=None):
         if df is None:
             df = pd.DataFrame(columns=["Chromosome", "Start", "End"])
+        attrs = dict(getattr(df, "attrs", {}))
         df = df.copy()
         if len(df) and "Chromosome" in df.columns:
             df = df[df["Chromosome"].notna()]  # pyranges groups by Chromosome; null keys vanish
         self._df = df.reset_index(drop=True)
+        self._df.attrs.update(attrs)
 
     @property
     def df(self):
@@ -60,7 +62,9 @@ class PyRanges:
         out = a.iloc[left_idx].reset_index(drop=True)
         bb = b.iloc[right_idx].reset_index(drop=True).drop(columns=["Chromosome"])
         bb = bb.rename(columns={c: c + suffix for c in bb.columns if c in out.columns})
-        return PyRanges(pd.concat([out, bb], axis=1))
+        joined = pd.concat([out, bb], axis=1)
+        joined.attrs.update(a.attrs)  # e.g. which PAM the search already evaluated
+        return PyRanges(joined)
 
 
 def overlap_pairs(a, b):

@@ -48,7 +48,7 @@ def frame_rows(df):
 def test_class_api_flow_on_plasmids(golden_dir, cn32_spacers):
     genbank = GenBankParser(os.path.join(golden_dir, "zmo_plasmids.gb"))
     barcodes = BarCodeLibrary()
-    barcodes.load_from_list(cn32_spacers[:3000] + ["ACGTACGTACGTACGTACGTACGTACGTACGT", "acgtnacgtacgtacgtacg"])
+    barcodes.load_from_list(cn32_spacers[-3000:] + ["ACGTACGTACGTACGTACGTACGTACGTACGT", "acgtnacgtacgtacgtacg"])
     pam = PAMFinder(genbank.records, "NGNC", "downstream")
     with BowtieRunner() as bowtie:
         bowtie.make_fasta(genbank.records)
