@@ -91,7 +91,7 @@ static __device__ __noinline__ void mv_resolve(const SearchParams& p, const uint
 // - a single lane walking the slow path (dependent loads of the entry id, contig table and PAM
 // bases) would stall its warp for microseconds, and ncu showed 11.6 active lanes per instruction
 // when it did - they are pushed to a per-warp shared-memory queue and resolved 32 at a time.
-__global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_constant__ SearchParams p,
+__global__ void __launch_bounds__(MV_THREADS, 2) k_merge_verify(const __grid_constant__ SearchParams p,
                                                              const uint4* __restrict__ gwin,
                                                              const uint32_t* __restrict__ n_rec_ptr) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
@@ -152,23 +152,42 @@ __global__ void __launch_bounds__(MV_THREADS) k_merge_verify(const __grid_consta
             cand += (unsigned long long)(le - ls) * MV_ITEMS;
             for (uint32_t e0 = ls; e0 < le; e0 += 32) {
                 const uint32_t e1 = min(e0 + 32, le);
-#pragma unroll 2
-                for (uint32_t e = e0; e < e1; e++) {
-                    const uint2 qq = __ldg(ent + e);
+                uint32_t e = e0;
+                // groups of 4 entries x MV_ITEMS windows: 16 independent LOP3/POPC chains, one
+                // min-reduce and one branch per group
+                for (; e + 4 <= e1; e += 4) {
+                    const uint2 qa = __ldg(ent + e), qb = __ldg(ent + e + 1), qc = __ldg(ent + e + 2),
+                                qd = __ldg(ent + e + 3);
                     int best = 33;
 #pragma unroll
-                    for (int it = 0; it < MV_ITEMS; it++)
-                        best = min(best, __popc((wv[it].y ^ qq.x) | (wv[it].z ^ qq.y)));
+                    for (int it = 0; it < MV_ITEMS; it++) {
+                        const int ca = __popc((wv[it].y ^ qa.x) | (wv[it].z ^ qa.y));
+                        const int cb = __popc((wv[it].y ^ qb.x) | (wv[it].z ^ qb.y));
+                        const int cc = __popc((wv[it].y ^ qc.x) | (wv[it].z ^ qc.y));
+                        const int cd = __popc((wv[it].y ^ qd.x) | (wv[it].z ^ qd.y));
+                        best = min(min(best, ca), min(min(cb, cc), cd));
+                    }
                     if (best <= k) {
+#pragma unroll 1
+                        for (uint32_t j = 0; j < 4; j++) {
+                            const uint2 qq = __ldg(ent + e + j);
 #pragma unroll
-                        for (int it = 0; it < MV_ITEMS; it++) {
-                            const uint4 w = wv[it];
-                            if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+                            for (int it = 0; it < MV_ITEMS; it++) {
+                                const uint4 w = wv[it];
+                                if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e + j, qq);
+                            }
                         }
                     }
                 }
-                // drain the queue every 32 entries: at most 32*MV_ITEMS new candidates per lane
-                // group, so the queue (MV_WQ) cannot overflow in the common case
+                for (; e < e1; e++) {
+                    const uint2 qq = __ldg(ent + e);
+#pragma unroll
+                    for (int it = 0; it < MV_ITEMS; it++) {
+                        const uint4 w = wv[it];
+                        if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+                    }
+                }
+                // drain the queue every 32 entries
                 __syncwarp();
                 uint32_t nq = min(*qn, (uint32_t)MV_WQ);
                 while (nq >= 32) {
