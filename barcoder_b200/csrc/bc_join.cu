@@ -86,14 +86,55 @@ static __device__ __noinline__ void mv_resolve(const SearchParams& p, const uint
     }
 }
 
-// Verify kernel, warp-autonomous (no block barriers): each warp owns warp-tiles of 32*MV_ITEMS
+// Queue full (pathological hit density): resolve one candidate on the spot.
+static __device__ __noinline__ void mv_overflow(const SearchParams& p, uint32_t pos, uint32_t m, uint32_t e,
+                                                uint32_t slot) {
+    uint4 rec;
+    if (bc_make_hit(p, mv_combo_of_slot(p, slot), pos, p.ent_id[e], m, &rec)) {
+        const unsigned long long g = atomicAdd(p.count, 1ull);
+        if (g < p.cap) reinterpret_cast<uint4*>(p.hits)[g] = rec;
+    }
+}
+
+// Verify kernels, warp-autonomous (no block barriers): each warp owns warp-tiles of 32*MV_ITEMS
 // sorted records.  Candidates that pass the popcount filter are NOT resolved where they are found
 // - a single lane walking the slow path (dependent loads of the entry id, contig table and PAM
 // bases) would stall its warp for microseconds, and ncu showed 11.6 active lanes per instruction
 // when it did - they are pushed to a per-warp shared-memory queue and resolved 32 at a time.
-__global__ void __launch_bounds__(MV_THREADS, 2) k_merge_verify(const __grid_constant__ SearchParams p,
-                                                             const uint4* __restrict__ gwin,
-                                                             const uint32_t* __restrict__ n_rec_ptr) {
+//
+// Two instantiations share the record stream (keeps registers and code size down):
+//   DENSE = true   warp-tiles that lie entirely in ONE directory slot (cfg 4 at b=5: ~300 entries
+//                  x ~1500 windows per slot): the bucket is walked once, 4 entries x MV_ITEMS
+//                  windows = 16 independent LOP3/POPC chains per group, one broadcast load per
+//                  MV_ITEMS candidates;
+//   DENSE = false  all other warp-tiles: every lane walks the bucket of each of its records.
+#define MV_CANDIDATE(E, Q)                                                                      \
+    do {                                                                                        \
+        const uint32_t m_ = (w.y ^ (Q).x) | (w.z ^ (Q).y);                                      \
+        const uint32_t qs = atomicAdd(qn, 1u);                                                  \
+        if (qs < MV_WQ) q[qs] = make_uint4(w.x, m_, (E), w.w);                                  \
+        else mv_overflow(p, w.x, m_, (E), w.w);                                                 \
+    } while (0)
+
+// resolve full batches of 32 queued candidates; warp-uniform, called at warp-converged points
+__device__ __forceinline__ void mv_drain(const SearchParams& p, uint4* q, uint32_t* qn, uint32_t lane) {
+    __syncwarp();
+    uint32_t nq = min(*qn, (uint32_t)MV_WQ);
+    if (nq >= 32) {
+        do {
+            mv_resolve(p, q + (nq - 32), 32);
+            nq -= 32;
+        } while (nq >= 32);
+        __syncwarp();
+        if (lane == 0) *qn = nq;
+    }
+    __syncwarp();
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(MV_THREADS, DENSE ? 2 : 3) k_merge_verify(const __grid_constant__ SearchParams p,
+                                                                const uint4* __restrict__ gwin,
+                                                                const uint32_t* __restrict__ n_rec_ptr) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
     __shared__ uint32_t s_qn[MV_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -108,74 +149,41 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_merge_verify(const __grid_con
     const int k = (int)p.k;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
-    // entry E (words Q) of the index is within k mismatches of window w
-#define MV_CANDIDATE(E, Q)                                                                      \
-    do {                                                                                        \
-        const uint32_t m_ = (w.y ^ (Q).x) | (w.z ^ (Q).y);                                      \
-        const uint32_t qs = atomicAdd(qn, 1u);                                                  \
-        if (qs < MV_WQ) q[qs] = make_uint4(w.x, m_, (E), w.w);                                  \
-        else {                                                                                  \
-            uint4 rec_;                                                                         \
-            if (bc_make_hit(p, mv_combo_of_slot(p, w.w), w.x, p.ent_id[(E)], m_, &rec_)) {      \
-                const unsigned long long g_ = atomicAdd(p.count, 1ull);                         \
-                if (g_ < p.cap) reinterpret_cast<uint4*>(p.hits)[g_] = rec_;                    \
-            }                                                                                   \
-        }                                                                                       \
-    } while (0)
     for (uint32_t wt = blockIdx.x * MV_WARPS + warp; wt < n_wtiles; wt += n_warps) {
-        // Issue the loads of all MV_ITEMS records, then of their directory entries, before any
-        // dependent work: three memory latencies per warp-tile instead of three per record.
+        // records are sorted by slot: a full tile is uniform iff its first and last slots agree
+        const uint32_t first = wt * wtile, last = min(first + wtile, n_rec) - 1;
+        const bool uniform = (first + wtile <= n_rec) && (__ldg(&gwin[first].w) == __ldg(&gwin[last].w));
+        if (uniform != DENSE) continue;
         uint4 wv[MV_ITEMS];
-        uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
 #pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) {
-            const uint32_t i = wt * wtile + it * 32 + lane;
-            wv[it] = __ldcs(gwin + min(i, n_rec - 1));
-        }
-#pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) {
-            const uint32_t i = wt * wtile + it * 32 + lane;
-            lsv[it] = __ldg(p.dir + wv[it].w);
-            lev[it] = i < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
-        }
-        // Dense buckets (cfg 4 at b=5: ~300 entries x ~1500 windows per slot): when the whole
-        // warp-tile lies in ONE slot, walk the bucket once and test every entry against all
-        // MV_ITEMS windows of the lane - one broadcast load per MV_ITEMS candidates and
-        // MV_ITEMS independent LOP3/POPC chains per entry.
-        const uint32_t slot0 = __shfl_sync(0xffffffffu, wv[0].w, 0);
-        const bool full_tile = (wt + 1) * wtile <= n_rec;
-        bool uniform = full_tile;
-#pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) uniform = uniform && (wv[it].w == slot0);
-        if (__all_sync(0xffffffffu, uniform)) {
-            const uint32_t ls = lsv[0], le = lev[0];
+        for (int it = 0; it < MV_ITEMS; it++) wv[it] = __ldcs(gwin + min(first + it * 32 + lane, n_rec - 1));
+        if (DENSE) {
+            const uint32_t ls = __ldg(p.dir + wv[0].w), le = __ldg(p.dir + wv[0].w + 1);
             cand += (unsigned long long)(le - ls) * MV_ITEMS;
             for (uint32_t e0 = ls; e0 < le; e0 += 32) {
                 const uint32_t e1 = min(e0 + 32, le);
                 uint32_t e = e0;
-                // groups of 4 entries x MV_ITEMS windows: 16 independent LOP3/POPC chains, one
-                // min-reduce and one branch per group
                 for (; e + 4 <= e1; e += 4) {
                     const uint2 qa = __ldg(ent + e), qb = __ldg(ent + e + 1), qc = __ldg(ent + e + 2),
                                 qd = __ldg(ent + e + 3);
+                    int cnt[MV_ITEMS][4];
                     int best = 33;
 #pragma unroll
                     for (int it = 0; it < MV_ITEMS; it++) {
-                        const int ca = __popc((wv[it].y ^ qa.x) | (wv[it].z ^ qa.y));
-                        const int cb = __popc((wv[it].y ^ qb.x) | (wv[it].z ^ qb.y));
-                        const int cc = __popc((wv[it].y ^ qc.x) | (wv[it].z ^ qc.y));
-                        const int cd = __popc((wv[it].y ^ qd.x) | (wv[it].z ^ qd.y));
-                        best = min(min(best, ca), min(min(cb, cc), cd));
+                        cnt[it][0] = __popc((wv[it].y ^ qa.x) | (wv[it].z ^ qa.y));
+                        cnt[it][1] = __popc((wv[it].y ^ qb.x) | (wv[it].z ^ qb.y));
+                        cnt[it][2] = __popc((wv[it].y ^ qc.x) | (wv[it].z ^ qc.y));
+                        cnt[it][3] = __popc((wv[it].y ^ qd.x) | (wv[it].z ^ qd.y));
+                        best = min(min(best, cnt[it][0]), min(min(cnt[it][1], cnt[it][2]), cnt[it][3]));
                     }
-                    if (best <= k) {
-#pragma unroll 1
-                        for (uint32_t j = 0; j < 4; j++) {
-                            const uint2 qq = __ldg(ent + e + j);
+                    if (best <= k) {  // ~1 group in 4 at cfg-4 density: keep this path short
 #pragma unroll
-                            for (int it = 0; it < MV_ITEMS; it++) {
-                                const uint4 w = wv[it];
-                                if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e + j, qq);
-                            }
+                        for (int it = 0; it < MV_ITEMS; it++) {
+                            const uint4 w = wv[it];
+                            if (cnt[it][0] <= k) MV_CANDIDATE(e, qa);
+                            if (cnt[it][1] <= k) MV_CANDIDATE(e + 1, qb);
+                            if (cnt[it][2] <= k) MV_CANDIDATE(e + 2, qc);
+                            if (cnt[it][3] <= k) MV_CANDIDATE(e + 3, qd);
                         }
                     }
                 }
@@ -187,61 +195,52 @@ __global__ void __launch_bounds__(MV_THREADS, 2) k_merge_verify(const __grid_con
                         if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
                     }
                 }
-                // drain the queue every 32 entries
-                __syncwarp();
-                uint32_t nq = min(*qn, (uint32_t)MV_WQ);
-                while (nq >= 32) {
-                    mv_resolve(p, q + (nq - 32), 32);
-                    nq -= 32;
-                }
-                __syncwarp();
-                if (lane == 0) *qn = nq;
-                __syncwarp();
+                mv_drain(p, q, qn, lane);  // every 32 entries
             }
-            continue;
-        }
+        } else {
+            // Issue the directory loads of all MV_ITEMS records before any dependent work.
+            uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
 #pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) {
-            const uint4 w = wv[it];
-            const uint32_t ls = lsv[it], le = lev[it];
-            cand += le - ls;
-            uint32_t e = ls;
-            // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
-            // candidate is re-examined entry by entry
-            for (; e + 4 <= le; e += 4) {
-                const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
-                            q3 = __ldg(ent + e + 3);
-                const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
-                const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
-                const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
-                const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
-                if (min(min(c0, c1), min(c2, c3)) <= k) {
-                    if (c0 <= k) MV_CANDIDATE(e, q0);
-                    if (c1 <= k) MV_CANDIDATE(e + 1, q1);
-                    if (c2 <= k) MV_CANDIDATE(e + 2, q2);
-                    if (c3 <= k) MV_CANDIDATE(e + 3, q3);
+            for (int it = 0; it < MV_ITEMS; it++) {
+                lsv[it] = __ldg(p.dir + wv[it].w);
+                lev[it] = first + it * 32 + lane < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
+            }
+#pragma unroll
+            for (int it = 0; it < MV_ITEMS; it++) {
+                const uint4 w = wv[it];
+                const uint32_t ls = lsv[it], le = lev[it];
+                cand += le - ls;
+                uint32_t e = ls;
+                // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
+                // candidate is re-examined
+                for (; e + 4 <= le; e += 4) {
+                    const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
+                                q3 = __ldg(ent + e + 3);
+                    const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
+                    const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
+                    const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
+                    const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
+                    if (min(min(c0, c1), min(c2, c3)) <= k) {
+                        if (c0 <= k) MV_CANDIDATE(e, q0);
+                        if (c1 <= k) MV_CANDIDATE(e + 1, q1);
+                        if (c2 <= k) MV_CANDIDATE(e + 2, q2);
+                        if (c3 <= k) MV_CANDIDATE(e + 3, q3);
+                    }
                 }
+                for (; e < le; e++) {
+                    const uint2 qq = __ldg(ent + e);
+                    if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+                }
+                mv_drain(p, q, qn, lane);
             }
-            for (; e < le; e++) {
-                const uint2 qq = __ldg(ent + e);
-                if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
-            }
-            __syncwarp();
-            uint32_t nq = min(*qn, (uint32_t)MV_WQ);  // warp-uniform: written before the syncwarp
-            while (nq >= 32) {
-                mv_resolve(p, q + (nq - 32), 32);
-                nq -= 32;
-            }
-            __syncwarp();
-            if (lane == 0) *qn = nq;
-            __syncwarp();
         }
     }
-#undef MV_CANDIDATE
+    __syncwarp();
     const uint32_t nq = min(*qn, (uint32_t)MV_WQ);
     if (nq) mv_resolve(p, q, nq);
     if (p.count_candidates) atomicAdd(p.count + 1, cand);
 }
+#undef MV_CANDIDATE
 
 // ------------------------------------------------------------------------------------------ host
 bool bc_join_supported(const ComboDesc*, uint32_t n_combos, uint64_t) { return n_combos > 0; }
@@ -333,10 +332,12 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         JCK(cudaGetLastError());
         JCK(cudaEventRecord(ws.ev_a, st));
         // the last directory slot is the end sentinel: after the scan it holds the record count
-        k_merge_verify<<<(uint32_t)sm_count * 8u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
+        k_merge_verify<true><<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
+        JCK(cudaGetLastError());
+        k_merge_verify<false><<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
         JCK(cudaGetLastError());
         JCK(cudaEventRecord(ws.ev_b, st));
-        bc_launch_counter += 3;
+        bc_launch_counter += 4;
         // events are reused per chunk, so read them before the next record
         JCK(cudaEventSynchronize(ws.ev_b));
         float ms = 0;
