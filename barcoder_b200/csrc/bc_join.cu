@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? 2 : 3) k_merge_verify(cons
     const uint32_t wtile = 32 * MV_ITEMS;
     const uint32_t n_wtiles = (n_rec + wtile - 1) / wtile;
     const uint32_t n_warps = gridDim.x * MV_WARPS;
-    const int k = (int)p.k;
+    const int k = (int)p.k, k1 = k + 1;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
     for (uint32_t wt = blockIdx.x * MV_WARPS + warp; wt < n_wtiles; wt += n_warps) {
@@ -166,17 +166,22 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? 2 : 3) k_merge_verify(cons
                 for (; e + 4 <= e1; e += 4) {
                     const uint2 qa = __ldg(ent + e), qb = __ldg(ent + e + 1), qc = __ldg(ent + e + 2),
                                 qd = __ldg(ent + e + 3);
+                    // The 16 results are folded with compare+predicate-OR (ALU pipe, full rate):
+                    // integer min (VIMNMX) measured as slow as POPC itself on sm_100a and capped
+                    // the loop near 55 % of the POPC roofline.
+                    // (count - (k+1)) is negative iff count <= k: OR-ing the differences keeps the
+                    // sign bit of any candidate, with plain IADD/LOP3.
                     int cnt[MV_ITEMS][4];
-                    int best = 33;
+                    int acc = 0;
 #pragma unroll
                     for (int it = 0; it < MV_ITEMS; it++) {
                         cnt[it][0] = __popc((wv[it].y ^ qa.x) | (wv[it].z ^ qa.y));
                         cnt[it][1] = __popc((wv[it].y ^ qb.x) | (wv[it].z ^ qb.y));
                         cnt[it][2] = __popc((wv[it].y ^ qc.x) | (wv[it].z ^ qc.y));
                         cnt[it][3] = __popc((wv[it].y ^ qd.x) | (wv[it].z ^ qd.y));
-                        best = min(min(best, cnt[it][0]), min(min(cnt[it][1], cnt[it][2]), cnt[it][3]));
+                        acc |= (cnt[it][0] - k1) | (cnt[it][1] - k1) | (cnt[it][2] - k1) | (cnt[it][3] - k1);
                     }
-                    if (best <= k) {  // ~1 group in 4 at cfg-4 density: keep this path short
+                    if (acc < 0) {  // ~1 group in 4 at cfg-4 density: keep this path short
 #pragma unroll
                         for (int it = 0; it < MV_ITEMS; it++) {
                             const uint4 w = wv[it];
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? 2 : 3) k_merge_verify(cons
                     const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
                     const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
                     const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
-                    if (min(min(c0, c1), min(c2, c3)) <= k) {
+                    if (((c0 - k1) | (c1 - k1) | (c2 - k1) | (c3 - k1)) < 0) {
                         if (c0 <= k) MV_CANDIDATE(e, q0);
                         if (c1 <= k) MV_CANDIDATE(e + 1, q1);
                         if (c2 <= k) MV_CANDIDATE(e + 2, q2);
