@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbarcoder_b200.so")
+LIB_PATH = os.environ.get("BARCODER_B200_LIB") or os.path.join(_PKG, "libbarcoder_b200.so")
 
 BC_OK = 0
 BC_PAM_IUPAC = 1

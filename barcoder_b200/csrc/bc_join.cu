@@ -57,6 +57,12 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 #define MV_WARPS (MV_THREADS / 32)
 #define MV_ITEMS 4    // records per lane per warp-tile
 #define MV_WQ 128     // per-warp candidate queue (entries)
+#ifndef MV_DENSE_ENTRIES
+#define MV_DENSE_ENTRIES 2    // index entries per group in the dense kernel (2 or 4)
+#endif
+#ifndef MV_DENSE_MINBLOCKS
+#define MV_DENSE_MINBLOCKS 3  // occupancy target of the dense kernel (CTAs per SM)
+#endif
 
 __device__ __forceinline__ uint32_t mv_combo_of_slot(const SearchParams& p, uint32_t slot) {
     uint32_t c = 0;
@@ -116,6 +122,13 @@ static __device__ __noinline__ void mv_overflow(const SearchParams& p, uint32_t 
         else mv_overflow(p, w.x, m_, (E), w.w);                                                 \
     } while (0)
 
+// rare path of the dense kernel: re-test one window against the two entries of a group
+static __device__ __noinline__ void mv_dense_candidates(const SearchParams& p, uint4* q, uint32_t* qn, const uint4 w,
+                                                        const uint2 qa, const uint2 qb, uint32_t e, int k) {
+    if (__popc((w.y ^ qa.x) | (w.z ^ qa.y)) <= k) MV_CANDIDATE(e, qa);
+    if (__popc((w.y ^ qb.x) | (w.z ^ qb.y)) <= k) MV_CANDIDATE(e + 1, qb);
+}
+
 // resolve full batches of 32 queued candidates; warp-uniform, called at warp-converged points
 __device__ __forceinline__ void mv_drain(const SearchParams& p, uint4* q, uint32_t* qn, uint32_t lane) {
     __syncwarp();
@@ -132,7 +145,7 @@ __device__ __forceinline__ void mv_drain(const SearchParams& p, uint4* q, uint32
 }
 
 template <bool DENSE>
-__global__ void __launch_bounds__(MV_THREADS, DENSE ? 2 : 3) k_merge_verify(const __grid_constant__ SearchParams p,
+__global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_merge_verify(const __grid_constant__ SearchParams p,
                                                                 const uint4* __restrict__ gwin,
                                                                 const uint32_t* __restrict__ n_rec_ptr) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
@@ -163,32 +176,31 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? 2 : 3) k_merge_verify(cons
             for (uint32_t e0 = ls; e0 < le; e0 += 32) {
                 const uint32_t e1 = min(e0 + 32, le);
                 uint32_t e = e0;
-                for (; e + 4 <= e1; e += 4) {
-                    const uint2 qa = __ldg(ent + e), qb = __ldg(ent + e + 1), qc = __ldg(ent + e + 2),
-                                qd = __ldg(ent + e + 3);
-                    // The 16 results are folded with compare+predicate-OR (ALU pipe, full rate):
-                    // integer min (VIMNMX) measured as slow as POPC itself on sm_100a and capped
-                    // the loop near 55 % of the POPC roofline.
+                for (; e + MV_DENSE_ENTRIES <= e1; e += MV_DENSE_ENTRIES) {
+                    uint2 qe[MV_DENSE_ENTRIES];
+#pragma unroll
+                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) qe[j] = __ldg(ent + e + j);
                     // (count - (k+1)) is negative iff count <= k: OR-ing the differences keeps the
-                    // sign bit of any candidate, with plain IADD/LOP3.
-                    int cnt[MV_ITEMS][4];
+                    // sign bit of any candidate with plain IADD/LOP3.  At cfg-4 density about one
+                    // group in ten contains a candidate in SOME lane, so the follow-up must stay
+                    // short and inline: one compare+branch per count, a queue push where it fires.
+                    int d[MV_ITEMS][MV_DENSE_ENTRIES];
                     int acc = 0;
 #pragma unroll
                     for (int it = 0; it < MV_ITEMS; it++) {
-                        cnt[it][0] = __popc((wv[it].y ^ qa.x) | (wv[it].z ^ qa.y));
-                        cnt[it][1] = __popc((wv[it].y ^ qb.x) | (wv[it].z ^ qb.y));
-                        cnt[it][2] = __popc((wv[it].y ^ qc.x) | (wv[it].z ^ qc.y));
-                        cnt[it][3] = __popc((wv[it].y ^ qd.x) | (wv[it].z ^ qd.y));
-                        acc |= (cnt[it][0] - k1) | (cnt[it][1] - k1) | (cnt[it][2] - k1) | (cnt[it][3] - k1);
+#pragma unroll
+                        for (int j = 0; j < MV_DENSE_ENTRIES; j++) {
+                            d[it][j] = __popc((wv[it].y ^ qe[j].x) | (wv[it].z ^ qe[j].y)) - k1;
+                            acc |= d[it][j];
+                        }
                     }
-                    if (acc < 0) {  // ~1 group in 4 at cfg-4 density: keep this path short
+                    if (acc < 0) {
 #pragma unroll
                         for (int it = 0; it < MV_ITEMS; it++) {
                             const uint4 w = wv[it];
-                            if (cnt[it][0] <= k) MV_CANDIDATE(e, qa);
-                            if (cnt[it][1] <= k) MV_CANDIDATE(e + 1, qb);
-                            if (cnt[it][2] <= k) MV_CANDIDATE(e + 2, qc);
-                            if (cnt[it][3] <= k) MV_CANDIDATE(e + 3, qd);
+#pragma unroll
+                            for (int j = 0; j < MV_DENSE_ENTRIES; j++)
+                                if (d[it][j] < 0) MV_CANDIDATE(e + j, qe[j]);
                         }
                     }
                 }
@@ -337,7 +349,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         JCK(cudaGetLastError());
         JCK(cudaEventRecord(ws.ev_a, st));
         // the last directory slot is the end sentinel: after the scan it holds the record count
-        k_merge_verify<true><<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
+        k_merge_verify<true><<<(uint32_t)sm_count * 8u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
         JCK(cudaGetLastError());
         k_merge_verify<false><<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
         JCK(cudaGetLastError());

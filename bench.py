@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 probe, 2 join")
     ap.add_argument("--blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel experiments only)")
     ap.add_argument("--verify", action="store_true", help="check a sample of the result against the oracle")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -304,14 +305,17 @@ def main():
     st = s.stats()
 
     # ---- end-to-end arm: host buffers in, host records out
-    e2e_steps = max(2, min(args.steps, 3))
-    step_e2e()
+    e2e_steps = max(2, min(args.steps, 3)) if not args.no_e2e else 0
+    nh_e2e = 0
+    if e2e_steps:
+        step_e2e()
     barrier()
     ev0.record()
     for _ in range(e2e_steps):
         nh_e2e, out = step_e2e()
     ev1.record()
     barrier()
+    e2e_steps = max(e2e_steps, 1)
     ms_e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
