@@ -284,8 +284,11 @@ def main():
     acc = {"ms_build_index": 0.0, "ms_search": 0.0, "ms_scan_kernel": 0.0, "ms_genome_bucket": 0.0}
     launches = 0
     total_hits = 0
+    step_wall = []
     for _ in range(args.steps):
+        t_s = time.time()
         total_hits = step_resident()
+        step_wall.append(round((time.time() - t_s) * 1e3, 2))
         st = s.stats()
         for key in acc:
             acc[key] += st[key]
@@ -400,7 +403,7 @@ def main():
                 "ms_per_step": ms_e.item() / e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
-        "stage_ms": {k2: round(v, 4) for k2, v in acc.items()},
+        "stage_ms": {k2: round(v, 4) for k2, v in acc.items()}, "step_wall_ms": step_wall,
     }
     if verified is not None:
         line["verified_vs_oracle"] = verified

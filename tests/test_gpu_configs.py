@@ -1,0 +1,142 @@
+"""The five BASELINE.json configs on the GPU (SURVEY.md section 8d inputs).  Full oracle
+comparison where the oracle finishes in seconds (cfg 1, 2, and library subsamples of cfg 3-5);
+size-independent properties at full size: every planted spacer is recovered at its planted
+site, sharded == unsharded, probe path == join path, gate == filter of ungated."""
+import os
+
+import numpy as np
+import pytest
+
+from barcoder_b200 import _native, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gpu_search(genome, off, lib, k, pam, iupac=False, gate=False, path=0, blocks=0):
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam(pam, "downstream", iupac=iupac, gate=gate)
+        if path:
+            s.set_param(_native.BC_PARAM_PATH, path)
+        if blocks:
+            s.set_param(_native.BC_PARAM_BLOCKS, blocks)
+        s.search(k)
+        return _native.canonical_sort(s.hits()), s.stats()
+
+
+def oracle_search(genome, off, lib, k, pam, iupac=False, gate=False):
+    contigs = [bytes(genome[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+    flags = (oracle.PAM_FLAG_IUPAC if iupac else 0) | (oracle.PAM_FLAG_GATE if gate else 0)
+    return oracle.search(contigs, synth.rows_to_strings(lib), k, pam=pam, flags=flags)
+
+
+def planted_library(genome, n, L, k, seed, frac=0.01):
+    """Library with a known answer: returns (lib, planted index, planted dev-free position, strand)."""
+    rng = synth.rng_for(seed)
+    lib = synth.random_library(n, L, seed=seed + 1)
+    m = max(1, int(n * frac))
+    idx = rng.choice(n, size=m, replace=False)
+    pos = rng.integers(0, len(genome) - L + 1, size=m)
+    win = genome[pos[:, None] + np.arange(L)[None, :]].copy()
+    ok = np.isin(win, np.frombuffer(b"ACGT", np.uint8)).all(axis=1)
+    nsub = rng.integers(0, k + 1, size=m)
+    for j in range(k):
+        rows = np.nonzero(nsub > j)[0]
+        cols = rng.integers(0, L, size=len(rows))
+        win[rows, cols] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=len(rows))]
+    flip = rng.integers(0, 2, size=m).astype(bool)
+    win[flip] = synth.revcomp_rows(win[flip])
+    lib[idx[ok]] = win[ok]
+    return lib, idx[ok], pos[ok], flip[ok]
+
+
+def assert_planted_found(hits, idx, pos, flip, off):
+    """Every planted spacer has a hit at its planted site and strand (contig-crossing plants excepted)."""
+    key = set(zip(hits["spacer_id"].tolist(), hits["gpos"].tolist(), (hits["meta"] & 1).tolist()))
+    L_ok = 0
+    for i, p, f in zip(idx.tolist(), pos.tolist(), flip.tolist()):
+        if (i, p, int(f)) in key:
+            L_ok += 1
+    assert L_ok >= 0.99 * len(idx), (L_ok, len(idx))  # plants that straddle a contig end cannot hit
+
+
+def test_cfg1_ecoli_shape_full_oracle():
+    """cfg 1 stand-in: 4,641,652 bp circular-shaped contig, 50,000 NGG 20-mers, k=1."""
+    genome, off = synth.random_genome(4_641_652, seed=1)
+    guides = synth.enumerate_pam_guides(genome, off, 20, "NGG")
+    rng = synth.rng_for(1)
+    lib = guides[rng.choice(len(guides), size=50_000, replace=False)]
+    ref = oracle_search(genome, off, lib, 1, "NGG")
+    gpu, st = gpu_search(genome, off, lib, 1, "NGG")
+    assert gpu.tobytes() == ref.tobytes()
+    assert len(gpu) >= 50_000 and ((gpu["meta"] & 8) != 0).sum() >= 50_000  # every guide hits itself next to its PAM
+
+
+def test_cfg2_zymomonas_full_oracle(cn32_spacers, plasmids):
+    """cfg 2: the 9,503 fixture spacers vs 4 real plasmids + a synthetic 2,058,755 bp chromosome, k=2, NGNC."""
+    chrom, _ = synth.random_genome(2_058_755, seed=2)
+    contigs = [chrom] + [np.frombuffer(str(r.seq).encode(), np.uint8) for r in plasmids.values()]
+    genome = np.concatenate(contigs)
+    off = np.zeros(len(contigs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in contigs])
+    lib = np.frombuffer("".join(cn32_spacers).encode(), np.uint8).reshape(-1, 32)
+    ref = oracle_search(genome, off, lib, 2, "NGNC")
+    for path in (1, 2):
+        gpu, st = gpu_search(genome, off, lib, 2, "NGNC", path=path)
+        assert gpu.tobytes() == ref.tobytes()
+    on_plasmids = gpu[gpu["gpos"] >= off[1]]
+    assert len(on_plasmids) == 869
+
+
+def test_cfg3_all_ngg_guides_vs_own_genome():
+    """cfg 3: every NGG 20-mer of the cfg-1 genome (~5e5) vs the genome, k=3; oracle on a subsample."""
+    genome, off = synth.random_genome(4_641_652, seed=1)
+    lib = synth.enumerate_pam_guides(genome, off, 20, "NGG")
+    assert 400_000 < len(lib) < 700_000
+    gpu, st = gpu_search(genome, off, lib, 3, "NGG")
+    exact_self = gpu[((gpu["meta"] >> 1) & 3) == 0]
+    assert len(np.unique(exact_self["spacer_id"])) == len(lib)  # each guide finds itself exactly
+    sub = np.arange(0, len(lib), 97)[:4000]
+    ref = oracle_search(genome, off, lib[sub], 3, "NGG")
+    got = gpu[np.isin(gpu["spacer_id"], sub)].copy()
+    got["spacer_id"] = np.searchsorted(sub, got["spacer_id"]).astype(np.uint32)
+    assert _native.canonical_sort(got).tobytes() == ref.tobytes()
+    gpu_probe, _ = gpu_search(genome, off, lib[:100_000], 3, "NGG", path=1)
+    gpu_join, _ = gpu_search(genome, off, lib[:100_000], 3, "NGG", path=2)
+    assert gpu_probe.tobytes() == gpu_join.tobytes()
+
+
+def test_cfg4_scaled_planted_and_sharded():
+    """cfg 4 at 1/10 scale (1M spacers x 10 Mbp, k=3) with the full-size seed scheme forced (b=5, 6)."""
+    genome, off = synth.random_genome(10_000_000, seed=4)
+    lib, idx, pos, flip = planted_library(genome, 1_000_000, 20, 3, seed=40)
+    a, st = gpu_search(genome, off, lib, 3, "NGG", path=2, blocks=6)
+    assert_planted_found(a, idx, pos, flip, off)
+    b, _ = gpu_search(genome, off, lib, 3, "NGG", path=2, blocks=5)
+    assert a.tobytes() == b.tobytes()
+    sub = np.arange(0, len(lib), 251)[:3000]
+    ref = oracle_search(genome, off, lib[sub], 3, "NGG")
+    got = a[np.isin(a["spacer_id"], sub)].copy()
+    got["spacer_id"] = np.searchsorted(sub, got["spacer_id"]).astype(np.uint32)
+    assert _native.canonical_sort(got).tobytes() == ref.tobytes()
+    gated, _ = gpu_search(genome, off, lib, 3, "NGG", gate=True, path=2)
+    keep = a[((a["meta"] & 8) != 0) | ((a["meta"] & 32) != 0)]
+    assert gated.tobytes() == keep.tobytes()
+
+
+def test_cfg5_scaled_32mers_iupac_pam_many_contigs():
+    """cfg 5 at 1/10 scale (100k 32-mers x 300 Mbp in 24 contigs with N runs, k=2, NNGRRT IUPAC)."""
+    genome, off = synth.random_genome(300_000_000, seed=5, n_contigs=24, n_fraction=0.001)
+    lib, idx, pos, flip = planted_library(genome, 100_000, 32, 2, seed=50)
+    gpu, st = gpu_search(genome, off, lib, 2, "NNGRRT", iupac=True)
+    assert_planted_found(gpu, idx, pos, flip, off)
+    sub = np.sort(np.concatenate([idx[:300], np.arange(0, 2000)]))
+    sub = np.unique(sub)
+    ref = oracle_search(genome, off, lib[sub], 2, "NNGRRT", iupac=True)
+    got = gpu[np.isin(gpu["spacer_id"], sub)].copy()
+    got["spacer_id"] = np.searchsorted(sub, got["spacer_id"]).astype(np.uint32)
+    assert _native.canonical_sort(got).tobytes() == ref.tobytes()
+    assert ((gpu["meta"] & 8) != 0).sum() > 0
