@@ -47,6 +47,8 @@ struct bc_ctx {
     uint64_t dir_slots = 0;
     uint32_t *d_dir = nullptr, *d_cursor = nullptr, *d_scan_tmp = nullptr, *d_ent_id = nullptr;
     uint2* d_ent_hl = nullptr;
+    uint4* d_ent_tmp = nullptr;       // level-1 (coarse) output of the index scatter
+    uint32_t* d_coarse_cursor = nullptr;
     uint64_t ent_cap = 0, dir_cap = 0, scan_tmp_cap = 0;
 
     // join workspace
@@ -127,6 +129,7 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B); dfree(ctx->d_start_dev);
     dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn); dfree(ctx->d_any_n);
     dfree(ctx->d_dir); dfree(ctx->d_cursor); dfree(ctx->d_scan_tmp); dfree(ctx->d_ent_id); dfree(ctx->d_ent_hl);
+    dfree(ctx->d_ent_tmp); dfree(ctx->d_coarse_cursor);
     dfree(ctx->d_hits); dfree(ctx->d_count);
     bc_join_free(ctx->join);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -420,10 +423,11 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     const uint64_t ent_needed = E * s.n_combos;
     if (ent_needed >= (1ull << 32)) return fail(ctx, BC_ELIMIT, "library x combinations exceeds 2^32 index entries");
     if (ent_needed > ctx->ent_cap) {
-        dfree(ctx->d_ent_hl); dfree(ctx->d_ent_id);
+        dfree(ctx->d_ent_hl); dfree(ctx->d_ent_id); dfree(ctx->d_ent_tmp);
         ctx->ent_cap = 0;
         CK(cudaMalloc(&ctx->d_ent_hl, (ent_needed + 1) * sizeof(uint2)));
         CK(cudaMalloc(&ctx->d_ent_id, (ent_needed + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_ent_tmp, (ent_needed + 1) * sizeof(uint4)));
         ctx->ent_cap = ent_needed;
     }
     if (s.dir_slots > ctx->dir_cap) {
@@ -448,8 +452,9 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     memcpy(ip.combo, ctx->combo, sizeof ip.combo);
     const uint32_t launches0 = bc_launch_counter;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_hl,
-                             ctx->d_ent_id, ctx->sm_count, ctx->stream));
+    if (!ctx->d_coarse_cursor) CK(cudaMalloc(&ctx->d_coarse_cursor, ((size_t)BC_MAX_COMBOS << BC_COARSE_BITS) * 4 + 4));
+    CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_tmp,
+                             ctx->d_coarse_cursor, ctx->d_ent_hl, ctx->d_ent_id, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev0, ctx->ev1));

@@ -35,9 +35,11 @@ struct BucketParams {
 // are dropped here, so pass 2 never sees them.
 template <int PASS>
 __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketParams gp,
+                                                const __grid_constant__ CoarsePlan pl,
                                                 uint32_t* __restrict__ gdir_or_cursor, uint4* __restrict__ gwin) {
     const uint32_t lm = bc_lmask(gp.L);
-    const ComboDesc& cd = gp.combo[blockIdx.y];
+    const uint32_t c = blockIdx.y;
+    const ComboDesc& cd = gp.combo[c];
     for (uint32_t pos = gp.pos_begin + blockIdx.x * blockDim.x + threadIdx.x; pos < gp.pos_end;
          pos += gridDim.x * blockDim.x) {
         if (bc_window(gp.B, pos) & lm) continue;
@@ -47,8 +49,9 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
         if (PASS == 0) {
             atomicAdd(&gdir_or_cursor[slot], 1u);
         } else {
-            const uint32_t dst = atomicAdd(&gdir_or_cursor[slot], 1u);
-            __stcs(&gwin[dst], make_uint4(pos, wh, wl, slot));  // streaming: keep the directory in L2
+            // level 1 of the two-level scatter (bc_kernels.h): coarse partition, few open lines
+            const uint32_t dst = atomicAdd(&gdir_or_cursor[bc_coarse_of(pl, c, slot)], 1u);
+            gwin[dst] = make_uint4(pos, wh, wl, slot);
         }
     }
 }
@@ -266,6 +269,8 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_gdir) cudaFree(ws.d_gdir);
     if (ws.d_gcursor) cudaFree(ws.d_gcursor);
     if (ws.d_gwin) cudaFree(ws.d_gwin);
+    if (ws.d_gtmp) cudaFree(ws.d_gtmp);
+    if (ws.d_coarse_cursor) cudaFree(ws.d_coarse_cursor);
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
@@ -290,18 +295,20 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     // chunk the genome so the window records stay within the workspace budget
     size_t free_b = 0, total_b = 0;
     JCK(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t budget = ((uint64_t)free_b + ws.gwin_cap * sizeof(uint4)) / 2;
-    if (budget > (64ull << 30)) budget = 64ull << 30;
-    uint64_t chunk = budget / sizeof(uint4) / p.n_combos;
+    uint64_t budget = ((uint64_t)free_b + 2 * ws.gwin_cap * sizeof(uint4)) / 2;
+    if (budget > (96ull << 30)) budget = 96ull << 30;
+    uint64_t chunk = budget / (2 * sizeof(uint4)) / p.n_combos;  // two record arrays (coarse + final)
     if (chunk > p.n_pos) chunk = p.n_pos;
     if (chunk < 1) chunk = 1;
     if (chunk * p.n_combos >= (1ull << 32)) chunk = ((1ull << 32) - 1) / p.n_combos;  // 32-bit record indices
     const uint64_t rec_needed = chunk * p.n_combos;
     if (rec_needed > ws.gwin_cap) {
         if (ws.d_gwin) cudaFree(ws.d_gwin);
-        ws.d_gwin = nullptr;
+        if (ws.d_gtmp) cudaFree(ws.d_gtmp);
+        ws.d_gwin = ws.d_gtmp = nullptr;
         ws.gwin_cap = 0;
         JCK(cudaMalloc(&ws.d_gwin, (chunk * p.n_combos + 1) * sizeof(uint4)));
+        JCK(cudaMalloc(&ws.d_gtmp, (chunk * p.n_combos + 1) * sizeof(uint4)));
         ws.gwin_cap = chunk * p.n_combos;
     }
     if (dir_slots > ws.gdir_cap) {
@@ -321,6 +328,9 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         JCK(cudaMalloc(&ws.d_scan_tmp, tmp_words * 4));
         ws.scan_tmp_cap = tmp_words;
     }
+    if (!ws.d_coarse_cursor) JCK(cudaMalloc(&ws.d_coarse_cursor, ((size_t)BC_MAX_COMBOS << BC_COARSE_BITS) * 4 + 4));
+    CoarsePlan pl;
+    bc_make_coarse_plan(p.combo, p.n_combos, &pl);
     BucketParams gp;
     memset(&gp, 0, sizeof gp);
     gp.H = p.H; gp.Lo = p.Lo; gp.B = p.B;
@@ -341,12 +351,15 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         dim3 grid(gx, p.n_combos);
         JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
         JCK(cudaEventRecord(ws.ev_c, st));
-        k_bucket<0><<<grid, 256, 0, st>>>(gp, ws.d_gdir, nullptr);
+        k_bucket<0><<<grid, 256, 0, st>>>(gp, pl, ws.d_gdir, nullptr);
         JCK(cudaGetLastError());
         JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
         JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
-        k_bucket<1><<<grid, 256, 0, st>>>(gp, ws.d_gcursor, ws.d_gwin);
+        JCK(bc_launch_coarse_init(pl, ws.d_gdir, ws.d_coarse_cursor, st));
+        k_bucket<1><<<grid, 256, 0, st>>>(gp, pl, ws.d_coarse_cursor, ws.d_gtmp);
         JCK(cudaGetLastError());
+        JCK(bc_launch_fine_scatter(0, ws.d_gtmp, ws.d_gdir + (dir_slots - 1), ws.d_gcursor, ws.d_gwin, nullptr, nullptr,
+                                   sm_count, st));
         JCK(cudaEventRecord(ws.ev_a, st));
         // the last directory slot is the end sentinel: after the scan it holds the record count
         k_merge_verify<true><<<(uint32_t)sm_count * 8u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));

@@ -2,6 +2,8 @@
 // and the probe scan (K3-probe).  The bucket-join scan lives in bc_join.cu.
 #include "bc_kernels.h"
 
+#include <string.h>
+
 thread_local uint32_t bc_launch_counter = 0;
 
 // ------------------------------------------------------------------------------------------ K1
@@ -99,20 +101,105 @@ __global__ void __launch_bounds__(256) k_index_count(IndexParams ip, uint32_t* _
     }
 }
 
-__global__ void __launch_bounds__(256) k_index_scatter(IndexParams ip, uint32_t* __restrict__ cursor,
-                                                       uint2* __restrict__ ent_hl, uint32_t* __restrict__ ent_id) {
-    const ComboDesc cd = ip.combo[blockIdx.y];
+__global__ void __launch_bounds__(256) k_index_scatter(IndexParams ip, const __grid_constant__ CoarsePlan pl,
+                                                       uint32_t* __restrict__ coarse_cursor,
+                                                       uint4* __restrict__ tmp) {
+    const uint32_t c = blockIdx.y;
+    const ComboDesc cd = ip.combo[c];
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ip.n_entries; e += gridDim.x * blockDim.x) {
         if (ip.lib_has_n) {
             uint32_t nm = ip.sn[e >> 1];
             if (e & 1u) nm = bc_rev_bits(nm, ip.L);
             if (nm & cd.key_mask) continue;
         }
-        uint32_t h = ip.qh[e], l = ip.ql[e];
-        uint32_t slot = atomicAdd(&cursor[cd.dir_off + bc_combo_key(cd, h, l)], 1u);
-        ent_hl[slot] = make_uint2(h, l);
-        ent_id[slot] = e;
+        const uint32_t h = ip.qh[e], l = ip.ql[e];
+        const uint32_t slot = cd.dir_off + bc_combo_key(cd, h, l);
+        const uint32_t dst = atomicAdd(&coarse_cursor[bc_coarse_of(pl, c, slot)], 1u);
+        tmp[dst] = make_uint4(h, l, e, slot);
     }
+}
+
+// ------------------------------------------------------------------------- two-level scatter
+void bc_make_coarse_plan(const ComboDesc* combo, uint32_t n_combos, CoarsePlan* pl) {
+    memset(pl, 0, sizeof *pl);
+    pl->n_combos = n_combos;
+    uint32_t coarse = 0;
+    for (uint32_t c = 0; c < n_combos; c++) {
+        const uint32_t kb = 2u * combo[c].key_nt;
+        pl->shift[c] = kb > BC_COARSE_BITS ? kb - BC_COARSE_BITS : 0;
+        pl->coarse_off[c] = coarse;
+        pl->dir_off[c] = combo[c].dir_off;
+        coarse += 1u << (kb - pl->shift[c]);
+    }
+    pl->coarse_off[n_combos] = coarse;
+    pl->dir_off[n_combos] = n_combos ? combo[n_combos - 1].dir_off + (1u << (2u * combo[n_combos - 1].key_nt)) : 0;
+    pl->n_coarse = coarse;
+}
+
+__global__ void __launch_bounds__(256) k_coarse_init(const __grid_constant__ CoarsePlan pl,
+                                                     const uint32_t* __restrict__ fine_dir,
+                                                     uint32_t* __restrict__ coarse_cursor) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= pl.n_coarse) return;
+    uint32_t c = 0;
+    while (c + 1 < pl.n_combos && pl.coarse_off[c + 1] <= j) c++;
+    coarse_cursor[j] = fine_dir[pl.dir_off[c] + ((j - pl.coarse_off[c]) << pl.shift[c])];
+}
+
+cudaError_t bc_launch_coarse_init(const CoarsePlan& pl, const uint32_t* fine_dir, uint32_t* coarse_cursor,
+                                  cudaStream_t st) {
+    if (pl.n_coarse == 0) return cudaSuccess;
+    k_coarse_init<<<(pl.n_coarse + 255) / 256, 256, 0, st>>>(pl, fine_dir, coarse_cursor);
+    bc_launch_counter += 1;
+    return cudaGetLastError();
+}
+
+#define FS_THREADS 256
+#define FS_ITEMS 8
+template <int MODE>
+__global__ void __launch_bounds__(FS_THREADS) k_fine_scatter(const uint4* __restrict__ tmp,
+                                                             const uint32_t* __restrict__ n_rec_ptr,
+                                                             uint32_t* __restrict__ fine_cursor,
+                                                             uint4* __restrict__ out_rec, uint2* __restrict__ out_hl,
+                                                             uint32_t* __restrict__ out_id) {
+    const uint32_t n_rec = *n_rec_ptr;
+    const uint32_t chunk = FS_THREADS * FS_ITEMS;
+    const uint32_t n_chunks = (n_rec + chunk - 1) / chunk;
+    for (uint32_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        uint4 rec[FS_ITEMS];
+        uint32_t dst[FS_ITEMS];
+#pragma unroll
+        for (int it = 0; it < FS_ITEMS; it++) {
+            const uint32_t i = ch * chunk + it * FS_THREADS + threadIdx.x;
+            if (i < n_rec) rec[it] = __ldcs(tmp + i);
+        }
+#pragma unroll
+        for (int it = 0; it < FS_ITEMS; it++) {
+            const uint32_t i = ch * chunk + it * FS_THREADS + threadIdx.x;
+            if (i < n_rec) dst[it] = atomicAdd(&fine_cursor[rec[it].w], 1u);
+        }
+#pragma unroll
+        for (int it = 0; it < FS_ITEMS; it++) {
+            const uint32_t i = ch * chunk + it * FS_THREADS + threadIdx.x;
+            if (i < n_rec) {
+                if (MODE == 0) {
+                    out_rec[dst[it]] = rec[it];
+                } else {
+                    out_hl[dst[it]] = make_uint2(rec[it].x, rec[it].y);
+                    out_id[dst[it]] = rec[it].z;
+                }
+            }
+        }
+    }
+}
+
+cudaError_t bc_launch_fine_scatter(int mode, const uint4* tmp, const uint32_t* n_rec_ptr, uint32_t* fine_cursor,
+                                   uint4* out_rec, uint2* out_hl, uint32_t* out_id, int sm_count, cudaStream_t st) {
+    const uint32_t grid = (uint32_t)sm_count * 4u;
+    if (mode == 0) k_fine_scatter<0><<<grid, FS_THREADS, 0, st>>>(tmp, n_rec_ptr, fine_cursor, out_rec, out_hl, out_id);
+    else k_fine_scatter<1><<<grid, FS_THREADS, 0, st>>>(tmp, n_rec_ptr, fine_cursor, out_rec, out_hl, out_id);
+    bc_launch_counter += 1;
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------- prefix scan
@@ -293,8 +380,8 @@ cudaError_t bc_launch_pack_library(const uint8_t* d_ascii, uint32_t n, uint32_t 
 }
 
 cudaError_t bc_launch_index_build(const IndexParams& ip, uint32_t n_combos, uint32_t* d_dir, uint64_t dir_slots,
-                                  uint32_t* d_cursor, uint32_t* d_scan_tmp, uint2* ent_hl, uint32_t* ent_id,
-                                  int sm_count, cudaStream_t st) {
+                                  uint32_t* d_cursor, uint32_t* d_scan_tmp, uint4* ent_tmp, uint32_t* coarse_cursor,
+                                  uint2* ent_hl, uint32_t* ent_id, int sm_count, cudaStream_t st) {
     cudaError_t err = cudaMemsetAsync(d_dir, 0, dir_slots * sizeof(uint32_t), st);
     if (err != cudaSuccess) return err;
     if (ip.n_entries == 0) return cudaSuccess;
@@ -307,7 +394,12 @@ cudaError_t bc_launch_index_build(const IndexParams& ip, uint32_t n_combos, uint
     if ((err = bc_exclusive_scan(d_dir, dir_slots, d_scan_tmp, st)) != cudaSuccess) return err;
     err = cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
     if (err != cudaSuccess) return err;
-    k_index_scatter<<<grid, 256, 0, st>>>(ip, d_cursor, ent_hl, ent_id);
+    CoarsePlan pl;
+    bc_make_coarse_plan(ip.combo, n_combos, &pl);
+    if ((err = bc_launch_coarse_init(pl, d_dir, coarse_cursor, st)) != cudaSuccess) return err;
+    k_index_scatter<<<grid, 256, 0, st>>>(ip, pl, coarse_cursor, ent_tmp);
     bc_launch_counter += 2;
-    return cudaGetLastError();
+    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    // the directory's end sentinel holds the number of indexed entries after the scan
+    return bc_launch_fine_scatter(1, ent_tmp, d_dir + (dir_slots - 1), d_cursor, nullptr, ent_hl, ent_id, sm_count, st);
 }
