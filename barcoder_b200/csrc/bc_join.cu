@@ -33,6 +33,14 @@ struct BucketParams {
 
 // Pass 1.  PASS 0 counts, PASS 1 scatters.  Windows touching a non-ACGT base or a contig end
 // are dropped here, so pass 2 never sees them.
+// Pass 1 variants: PASS 0 counts (RED), PASS 1 scatters straight to the final slot (one returning
+// atomic per record), PASS 2 scatters to a coarse partition (level 1 of the two-level scatter in
+// bc_kernels.h; level 2 is k_fine_scatter).  Measured on cfg 4, b=6 (2e9 records): count 9 ms;
+// direct scatter 70 ms (3.4x DRAM write amplification, but only one returning-atomic pass);
+// two-level 37 + 37 ms (clean writes, two returning-atomic passes at ~5.5e10/s each).  The direct
+// scatter is the default for windows; the library index uses the two-level form (28.7 -> 17.5 ms).
+#define BC_WINDOWS_TWO_LEVEL 0
+
 template <int PASS>
 __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketParams gp,
                                                 const __grid_constant__ CoarsePlan pl,
@@ -48,8 +56,10 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
         if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
         if (PASS == 0) {
             atomicAdd(&gdir_or_cursor[slot], 1u);
+        } else if (PASS == 1) {
+            const uint32_t dst = atomicAdd(&gdir_or_cursor[slot], 1u);
+            gwin[dst] = make_uint4(pos, wh, wl, slot);
         } else {
-            // level 1 of the two-level scatter (bc_kernels.h): coarse partition, few open lines
             const uint32_t dst = atomicAdd(&gdir_or_cursor[bc_coarse_of(pl, c, slot)], 1u);
             gwin[dst] = make_uint4(pos, wh, wl, slot);
         }
@@ -295,9 +305,10 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     // chunk the genome so the window records stay within the workspace budget
     size_t free_b = 0, total_b = 0;
     JCK(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t budget = ((uint64_t)free_b + 2 * ws.gwin_cap * sizeof(uint4)) / 2;
+    const uint32_t n_arrays = BC_WINDOWS_TWO_LEVEL ? 2 : 1;  // record arrays (coarse + final)
+    uint64_t budget = ((uint64_t)free_b + n_arrays * ws.gwin_cap * sizeof(uint4)) / 2;
     if (budget > (96ull << 30)) budget = 96ull << 30;
-    uint64_t chunk = budget / (2 * sizeof(uint4)) / p.n_combos;  // two record arrays (coarse + final)
+    uint64_t chunk = budget / (n_arrays * sizeof(uint4)) / p.n_combos;
     if (chunk > p.n_pos) chunk = p.n_pos;
     if (chunk < 1) chunk = 1;
     if (chunk * p.n_combos >= (1ull << 32)) chunk = ((1ull << 32) - 1) / p.n_combos;  // 32-bit record indices
@@ -308,7 +319,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         ws.d_gwin = ws.d_gtmp = nullptr;
         ws.gwin_cap = 0;
         JCK(cudaMalloc(&ws.d_gwin, (chunk * p.n_combos + 1) * sizeof(uint4)));
-        JCK(cudaMalloc(&ws.d_gtmp, (chunk * p.n_combos + 1) * sizeof(uint4)));
+        if (BC_WINDOWS_TWO_LEVEL) JCK(cudaMalloc(&ws.d_gtmp, (chunk * p.n_combos + 1) * sizeof(uint4)));
         ws.gwin_cap = chunk * p.n_combos;
     }
     if (dir_slots > ws.gdir_cap) {
@@ -355,11 +366,16 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         JCK(cudaGetLastError());
         JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
         JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
-        JCK(bc_launch_coarse_init(pl, ws.d_gdir, ws.d_coarse_cursor, st));
-        k_bucket<1><<<grid, 256, 0, st>>>(gp, pl, ws.d_coarse_cursor, ws.d_gtmp);
-        JCK(cudaGetLastError());
-        JCK(bc_launch_fine_scatter(0, ws.d_gtmp, ws.d_gdir + (dir_slots - 1), ws.d_gcursor, ws.d_gwin, nullptr, nullptr,
-                                   sm_count, st));
+        if (BC_WINDOWS_TWO_LEVEL) {
+            JCK(bc_launch_coarse_init(pl, ws.d_gdir, ws.d_coarse_cursor, st));
+            k_bucket<2><<<grid, 256, 0, st>>>(gp, pl, ws.d_coarse_cursor, ws.d_gtmp);
+            JCK(cudaGetLastError());
+            JCK(bc_launch_fine_scatter(0, ws.d_gtmp, ws.d_gdir + (dir_slots - 1), ws.d_gcursor, ws.d_gwin, nullptr,
+                                       nullptr, sm_count, st));
+        } else {
+            k_bucket<1><<<grid, 256, 0, st>>>(gp, pl, ws.d_gcursor, ws.d_gwin);
+            JCK(cudaGetLastError());
+        }
         JCK(cudaEventRecord(ws.ev_a, st));
         // the last directory slot is the end sentinel: after the scan it holds the record count
         k_merge_verify<true><<<(uint32_t)sm_count * 8u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
