@@ -28,13 +28,13 @@ struct BucketParams {
     const uint32_t* lib_dir;      // library directory (to skip windows whose bucket is empty)
     uint32_t pos_begin, pos_end;  // dev positions handled by this chunk of the genome
     uint32_t L, n_combos, prune;
-    uint32_t* rank;               // [n_combos][pos_end - pos_begin] rank of each window within its slot
     ComboDesc combo[BC_MAX_COMBOS];
 };
 
 // Pass 1.  PASS 0 counts, PASS 1 scatters.  Windows touching a non-ACGT base or a contig end
 // are dropped here, so pass 2 never sees them.
-// Pass 1 variants: PASS 0 counts and records ranks, PASS 1 scatters straight to the final slot, PASS 2 scatters to a coarse partition (level 1 of the two-level scatter in
+// Pass 1 variants: PASS 0 counts (RED), PASS 1 scatters straight to the final slot (one returning
+// atomic per record), PASS 2 scatters to a coarse partition (level 1 of the two-level scatter in
 // bc_kernels.h; level 2 is k_fine_scatter).  Measured on cfg 4, b=6 (2e9 records): count 9 ms;
 // direct scatter 70 ms (3.4x DRAM write amplification, but only one returning-atomic pass);
 // two-level 37 + 37 ms (clean writes, two returning-atomic passes at ~5.5e10/s each).  The direct
@@ -55,14 +55,9 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
         const uint32_t slot = cd.dir_off + bc_combo_key(cd, wh, wl);
         if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
         if (PASS == 0) {
-            // Returning atomics run at ~5.5e10/s on B200 (4x slower than fire-and-forget RED), so
-            // each record takes exactly one: the count pass keeps the value it gets back as the
-            // window's rank inside its slot, and the scatter pass needs no atomic at all.
-            const size_t r = (size_t)c * (gp.pos_end - gp.pos_begin) + (pos - gp.pos_begin);
-            gp.rank[r] = atomicAdd(&gdir_or_cursor[slot], 1u);
+            atomicAdd(&gdir_or_cursor[slot], 1u);
         } else if (PASS == 1) {
-            const size_t r = (size_t)c * (gp.pos_end - gp.pos_begin) + (pos - gp.pos_begin);
-            const uint32_t dst = gdir_or_cursor[slot] + __ldcs(gp.rank + r);  // scanned directory + rank
+            const uint32_t dst = atomicAdd(&gdir_or_cursor[slot], 1u);
             gwin[dst] = make_uint4(pos, wh, wl, slot);
         } else {
             const uint32_t dst = atomicAdd(&gdir_or_cursor[bc_coarse_of(pl, c, slot)], 1u);
@@ -285,7 +280,6 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_gcursor) cudaFree(ws.d_gcursor);
     if (ws.d_gwin) cudaFree(ws.d_gwin);
     if (ws.d_gtmp) cudaFree(ws.d_gtmp);
-    if (ws.d_rank) cudaFree(ws.d_rank);
     if (ws.d_coarse_cursor) cudaFree(ws.d_coarse_cursor);
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
@@ -312,10 +306,9 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     size_t free_b = 0, total_b = 0;
     JCK(cudaMemGetInfo(&free_b, &total_b));
     const uint32_t n_arrays = BC_WINDOWS_TWO_LEVEL ? 2 : 1;  // record arrays (coarse + final)
-    const uint64_t per_rec = n_arrays * sizeof(uint4) + sizeof(uint32_t);  // + rank
-    uint64_t budget = ((uint64_t)free_b + ws.gwin_cap * per_rec) / 2;
+    uint64_t budget = ((uint64_t)free_b + n_arrays * ws.gwin_cap * sizeof(uint4)) / 2;
     if (budget > (96ull << 30)) budget = 96ull << 30;
-    uint64_t chunk = budget / per_rec / p.n_combos;
+    uint64_t chunk = budget / (n_arrays * sizeof(uint4)) / p.n_combos;
     if (chunk > p.n_pos) chunk = p.n_pos;
     if (chunk < 1) chunk = 1;
     if (chunk * p.n_combos >= (1ull << 32)) chunk = ((1ull << 32) - 1) / p.n_combos;  // 32-bit record indices
@@ -326,9 +319,6 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         ws.d_gwin = ws.d_gtmp = nullptr;
         ws.gwin_cap = 0;
         JCK(cudaMalloc(&ws.d_gwin, (chunk * p.n_combos + 1) * sizeof(uint4)));
-        if (ws.d_rank) cudaFree(ws.d_rank);
-        ws.d_rank = nullptr;
-        JCK(cudaMalloc(&ws.d_rank, (chunk * p.n_combos + 1) * sizeof(uint32_t)));
         if (BC_WINDOWS_TWO_LEVEL) JCK(cudaMalloc(&ws.d_gtmp, (chunk * p.n_combos + 1) * sizeof(uint4)));
         ws.gwin_cap = chunk * p.n_combos;
     }
@@ -361,7 +351,6 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     memcpy(gp.combo, p.combo, sizeof gp.combo);
     // Skipping windows whose library bucket is empty only pays when most buckets are empty.
     gp.prune = p.dir_entries < (dir_slots - 1) * 2 ? 1u : 0u;
-    gp.rank = ws.d_rank;
 
     for (uint64_t begin = 0; begin < p.n_pos; begin += chunk) {
         gp.pos_begin = (uint32_t)begin;
@@ -384,7 +373,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
             JCK(bc_launch_fine_scatter(0, ws.d_gtmp, ws.d_gdir + (dir_slots - 1), ws.d_gcursor, ws.d_gwin, nullptr,
                                        nullptr, sm_count, st));
         } else {
-            k_bucket<1><<<grid, 256, 0, st>>>(gp, pl, ws.d_gdir, ws.d_gwin);
+            k_bucket<1><<<grid, 256, 0, st>>>(gp, pl, ws.d_gcursor, ws.d_gwin);
             JCK(cudaGetLastError());
         }
         JCK(cudaEventRecord(ws.ev_a, st));
