@@ -125,60 +125,72 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline_run(cfg, genome, off, lib, budget_s=20.0, threads=None):
-    """Time the oracle (CPU restatement, kind 'port' - bowtie itself is not installable here) on a
-    bounded sample of the workload: the first n_s spacers against the first G_s bases."""
+def cpu_sample_once(cfg, genome, lib, n_s, G_s, threads):
     from oracle import oracle
     from barcoder_b200 import synth
-    threads = threads or os.cpu_count() or 1
+    contigs = [bytes(genome[:G_s])]
+    spacers = synth.rows_to_strings(lib[:n_s])
+    t0 = time.time()
+    hits = oracle.search(contigs, spacers, cfg["k"], pam=cfg["pam"], direction="downstream",
+                         flags=oracle.PAM_FLAG_IUPAC if cfg["iupac"] else 0, threads=threads)
+    dt = time.time() - t0
+    return dict(value=n_s * (G_s / 1e6) / dt, seconds=dt, n=n_s, G=G_s, hits=int(len(hits)))
+
+
+def cpu_calibrate(cfg, genome, lib, budget_s, threads):
+    """Pick a bounded sample (first n_s spacers x first G_s bases) that keeps the oracle busy for
+    roughly budget_s seconds on this box."""
     n_s = min(len(lib), 20_000)
     G_s = min(len(genome), 4_000_000)
     best = None
     for _ in range(4):
-        sub = genome[:G_s]
-        contigs = [bytes(sub)]
-        spacers = synth.rows_to_strings(lib[:n_s])
-        t0 = time.time()
-        hits = oracle.search(contigs, spacers, cfg["k"], pam=cfg["pam"], direction="downstream",
-                             flags=oracle.PAM_FLAG_IUPAC if cfg["iupac"] else 0, threads=threads)
-        dt = time.time() - t0
-        best = dict(value=n_s * (G_s / 1e6) / dt, seconds=dt, n=n_s, G=G_s, hits=int(len(hits)))
-        if dt >= budget_s / 3 or G_s >= len(genome):
+        best = cpu_sample_once(cfg, genome, lib, n_s, G_s, threads)
+        if best["seconds"] >= budget_s / 3 or G_s >= len(genome):
             break
-        G_s = min(len(genome), int(G_s * min(8.0, max(2.0, (budget_s / 1.5) / max(dt, 1e-3)))))
+        G_s = min(len(genome), int(G_s * min(8.0, max(2.0, (budget_s / 1.5) / max(best["seconds"], 1e-3)))))
+    return best
+
+
+def cpu_result(cfg, best, threads):
     return {"value": best["value"], "unit": "guides*Mbp/s", "cores": threads, "kind": "port",
             "sample": f"first {best['n']} spacers x first {best['G']} bp of the genome, k={cfg['k']}, "
-                      f"{best['seconds']:.1f} s, {best['hits']} hits; oracle/oracle.c pigeonhole search "
-                      f"(CPU restatement, not bowtie - bowtie 1.3.1 is not installable here)"}
+                      f"{best['seconds']:.1f} s, {best['hits']} hits; oracle/oracle.c pigeonhole search on "
+                      f"{threads} threads (CPU restatement, not bowtie - bowtie 1.3.1 is not installable here)"}
+
+
+def cpu_baseline_run(cfg, genome, off, lib, budget_s=20.0, threads=None):
+    """Time the oracle (CPU restatement, kind 'port') on a bounded sample of the workload."""
+    threads = threads or os.cpu_count() or 1
+    return cpu_result(cfg, cpu_calibrate(cfg, genome, lib, budget_s, threads), threads)
 
 
 def run_reference(args, cfg):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The
-    reference shells out to bowtie 1.3.1, which cannot be installed offline; the oracle port of the
-    same search stands in (see oracle/oracle.c header)."""
+    reference shells out to bowtie 1.3.1, which cannot be installed offline (and the repo is not
+    pip-installable); the oracle port of the same search stands in (see oracle/oracle.c header).
+    Every step searches the same bounded sample of the workload with all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     genome, off, lib = make_workload(cfg, 0, args.scale)
     threads = os.cpu_count() or 1
-    vals = []
-    res = None
+    cal = cpu_calibrate(cfg, genome, lib, 12.0, threads)
+    vals, last = [], cal
     for i in range(args.warmup + args.steps):
-        res = cpu_baseline_run(cfg, genome, off, lib, budget_s=12.0 if i else 6.0, threads=threads)
+        last = cpu_sample_once(cfg, genome, lib, cal["n"], cal["G"], threads)
         if i >= args.warmup:
-            vals.append(res["value"])
-        if i == 0:
-            # freeze the sample found by the calibration pass
-            pass
-    value = statistics.mean(vals)
+            vals.append(last["value"])
+    value = statistics.mean(vals) if vals else cal["value"]
     n_tot = len(lib) * args.gpus
+    res = cpu_result(cfg, last, threads)
     line = {
         "impl": "reference", "metric": "guides*Mbp/s at <=k mismatches", "value": value, "unit": "guides*Mbp/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * n_tot * (len(genome) / 1e6) / value, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 bit-planes (XOR/popcount)", "data": "synthetic",
+        "ms_per_step": 1e3 * last["seconds"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 2-bit packed (XOR/popcount)", "data": "synthetic",
         "config": {"workload": cfg["name"], "k": cfg["k"], "pam": cfg["pam"], "spacers_per_gpu": len(lib),
-                   "genome_bp": len(genome)},
+                   "genome_bp": len(genome), "note": "each step = the bounded sample in cpu_baseline.sample; "
+                   f"full job would take ~{n_tot * (len(genome) / 1e6) / value:.0f} s at this rate"},
         "cpu_baseline": dict(res, value=value),
         "e2e": {"value": value, "unit": "guides*Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -331,45 +343,57 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel group
+    # ---- roofline of the dominant kernel group (DESIGN.md sections 4 and 6)
     peaks, peak_src = measured_peaks()
     combos = st["combos"]
-    valid_windows = G  # upper bound; windows touching N / contig ends are dropped
+    records = float(G) * combos          # (window, combination) records; windows touching N are dropped
     parts = {"verify": acc["ms_scan_kernel"], "genome_bucket": acc["ms_genome_bucket"],
              "index_build": acc["ms_build_index"]}
     dominant = max(parts, key=parts.get)
     ipk = int_peak(local_rank)
     if st["path"] == 2:
-        # bucketing: read 3 planes once per combination-pass pair (count + scatter), write 16 B per
-        # (window, combination); verify: read those 16 B once + the index entries (12 B each) once
-        bytes_bucket = 2 * combos * (3 * G / 8) + 16.0 * valid_windows * combos + 3 * 4 * st["combos"] * 0
-        bytes_verify = 16.0 * valid_windows * combos + 12.0 * 2 * n * combos + 16.0 * st["hits"]
+        # window sort: the three planes are read once per pass and combination (count, scatter),
+        # one 16 B record written; verify: that record read once, the index entries (12 B) once,
+        # 16 B written per hit
+        alg_bytes = {"genome_bucket": 2 * combos * (3 * G / 8) + 16.0 * records,
+                     "verify": 16.0 * records + 12.0 * 2 * n * combos + 16.0 * st["hits"],
+                     "index_build": (8 + 16 + 16 + 12) * 2.0 * n * combos}
+        names = {"verify": "k_merge_verify<dense>+<sparse>", "genome_bucket": "k_bucket<0>+scan+k_bucket<1>",
+                 "index_build": "k_index_count+scan+k_index_scatter+k_fine_scatter"}
     else:
-        bytes_bucket = 0.0
-        bytes_verify = 3 * G / 8 + 16.0 * st["hits"]
-    bytes_index = (8 + 8 + 12) * 2.0 * n * combos
-    kernel_bytes = {"verify": bytes_verify, "genome_bucket": bytes_bucket, "index_build": bytes_index}[dominant]
+        alg_bytes = {"verify": 3 * G / 8 + 16.0 * st["hits"], "genome_bucket": 0.0,
+                     "index_build": (8 + 16 + 16 + 12) * 2.0 * n * combos}
+        names = {"verify": "k_scan_probe", "genome_bucket": "-", "index_build": "k_index_count+scan+scatter"}
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this configuration
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as h:
+            traffic = json.load(h).get(f"{args.config}:b{st['blocks']}:path{st['path']}", {}).get(dominant)
+    except OSError:
+        pass
     kernel_ms = parts[dominant]
-    achieved = kernel_bytes / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": {"verify": "k_join_verify" if st["path"] == 2 else "k_scan_probe",
-                                          "genome_bucket": "k_genome_bucket<0/1> + scan",
-                                          "index_build": "k_index_count/scatter + scan"}[dominant],
-                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+    achieved = alg_bytes[dominant] / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes[dominant],
                 "share_of_step": kernel_ms / max(ms_per_step, 1e-9),
-                "ms": {k2: round(v, 4) for k2, v in parts.items()}}
+                "ms": {k2: round(v, 4) for k2, v in parts.items()},
+                "note": "HBM view of the stage with the largest share of the step; the verify stage is "
+                        "integer-pipe bound and is rated in roofline_int"}
     roofline_int = None
     if ipk and st["path"] == 2 and acc["ms_scan_kernel"] > 0:
-        # candidates verified per second against the measured verify-atom rate (2 LOP3 + POPC + min)
+        # candidates verified per second against the measured POPC issue rate and the measured
+        # verify-atom rate (2 LOP3 + POPC + compare fed from a shared-memory broadcast)
         s.set_param(_native.BC_PARAM_COUNT_CANDIDATES, 1)
         s.search(k)
         cand = s.stats()["candidates"]
         s.set_param(_native.BC_PARAM_COUNT_CANDIDATES, 0)
         rate = cand / (acc["ms_scan_kernel"] / 1e3)
-        roofline_int = {"bound": "int_popc", "kernel": "k_join_verify", "achieved": rate / 1e12,
-                        "peak": ipk["verify_atom_per_s"] / 1e12, "unit": "Tpairs/s",
-                        "frac": rate / ipk["verify_atom_per_s"], "popc_peak_Tops": ipk["popc_per_s"] / 1e12,
-                        "candidates": cand, "peak_source": "bench_kernels/int_peak.cu measured in this run"}
+        roofline_int = {"bound": "int_popc", "kernel": names["verify"], "achieved": rate / 1e12,
+                        "peak": ipk["popc_per_s"] / 1e12, "unit": "Tpairs/s (1 POPC per pair)",
+                        "frac": rate / ipk["popc_per_s"], "frac_of_verify_atom": rate / ipk["verify_atom_per_s"],
+                        "verify_atom_peak": ipk["verify_atom_per_s"] / 1e12, "candidates": cand,
+                        "share_of_step": acc["ms_scan_kernel"] / max(ms_per_step, 1e-9),
+                        "peak_source": "bench_kernels/int_peak.cu measured in this run (POPC: 16/clk/SM)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

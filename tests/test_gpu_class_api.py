@@ -198,3 +198,36 @@ def test_two_shards_on_one_gpu_equal_one_shard():
         whole = _native.canonical_sort(s.hits())
     merged = _native.canonical_sort(np.concatenate(parts))
     assert merged.tobytes() == whole.tobytes()
+
+
+def test_targets_script_records_match_fixture(golden_dir, plasmids):
+    """the targets.py-shaped records (circular overhang, direction-aware PAM, per-gene rows,
+    origin-spanning gene) reproduce every plasmid row of the reference's CN-32-zmo.tsv."""
+    from barcoder_b200 import targets
+    with open(os.path.join(golden_dir, "cn32_plasmid_rows.tsv")) as h:
+        rows = list(csv.DictReader(h, delimiter="\t"))
+    spacers = sorted({r["spacer"] for r in rows})
+    final = targets.find_targets(spacers, plasmids, "NGNC", 0, "downstream")
+    assert {"spacer", "locus_tag", "gene", "chr", "target", "tar_start", "tar_end", "offset", "overlap", "sp_dir",
+            "tar_dir", "note"} <= set(final.columns)
+    got = {}
+    for r in final.itertuples():
+        if isinstance(r.target, str):
+            got[(r.spacer, r.chr, int(r.tar_start), r.locus_tag)] = r
+    for row in rows:
+        r = got.get((row["spacer"], row["chr"], int(row["tar_start"]), row["locus_tag"]))
+        assert r is not None, row
+        assert r.target.upper() == row["target"] and int(r.tar_end) == int(row["tar_end"])
+        assert r.sp_dir == row["sp_dir"] and r.tar_dir == row["tar_dir"] and r.gene == row["gene"]
+        assert int(r.offset) == int(row["offset"]) and int(r.overlap) == int(row["overlap"]), row
+        if "pam" in final.columns:
+            assert r.pam == row["pam"]
+    # JSON serialises like targets.py --json
+    import json
+    recs = json.loads(final.to_json(orient="records"))
+    assert len(recs) == len(final) and "note" in recs[0]
+    # mismatching hits carry lower-case target bases and a diff-compatible mask
+    mm = targets.find_targets(spacers[:200], plasmids, "NGNC", 2, "downstream")
+    assert "mismatches" in mm.columns
+    with_mm = mm[mm["mismatches"] > 0]
+    assert len(with_mm) and all(sum(ch.islower() for ch in t) == m for t, m in zip(with_mm["target"], with_mm["mismatches"]))
