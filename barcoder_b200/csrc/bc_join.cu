@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 #define MV_ITEMS 4    // records per lane per warp-tile
 #define MV_WQ 128     // per-warp candidate queue (entries)
 #ifndef MV_DENSE_ENTRIES
-#define MV_DENSE_ENTRIES 2    // index entries per group in the dense kernel (2 or 4)
+#define MV_DENSE_ENTRIES 4    // index entries per group in the dense kernel
 #endif
 #ifndef MV_DENSE_MINBLOCKS
-#define MV_DENSE_MINBLOCKS 3  // occupancy target of the dense kernel (CTAs per SM)
+#define MV_DENSE_MINBLOCKS 2  // occupancy target of the dense kernel (CTAs per SM)
 #endif
 
 __device__ __forceinline__ uint32_t mv_combo_of_slot(const SearchParams& p, uint32_t slot) {
@@ -186,47 +186,51 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
         if (DENSE) {
             const uint32_t ls = __ldg(p.dir + wv[0].w), le = __ldg(p.dir + wv[0].w + 1);
             cand += (unsigned long long)(le - ls) * MV_ITEMS;
-            for (uint32_t e0 = ls; e0 < le; e0 += 32) {
-                const uint32_t e1 = min(e0 + 32, le);
-                uint32_t e = e0;
-                for (; e + MV_DENSE_ENTRIES <= e1; e += MV_DENSE_ENTRIES) {
-                    uint2 qe[MV_DENSE_ENTRIES];
+            // Software-pipelined walk over the bucket: the entries of group g+1 are loaded while
+            // group g is evaluated (ncu: 27 % of the stall samples sat on the first use of the
+            // loaded words).  Loads past the end are clamped to the last entry; their results are
+            // ignored by the e + j < le guard on the candidate path.
+            uint2 cur[MV_DENSE_ENTRIES];
 #pragma unroll
-                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) qe[j] = __ldg(ent + e + j);
-                    // (count - (k+1)) is negative iff count <= k: OR-ing the differences keeps the
-                    // sign bit of any candidate with plain IADD/LOP3.  At cfg-4 density about one
-                    // group in ten contains a candidate in SOME lane, so the follow-up must stay
-                    // short and inline: one compare+branch per count, a queue push where it fires.
-                    int d[MV_ITEMS][MV_DENSE_ENTRIES];
-                    int acc = 0;
+            for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = __ldg(ent + min(ls + j, le - 1));
+            uint32_t since_drain = 0;
+            for (uint32_t e = ls; e < le; e += MV_DENSE_ENTRIES) {
+                uint2 nxt[MV_DENSE_ENTRIES];
 #pragma unroll
-                    for (int it = 0; it < MV_ITEMS; it++) {
+                for (int j = 0; j < MV_DENSE_ENTRIES; j++)
+                    nxt[j] = __ldg(ent + min(e + MV_DENSE_ENTRIES + j, le - 1));
+                // (count - (k+1)) is negative iff count <= k: OR-ing the differences keeps the sign
+                // bit of any candidate with plain IADD/LOP3.  About one group in ten contains a
+                // candidate in SOME lane at cfg-4 density, so the follow-up stays short and
+                // inline: one compare+branch per count, a queue push where it fires.
+                int d[MV_ITEMS][MV_DENSE_ENTRIES];
+                int acc = 0;
 #pragma unroll
-                        for (int j = 0; j < MV_DENSE_ENTRIES; j++) {
-                            d[it][j] = __popc((wv[it].y ^ qe[j].x) | (wv[it].z ^ qe[j].y)) - k1;
-                            acc |= d[it][j];
-                        }
-                    }
-                    if (acc < 0) {
+                for (int it = 0; it < MV_ITEMS; it++) {
 #pragma unroll
-                        for (int it = 0; it < MV_ITEMS; it++) {
-                            const uint4 w = wv[it];
-#pragma unroll
-                            for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                                if (d[it][j] < 0) MV_CANDIDATE(e + j, qe[j]);
-                        }
+                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) {
+                        d[it][j] = __popc((wv[it].y ^ cur[j].x) | (wv[it].z ^ cur[j].y)) - k1;
+                        acc |= d[it][j];
                     }
                 }
-                for (; e < e1; e++) {
-                    const uint2 qq = __ldg(ent + e);
+                if (acc < 0) {
 #pragma unroll
                     for (int it = 0; it < MV_ITEMS; it++) {
                         const uint4 w = wv[it];
-                        if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+#pragma unroll
+                        for (int j = 0; j < MV_DENSE_ENTRIES; j++)
+                            if (d[it][j] < 0 && e + j < le) MV_CANDIDATE(e + j, cur[j]);
                     }
                 }
-                mv_drain(p, q, qn, lane);  // every 32 entries
+#pragma unroll
+                for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = nxt[j];
+                since_drain += MV_DENSE_ENTRIES;
+                if (since_drain >= 32) {  // warp-uniform
+                    since_drain = 0;
+                    mv_drain(p, q, qn, lane);
+                }
             }
+            mv_drain(p, q, qn, lane);
         } else {
             // Issue the directory loads of all MV_ITEMS records before any dependent work.
             uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
