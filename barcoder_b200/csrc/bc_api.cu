@@ -361,18 +361,25 @@ static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_o
         if (ctx->par_blocks && (uint32_t)ctx->par_blocks != b) continue;
         Scheme s;
         if (!make_scheme(ctx->L, k, b, cap, E, &s)) continue;
-        // Cost model in units of one verified candidate of the join kernel (~0.45 ps of chip time
-        // on B200; constants fitted to measurements):
-        //   probe path: a directory probe is a dependent pair of random sector reads (~25 units
-        //               while the directory is L2-resident, ~90 from HBM); candidates are 8-byte
-        //               uncoalesced reads (~8 units);
-        //   join path : partitioning costs ~85 units per (window, combination) (two atomics and a
-        //               16-byte scattered write), candidates cost 1, plus a fixed launch/scan floor.
+        // Cost model in picoseconds of B200 time per unit, fitted to measurements on cfg 3/4/5
+        // (bench_kernels/scatter_lab.cu for the scatter terms):
+        //   probe path: a directory probe costs ~17 ps while the directories stay L2-resident and
+        //               ~58 ps once they live in HBM; a candidate is an uncoalesced 8-byte read, ~3 ps;
+        //   join path : the window sort costs ~28 ps per (window, combination) record with <= 2^16
+        //               slots per combination and ~6 ps more per doubling beyond that (open write
+        //               fronts outgrow L2); verify costs ~20 ps per record plus ~0.42 ps per candidate;
+        //   both      : the library index costs ~40 ps per (entry, combination); directories are
+        //               cleared, scanned and copied at ~5 ps per slot; fixed launch floor ~100 us.
         const double dir_bytes = 4.0 * (double)s.dir_slots;
-        const double dir_cost = 12.0 * (double)s.dir_slots;
-        const double c_probe = dir_bytes < 64e6 ? 25.0 : 90.0;
-        double probe_cost = windows * (c_probe * s.n_combos + 8.0 * s.cand_per_window) + dir_cost;
-        double join_cost = windows * (85.0 * s.n_combos + 1.0 * s.cand_per_window) + dir_cost + 4.0e8;
+        const double records = windows * s.n_combos;
+        const double entries = (double)E * s.n_combos;
+        const double cands = windows * s.cand_per_window;
+        const double common = 40.0 * entries + 5.0 * (double)s.dir_slots;
+        const double c_probe = dir_bytes < 100e6 ? 17.0 : 58.0;
+        double slots_per_combo = (double)s.dir_slots / s.n_combos, c_sort = 28.0;
+        while (slots_per_combo > 65536.0) { c_sort += 6.0; slots_per_combo *= 0.5; }
+        double probe_cost = c_probe * records + 3.0 * cands + common;
+        double join_cost = (c_sort + 20.0) * records + 0.42 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
         for (uint32_t path = 1; path <= 2; path++) {
             if (ctx->par_path && (uint32_t)ctx->par_path != path) continue;
             if (path == 2 && !bc_join_supported(s.combo, s.n_combos, E)) continue;

@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 
 #define MV_THREADS 256
 #define MV_WARPS (MV_THREADS / 32)
+#ifndef MV_ITEMS
 #define MV_ITEMS 4    // records per lane per warp-tile
+#endif
 #define MV_WQ 128     // per-warp candidate queue (entries)
 #ifndef MV_DENSE_ENTRIES
 #define MV_DENSE_ENTRIES 4    // index entries per group in the dense kernel
@@ -186,21 +188,25 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
         if (DENSE) {
             const uint32_t ls = __ldg(p.dir + wv[0].w), le = __ldg(p.dir + wv[0].w + 1);
             cand += (unsigned long long)(le - ls) * MV_ITEMS;
-            // Software-pipelined walk over the bucket: the entries of group g+1 are loaded while
-            // group g is evaluated (ncu: 27 % of the stall samples sat on the first use of the
-            // loaded words).  Loads past the end are clamped to the last entry; their results are
-            // ignored by the e + j < le guard on the candidate path.
+            // Software-pipelined walk over the bucket in groups of MV_DENSE_ENTRIES entries: the
+            // entries of group g+1 are loaded while group g is evaluated (ncu: 27 % of the stall
+            // samples sat on the first use of the loaded words before this).
+            const uint32_t n_groups = (le - ls) / MV_DENSE_ENTRIES;
+            const uint2* gp = ent + ls;
             uint2 cur[MV_DENSE_ENTRIES];
+            if (n_groups) {
 #pragma unroll
-            for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = __ldg(ent + min(ls + j, le - 1));
+                for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = __ldg(gp + j);
+            }
             uint32_t since_drain = 0;
-            for (uint32_t e = ls; e < le; e += MV_DENSE_ENTRIES) {
+            for (uint32_t g = 0; g < n_groups; g++, gp += MV_DENSE_ENTRIES) {
                 uint2 nxt[MV_DENSE_ENTRIES];
+                if (g + 1 < n_groups) {  // warp-uniform
 #pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                    nxt[j] = __ldg(ent + min(e + MV_DENSE_ENTRIES + j, le - 1));
+                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) nxt[j] = __ldg(gp + MV_DENSE_ENTRIES + j);
+                }
                 // (count - (k+1)) is negative iff count <= k: OR-ing the differences keeps the sign
-                // bit of any candidate with plain IADD/LOP3.  About one group in ten contains a
+                // bit of any candidate with plain IADD/LOP3.  About one group in five contains a
                 // candidate in SOME lane at cfg-4 density, so the follow-up stays short and
                 // inline: one compare+branch per count, a queue push where it fires.
                 int d[MV_ITEMS][MV_DENSE_ENTRIES];
@@ -214,12 +220,13 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
                     }
                 }
                 if (acc < 0) {
+                    const uint32_t e = ls + g * MV_DENSE_ENTRIES;
 #pragma unroll
                     for (int it = 0; it < MV_ITEMS; it++) {
                         const uint4 w = wv[it];
 #pragma unroll
                         for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                            if (d[it][j] < 0 && e + j < le) MV_CANDIDATE(e + j, cur[j]);
+                            if (d[it][j] < 0) MV_CANDIDATE(e + j, cur[j]);
                     }
                 }
 #pragma unroll
@@ -228,6 +235,14 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
                 if (since_drain >= 32) {  // warp-uniform
                     since_drain = 0;
                     mv_drain(p, q, qn, lane);
+                }
+            }
+            for (uint32_t e = ls + n_groups * MV_DENSE_ENTRIES; e < le; e++) {  // < MV_DENSE_ENTRIES entries
+                const uint2 qq = __ldg(ent + e);
+#pragma unroll
+                for (int it = 0; it < MV_ITEMS; it++) {
+                    const uint4 w = wv[it];
+                    if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
                 }
             }
             mv_drain(p, q, qn, lane);
@@ -245,8 +260,8 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
                 const uint32_t ls = lsv[it], le = lev[it];
                 cand += le - ls;
                 uint32_t e = ls;
-                // branch-free batches of 4: popcounts are min-reduced, only a batch containing a
-                // candidate is re-examined
+                // branch-free batches of 4: the sign bits of (count - (k+1)) are OR-ed, only a batch
+                // containing a candidate is re-examined
                 for (; e + 4 <= le; e += 4) {
                     const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
                                 q3 = __ldg(ent + e + 3);
