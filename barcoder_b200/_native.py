@@ -33,7 +33,7 @@ HIT_DTYPE = np.dtype([("spacer_id", "<u4"), ("gpos", "<u4"), ("mm_mask", "<u4"),
 EXPORTS = (
     "bc_abi_version", "bc_create", "bc_destroy", "bc_set_genome", "bc_set_genome_dev", "bc_set_library",
     "bc_set_library_dev", "bc_set_pam", "bc_set_param", "bc_build_index", "bc_search", "bc_copy_hits",
-    "bc_hits_device", "bc_get_stats", "bc_last_error",
+    "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
 )
 
 
@@ -91,6 +91,8 @@ def load():
     L.bc_copy_hits.argtypes = [vp, vp, u64]
     L.bc_hits_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.bc_get_stats.argtypes = [vp, ctypes.POINTER(BcStats)]
+    L.bc_enumerate_guides.argtypes = [vp, u32, ctypes.c_char_p, i32, u32, ctypes.POINTER(u64)]
+    L.bc_copy_guides.argtypes = [vp, vp, u64]
     L.bc_last_error.argtypes = [vp]
     L.bc_last_error.restype = ctypes.c_char_p
     for name in EXPORTS:
@@ -217,6 +219,25 @@ class Searcher:
         ptr, n = ctypes.c_void_p(), ctypes.c_uint64()
         self._check(self._L.bc_hits_device(self._ctx, ctypes.byref(ptr), ctypes.byref(n)))
         return ptr.value or 0, n.value
+
+    def enumerate_guides(self, L, pam, direction="downstream", iupac=False, reference_range=False):
+        """Distinct pure-ACGT L-mers next to a PAM match on either strand of the resident genome
+        (design_guides.py:22-49).  Returns uint8 ASCII rows [n, L], sorted."""
+        d = {"downstream": 0, "upstream": 1}[direction]
+        flags = (BC_PAM_IUPAC if iupac else 0) | (4 if reference_range else 0)
+        n = ctypes.c_uint64()
+        self._check(self._L.bc_enumerate_guides(self._ctx, int(L), pam.upper().encode("ascii"), d, flags,
+                                                ctypes.byref(n)))
+        codes = np.empty(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._L.bc_copy_guides(self._ctx, codes.ctypes.data, n.value))
+        out = np.empty((n.value, L), dtype=np.uint8)
+        letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+        for j in range(L):
+            out[:, j] = letters[((codes >> np.uint64(2 * j)) & np.uint64(3)).astype(np.uint8)]
+        if len(out):
+            out = np.unique(np.ascontiguousarray(out).view(np.dtype((np.void, L))).ravel()).view(np.uint8).reshape(-1, L)
+        return out
 
     def stats(self):
         st = BcStats()

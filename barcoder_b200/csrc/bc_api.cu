@@ -11,6 +11,7 @@
 
 #include "bc_kernels.h"
 #include "bc_join.h"
+#include "bc_guides.h"
 
 struct bc_ctx {
     int device = 0;
@@ -53,6 +54,7 @@ struct bc_ctx {
 
     // join workspace
     JoinWorkspace join;
+    GuideWorkspace guides;
 
     // results
     bc_hit* d_hits = nullptr;
@@ -132,6 +134,7 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     dfree(ctx->d_ent_tmp); dfree(ctx->d_coarse_cursor);
     dfree(ctx->d_hits); dfree(ctx->d_count);
     bc_join_free(ctx->join);
+    bc_guides_free(ctx->guides);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -595,5 +598,39 @@ extern "C" int bc_hits_device(bc_ctx* ctx, const bc_hit** d_hits, uint64_t* n_hi
 extern "C" int bc_get_stats(bc_ctx* ctx, bc_stats* out) {
     if (!ctx || !out) return BC_EINVAL;
     *out = ctx->stats;
+    return BC_OK;
+}
+
+// -------------------------------------------------------------------------------- guide enumeration
+extern "C" int bc_enumerate_guides(bc_ctx* ctx, uint32_t L, const char* pam, int direction, uint32_t flags,
+                                   uint64_t* n_guides_out) {
+    if (!ctx) return BC_EINVAL;
+    if (n_guides_out) *n_guides_out = 0;
+    if (!ctx->have_genome) return fail(ctx, BC_EINVAL, "bc_enumerate_guides: no genome loaded");
+    if (L < 1 || L > 32) return fail(ctx, BC_ELIMIT, "guide length must be 1..32");
+    if (!pam) pam = "";
+    const size_t P = strlen(pam);
+    if (P > 8) return fail(ctx, BC_ELIMIT, "PAM longer than 8 letters");
+    if (direction != 0 && direction != 1) return fail(ctx, BC_EINVAL, "direction must be 0 or 1");
+    uint32_t sets[8] = {0};
+    for (size_t i = 0; i < P; i++) sets[i] = iupac_set(pam[i], flags);
+    CK(cudaSetDevice(ctx->device));
+    uint64_t n = 0;
+    CK(bc_guides_enumerate(ctx->guides, ctx->d_H, ctx->d_L, ctx->d_B, ctx->d_start_dev, ctx->n_pos, ctx->n_contigs, L,
+                           (uint32_t)P, sets, direction, (flags & BC_GUIDES_REFERENCE_RANGE) ? 1 : 0, ctx->sm_count,
+                           ctx->stream, &n));
+    if (n_guides_out) *n_guides_out = n;
+    return BC_OK;
+}
+
+extern "C" int bc_copy_guides(bc_ctx* ctx, uint64_t* dst, uint64_t cap) {
+    if (!ctx) return BC_EINVAL;
+    const uint64_t n = ctx->guides.n_guides;
+    if (cap < n) return fail(ctx, BC_EINVAL, "bc_copy_guides: destination too small");
+    if (n == 0) return BC_OK;
+    if (!dst) return fail(ctx, BC_EINVAL, "bc_copy_guides: null destination");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, ctx->guides.d_out, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return BC_OK;
 }

@@ -142,6 +142,19 @@ int bc_hits_device(bc_ctx* ctx, const bc_hit** d_hits, uint64_t* n_hits);
 
 int bc_get_stats(bc_ctx* ctx, bc_stats* out);
 
+/* Replaces the per-position Python loops that enumerate guides next to PAM sites
+ * (design_guides.py:22-49 find_sequences_with_barcode_and_pam; PAMProcessor.py:27-57): every
+ * distinct pure-ACGT L-mer adjacent to a match of `pam` on either strand of every contig of
+ * the resident genome, as a set.  direction 0: PAM 3' of the guide, 1: PAM 5'.  flags:
+ * BC_PAM_IUPAC as in bc_set_pam; BC_GUIDES_REFERENCE_RANGE reproduces design_guides.py:31,
+ * whose loop bound drops the last len(pam) start positions for an upstream PAM as well.
+ * bc_copy_guides returns 2-bit codes: base j of the guide at bits [2j, 2j+2), A0 C1 G2 T3;
+ * order unspecified (the reference builds a Python set). */
+#define BC_GUIDES_REFERENCE_RANGE 4u
+int bc_enumerate_guides(bc_ctx* ctx, uint32_t L, const char* pam, int direction, uint32_t flags,
+                        uint64_t* n_guides_out);
+int bc_copy_guides(bc_ctx* ctx, uint64_t* dst, uint64_t cap);
+
 /* Replaces BowtieError.message (BowtieRunner.py:144-150). */
 const char* bc_last_error(bc_ctx* ctx);
 

@@ -166,3 +166,24 @@ def py_pam_script(seq, start, end, strand, pam, direction="downstream"):
     if pam == "N" * len(pam) or not pam:
         return s, True
     return s, bool(re.match(pam.replace("N", "."), s))
+
+
+def py_enumerate_guides(contigs, L, pam, direction="downstream"):
+    """Literal restatement of design_guides.find_sequences_with_barcode_and_pam
+    (design_guides.py:22-49) on plain strings: both strands, regex with N -> [ATGC] matched at the
+    start of the slice, spacer must be pure GATC, result is a set.  Keeps the reference's loop
+    bound (range(len - L - len(pam) + 1)) and its negative-index slices for the upstream PAM."""
+    out = set()
+    rx = re.compile(pam.replace("N", "[ATGC]"))
+    for ref in contigs:
+        for sequence in (ref, revcomp(ref)):
+            for i in range(len(sequence) - L - len(pam) + 1):
+                if direction == "downstream":
+                    hit = rx.match(sequence[i + L:i + L + len(pam)])
+                else:
+                    hit = rx.match(sequence[i - len(pam):i])
+                if hit:
+                    spacer = sequence[i:i + L]
+                    if all(b in "GATC" for b in spacer):
+                        out.add(spacer)
+    return out

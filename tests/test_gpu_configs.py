@@ -140,3 +140,35 @@ def test_cfg5_scaled_32mers_iupac_pam_many_contigs():
     got["spacer_id"] = np.searchsorted(sub, got["spacer_id"]).astype(np.uint32)
     assert _native.canonical_sort(got).tobytes() == ref.tobytes()
     assert ((gpu["meta"] & 8) != 0).sum() > 0
+
+
+@pytest.mark.parametrize("direction", ["downstream", "upstream"])
+@pytest.mark.parametrize("L,pam", [(20, "NGG"), (32, "NGNC"), (7, "TTTN"), (20, "")])
+def test_guide_enumeration_matches_design_guides(direction, L, pam):
+    """device enumeration == literal design_guides.py loop (reference loop bounds)."""
+    genome, off = synth.random_genome(30_000, seed=L + len(pam), n_contigs=3, n_fraction=0.02, n_run=11)
+    contigs = [bytes(genome[int(off[i]):int(off[i + 1])]).decode() for i in range(3)]
+    want = oracle.py_enumerate_guides(contigs, L, pam, direction)
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        got = s.enumerate_guides(L, pam, direction, reference_range=True)
+        assert {bytes(r).decode() for r in got} == want
+        full = s.enumerate_guides(L, pam, direction, reference_range=False)
+        assert want <= {bytes(r).decode() for r in full}
+    if direction == "downstream" and pam:
+        host = synth.enumerate_pam_guides(genome, off, L, pam)
+        assert np.array_equal(host, got)
+
+
+def test_guide_enumeration_ecoli_scale_and_all_t():
+    genome, off = synth.random_genome(4_641_652, seed=1)
+    host = synth.enumerate_pam_guides(genome, off, 20, "NGG")
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        got = s.enumerate_guides(20, "NGG")
+    assert np.array_equal(host, got)
+    g = np.frombuffer(b"ACG" + b"T" * 32 + b"AGGTTT", np.uint8)
+    with _native.Searcher(0) as s:
+        s.set_genome_array(g, np.array([0, len(g)], np.uint64))
+        got = {bytes(r).decode() for r in s.enumerate_guides(32, "NGG")}
+    assert "T" * 32 in got and got == oracle.py_enumerate_guides([bytes(g).decode()], 32, "NGG")
