@@ -38,6 +38,7 @@ struct bc_ctx {
 
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
+    int64_t par_scan_rank = 0, par_scan_world = 1;
 
     // index
     bool have_index = false;
@@ -289,6 +290,11 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
         case BC_PARAM_COUNT_CANDIDATES: ctx->par_count = value; return BC_OK;
         case BC_PARAM_HIT_CAPACITY: ctx->par_hit_cap = value; return BC_OK;
         case BC_PARAM_SPACER_ID_BASE: ctx->par_id_base = value; return BC_OK;
+        case BC_PARAM_SCAN_PART: {
+            const int64_t rank = value & 0xffff, world = (value >> 16) & 0xffff;
+            if (world < 1 || rank >= world) return fail(ctx, BC_EINVAL, "scan part must be rank | world << 16 with rank < world");
+            ctx->par_scan_rank = rank; ctx->par_scan_world = world; return BC_OK;
+        }
         default: return fail(ctx, BC_EINVAL, "unknown parameter");
     }
 }
@@ -479,6 +485,8 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->H = ctx->d_H; p->Lo = ctx->d_L; p->B = ctx->d_B;
     p->start_dev = ctx->d_start_dev;
     p->n_pos = ctx->n_pos;
+    p->pos_begin = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)ctx->par_scan_rank / (uint64_t)ctx->par_scan_world);
+    p->pos_end = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)(ctx->par_scan_rank + 1) / (uint64_t)ctx->par_scan_world);
     p->n_contigs = ctx->n_contigs;
     p->sn = ctx->d_sn;
     p->lib_has_n = ctx->lib_has_n;

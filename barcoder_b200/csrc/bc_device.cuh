@@ -39,6 +39,7 @@ struct SearchParams {
     const uint32_t* B;
     const uint32_t* start_dev;  // [n_contigs+1] dev position of each contig start; last = n_pos
     uint32_t n_pos;             // dev positions (bases + separators)
+    uint32_t pos_begin, pos_end;  // window start positions this context scans (genome-range sharding)
     uint32_t n_contigs;
     // library
     const uint32_t* sn;         // [n] spacer-orientation mask of non-ACGT spacer characters

@@ -371,9 +371,9 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     // Skipping windows whose library bucket is empty only pays when most buckets are empty.
     gp.prune = p.dir_entries < (dir_slots - 1) * 2 ? 1u : 0u;
 
-    for (uint64_t begin = 0; begin < p.n_pos; begin += chunk) {
+    for (uint64_t begin = p.pos_begin; begin < p.pos_end; begin += chunk) {
         gp.pos_begin = (uint32_t)begin;
-        gp.pos_end = (uint32_t)((begin + chunk < p.n_pos) ? begin + chunk : p.n_pos);
+        gp.pos_end = (uint32_t)((begin + chunk < p.pos_end) ? begin + chunk : p.pos_end);
         uint32_t npos = gp.pos_end - gp.pos_begin;
         uint32_t gx = (npos + 255) / 256;
         uint32_t maxb = (uint32_t)sm_count * 8u;

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
     if (threadIdx.x == 0) stage.n = 0;
     const uint32_t lm = bc_lmask(p.L);
     unsigned long long cand = 0, probes = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = p.pos_begin / PROBE_TILE_POS + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t w0 = tile * PROBE_TILE_WORDS;
         __syncthreads();
         if (threadIdx.x <= PROBE_TILE_WORDS) {  // planes are padded, w0 + 64 is always readable
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
         for (uint32_t step = 0; step < PROBE_STEPS; step++) {
             const uint32_t t = step * PROBE_THREADS + threadIdx.x;
             const uint32_t pos = tile * PROBE_TILE_POS + t;
-            if (pos >= p.n_pos) continue;
+            if (pos < p.pos_begin || pos >= p.pos_end) continue;
             if (bc_window(sB, t) & lm) continue;  // window touches a non-ACGT base or a contig end
             const uint32_t wh = bc_window(sH, t) & lm, wl = bc_window(sL, t) & lm;
             for (uint32_t c = 0; c < p.n_combos; c++) {
@@ -349,10 +349,11 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
 }
 
 cudaError_t bc_launch_scan_probe(const SearchParams& p, int sm_count, cudaStream_t st) {
-    uint32_t n_tiles = (p.n_pos + PROBE_TILE_POS - 1) / PROBE_TILE_POS;
-    if (n_tiles == 0) return cudaSuccess;
+    if (p.pos_end <= p.pos_begin) return cudaSuccess;
+    uint32_t n_tiles = (p.pos_end + PROBE_TILE_POS - 1) / PROBE_TILE_POS;  // one past the last tile
+    uint32_t my_tiles = n_tiles - p.pos_begin / PROBE_TILE_POS;
     uint32_t grid = (uint32_t)sm_count * 8u;
-    if (grid > n_tiles) grid = n_tiles;
+    if (grid > my_tiles) grid = my_tiles;
     k_scan_probe<<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
     bc_launch_counter += 1;
     return cudaGetLastError();

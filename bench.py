@@ -209,6 +209,9 @@ def main():
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 probe, 2 join")
     ap.add_argument("--blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default=None, choices=["library", "genome"],
+                    help="multi-GPU partitioning: library shards (weak scaling, default) or genome ranges "
+                         "(strong scaling; default for cfg5, which is probe-bound)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel experiments only)")
     ap.add_argument("--verify", action="store_true", help="check a sample of the result against the oracle")
     args = ap.parse_args()
@@ -234,7 +237,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    genome, off, lib = make_workload(cfg, rank, args.scale)
+    shard = args.shard or ("genome" if args.config == "cfg5" else "library")
+    genome, off, lib = make_workload(cfg, rank if shard == "library" else 0, args.scale)
     n, L = lib.shape
     G = len(genome)
     k = cfg["k"]
@@ -248,7 +252,10 @@ def main():
 
     s = _native.Searcher(local_rank)
     s.set_pam(cfg["pam"], "downstream", iupac=cfg["iupac"], gate=False)
-    s.set_param(_native.BC_PARAM_SPACER_ID_BASE, rank * n)
+    if shard == "library":
+        s.set_param(_native.BC_PARAM_SPACER_ID_BASE, rank * n)
+    else:  # every rank holds the whole library and scans its 1/world slice of the genome
+        s.set_param(_native.BC_PARAM_SCAN_PART, rank | (world << 16))
     if args.path:
         s.set_param(_native.BC_PARAM_PATH, args.path)
     if args.blocks:
@@ -313,7 +320,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
-    guides_total = n * world
+    guides_total = n * world if shard == "library" else n
     value = guides_total * (G / 1e6) / (ms_per_step / 1e3)
     for key in acc:
         acc[key] /= args.steps
@@ -417,9 +424,11 @@ def main():
     line = {
         "metric": "guides*Mbp/s at <=k mismatches", "value": value, "unit": "guides*Mbp/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (XOR/popcount)", "data": "synthetic",
+        "scaling": "weak" if shard == "library" else "strong", "vs_baseline": None,
+        "dtype": "u32 bit-planes (XOR/popcount)", "data": "synthetic",
         "config": {"workload": cfg["name"], "k": k, "pam": cfg["pam"], "spacers_per_gpu": n, "genome_bp": G,
-                   "L": L, "parallelism": f"library-shard x{world}, genome replicated",
+                   "L": L, "parallelism": (f"library-shard x{world}, genome replicated" if shard == "library" else
+                                           f"genome-range x{world}, library replicated"),
                    "seed_scheme": f"b={st['blocks']} blocks, {combos} combinations, path={st['path']}",
                    "l2": "working set (window records + index) is far larger than the 126 MB L2; no flush needed",
                    "hits_per_step": int(total_hits)},

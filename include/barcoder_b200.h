@@ -68,6 +68,8 @@ typedef struct {
 #define BC_PARAM_COUNT_CANDIDATES 3 /* 1 = count verified candidates into bc_stats        */
 #define BC_PARAM_HIT_CAPACITY 4     /* initial hit-buffer capacity (records)              */
 #define BC_PARAM_SPACER_ID_BASE 5   /* added to every spacer_id (global ids of a library shard) */
+#define BC_PARAM_SCAN_PART 6         /* genome-range sharding: value = rank | world << 16; this
+                                       context scans only its 1/world slice of window starts  */
 
 typedef struct {
     uint64_t genome_bases;    /* G                                                   */

@@ -172,3 +172,25 @@ def test_guide_enumeration_ecoli_scale_and_all_t():
         s.set_genome_array(g, np.array([0, len(g)], np.uint64))
         got = {bytes(r).decode() for r in s.enumerate_guides(32, "NGG")}
     assert "T" * 32 in got and got == oracle.py_enumerate_guides([bytes(g).decode()], 32, "NGG")
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_genome_range_parts_equal_whole(path):
+    """genome-range sharding (BC_PARAM_SCAN_PART) - the union of the parts is the whole."""
+    genome, off = synth.random_genome(1_500_000, seed=61, n_contigs=5, n_fraction=0.002)
+    lib = synth.random_library(20_000, 20, seed=62)
+    synth.plant(lib, genome, 0.3, 2, seed=63)
+    whole, _ = gpu_search(genome, off, lib, 2, "NGG", path=path)
+    parts = []
+    for r in range(3):
+        with _native.Searcher(0) as s:
+            s.set_genome_array(genome, off)
+            s.set_library(lib)
+            s.set_pam("NGG")
+            s.set_param(_native.BC_PARAM_PATH, path)
+            s.set_param(_native.BC_PARAM_SCAN_PART, r | (3 << 16))
+            s.search(2)
+            parts.append(s.hits())
+    assert sum(len(p) for p in parts) == len(whole)
+    assert _native.canonical_sort(np.concatenate(parts)).tobytes() == whole.tobytes()
+    assert all(len(p) > 0 for p in parts)
