@@ -504,6 +504,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->pam_dir = ctx->pam_dir;
     p->pam_flags = ctx->pam_flags;
     memcpy(p->pam_sets, ctx->pam_sets, sizeof p->pam_sets);
+    p->gate_first = ((ctx->pam_flags & BC_PAM_GATE) && ctx->P > 0) ? 1u : 0u;
     p->hits = ctx->d_hits;
     p->count = ctx->d_count;
     p->cap = ctx->hit_cap;

@@ -55,6 +55,7 @@ struct SearchParams {
     // PAM
     uint32_t P, pam_dir, pam_flags;
     uint32_t pam_sets[8];       // per PAM position: allowed set over {A=1,C=2,G=4,T=8}
+    uint32_t gate_first;        // 1: evaluate the PAM gate before any index work
     // output
     bc_hit* hits;
     unsigned long long* count;  // [0] hits, [1] candidates, [2] probes
@@ -81,6 +82,44 @@ __device__ __forceinline__ uint32_t bc_combo_key(const ComboDesc& cd, uint32_t h
 }
 
 __device__ __forceinline__ uint32_t bc_rev_bits(uint32_t m, uint32_t L) { return __brev(m) >> (32 - L); }
+
+// PAM-first gate (BC_PAM_GATE): can a window at dev position `pos` still produce a reportable hit
+// on at least one strand?  Evaluated before any index work, so at NGG about 7 windows in 8 are
+// dropped up front.  A PAM site that touches a non-ACGT base or a contig end counts as "maybe":
+// bc_make_hit decides those exactly (ambiguous PAMs are kept for the host, truncated ones dropped).
+struct PamGate {
+    uint32_t P, L, right_for_plus;  // right_for_plus: '+' hits have their PAM right of the window
+    uint32_t sets[8];
+};
+
+__device__ __forceinline__ bool bc_gate_side(const PamGate& g, const uint32_t* __restrict__ H,
+                                             const uint32_t* __restrict__ Lo, const uint32_t* __restrict__ B,
+                                             uint32_t a, bool rc) {
+    const uint32_t pm = (1u << g.P) - 1u;
+    if (bc_window(B, a) & pm) return true;  // ambiguous or contig end: decided later
+    const uint32_t h = bc_window(H, a), l = bc_window(Lo, a);
+    for (uint32_t i = 0; i < g.P; i++) {
+        const uint32_t j = rc ? g.P - 1 - i : i;
+        uint32_t code = (((h >> j) & 1u) << 1) | ((l >> j) & 1u);
+        if (rc) code = 3u - code;
+        if (!((g.sets[i] >> code) & 1u)) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool bc_gate_window(const PamGate& g, const uint32_t* __restrict__ H,
+                                               const uint32_t* __restrict__ Lo, const uint32_t* __restrict__ B,
+                                               uint32_t pos) {
+    // '+' strand hits read the PAM forward on one side, '-' strand hits read it reverse-complemented
+    // on the other side
+    const uint32_t right = pos + g.L;
+    const bool left_ok = pos >= g.P;
+    const bool plus = g.right_for_plus ? bc_gate_side(g, H, Lo, B, right, false)
+                                       : (left_ok && bc_gate_side(g, H, Lo, B, pos - g.P, false));
+    if (plus) return true;
+    return g.right_for_plus ? (left_ok && bc_gate_side(g, H, Lo, B, pos - g.P, true))
+                            : bc_gate_side(g, H, Lo, B, right, true);
+}
 
 // Ownership: a hit with <= k mismatches has >= b-k exact blocks; it is reported by the seed
 // combination made of its LOWEST b-k exact blocks and by no other, so every alignment is emitted

@@ -307,6 +307,9 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
     __shared__ HitStage stage;
     if (threadIdx.x == 0) stage.n = 0;
     const uint32_t lm = bc_lmask(p.L);
+    PamGate gate;
+    gate.P = p.P; gate.L = p.L; gate.right_for_plus = p.pam_dir == 0;
+    for (int i = 0; i < 8; i++) gate.sets[i] = p.pam_sets[i];
     unsigned long long cand = 0, probes = 0;
     for (uint32_t tile = p.pos_begin / PROBE_TILE_POS + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t w0 = tile * PROBE_TILE_WORDS;
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
             const uint32_t pos = tile * PROBE_TILE_POS + t;
             if (pos < p.pos_begin || pos >= p.pos_end) continue;
             if (bc_window(sB, t) & lm) continue;  // window touches a non-ACGT base or a contig end
+            if (p.gate_first && !bc_gate_window(gate, p.H, p.Lo, p.B, pos)) continue;
             const uint32_t wh = bc_window(sH, t) & lm, wl = bc_window(sL, t) & lm;
             for (uint32_t c = 0; c < p.n_combos; c++) {
                 const uint32_t slot = p.combo[c].dir_off + bc_combo_key(p.combo[c], wh, wl);

@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--shard", default=None, choices=["library", "genome"],
                     help="multi-GPU partitioning: library shards (weak scaling, default) or genome ranges "
                          "(strong scaling; default for cfg5, which is probe-bound)")
+    ap.add_argument("--gate", action="store_true", help="PAM-first gating: report only PAM-adjacent hits")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel experiments only)")
     ap.add_argument("--verify", action="store_true", help="check a sample of the result against the oracle")
     args = ap.parse_args()
@@ -251,7 +252,7 @@ def main():
     torch.cuda.synchronize()
 
     s = _native.Searcher(local_rank)
-    s.set_pam(cfg["pam"], "downstream", iupac=cfg["iupac"], gate=False)
+    s.set_pam(cfg["pam"], "downstream", iupac=cfg["iupac"], gate=args.gate)
     if shard == "library":
         s.set_param(_native.BC_PARAM_SPACER_ID_BASE, rank * n)
     else:  # every rank holds the whole library and scans its 1/world slice of the genome
@@ -427,7 +428,7 @@ def main():
         "scaling": "weak" if shard == "library" else "strong", "vs_baseline": None,
         "dtype": "u32 bit-planes (XOR/popcount)", "data": "synthetic",
         "config": {"workload": cfg["name"], "k": k, "pam": cfg["pam"], "spacers_per_gpu": n, "genome_bp": G,
-                   "L": L, "parallelism": (f"library-shard x{world}, genome replicated" if shard == "library" else
+                   "L": L, "pam_gate": bool(args.gate), "parallelism": (f"library-shard x{world}, genome replicated" if shard == "library" else
                                            f"genome-range x{world}, library replicated"),
                    "seed_scheme": f"b={st['blocks']} blocks, {combos} combinations, path={st['path']}",
                    "l2": "working set (window records + index) is far larger than the 126 MB L2; no flush needed",
