@@ -153,13 +153,15 @@ static int set_genome_common(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t
     for (uint32_t c = 0; c < n_contigs; c++)
         if (contig_offsets[c + 1] < contig_offsets[c]) return fail(ctx, BC_EINVAL, "contig_offsets must be non-decreasing");
     if (contig_offsets[0] != 0) return fail(ctx, BC_EINVAL, "contig_offsets[0] must be 0");
-    if (G + n_contigs + 64 >= (1ull << 32)) return fail(ctx, BC_ELIMIT, "genome longer than 2^32 - 64 positions");
+    if (G + n_contigs + 8192 >= (1ull << 32)) return fail(ctx, BC_ELIMIT, "genome longer than 2^32 - 8192 positions");
     ctx->have_genome = false;
     ctx->G = G;
     ctx->n_contigs = n_contigs;
     ctx->coff.assign(contig_offsets, contig_offsets + n_contigs + 1);
     ctx->n_pos = (uint32_t)(G + n_contigs);
-    ctx->n_words = (ctx->n_pos + 31) / 32 + 4;  // tail words are all-ambiguous padding
+    // whole probe tiles (2048 positions = 64 words) plus one halo tile: every kernel may read a
+    // full tile and the word after it; the tail words are all-ambiguous padding
+    ctx->n_words = ((ctx->n_pos + 2047) / 2048) * 64 + 64 + 4;
     dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B); dfree(ctx->d_start_dev);
     CK(cudaMalloc(&ctx->d_H, (size_t)ctx->n_words * 4));
     CK(cudaMalloc(&ctx->d_L, (size_t)ctx->n_words * 4));
