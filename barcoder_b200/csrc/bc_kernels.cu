@@ -299,47 +299,66 @@ cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cud
 #define PROBE_THREADS 256
 #define PROBE_STEPS 8
 #define PROBE_TILE_POS (PROBE_THREADS * PROBE_STEPS)  // 2048 windows
-#define PROBE_TILE_WORDS (PROBE_TILE_POS / 32)        // 64 words per plane (+1 halo)
+#define PROBE_TILE_WORDS (PROBE_TILE_POS / 32)        // 64 words per plane, + 1 halo word before, 2 after
+#define PROBE_SMEM_WORDS (PROBE_TILE_WORDS + 3)
+#define PROBE_BATCH 4                                 // combinations probed together (loads in flight)
 
 __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_constant__ SearchParams p,
                                                               uint32_t n_tiles) {
-    __shared__ uint32_t sH[PROBE_TILE_WORDS + 1], sL[PROBE_TILE_WORDS + 1], sB[PROBE_TILE_WORDS + 1];
+    // plane words [w0 - 1, w0 + 66): the tile, the word before it (PAM left of the first window)
+    // and two after it (window + PAM right of the last window)
+    __shared__ uint32_t sH[PROBE_SMEM_WORDS], sL[PROBE_SMEM_WORDS], sB[PROBE_SMEM_WORDS];
     __shared__ HitStage stage;
     if (threadIdx.x == 0) stage.n = 0;
     const uint32_t lm = bc_lmask(p.L);
     PamGate gate;
     gate.P = p.P; gate.L = p.L; gate.right_for_plus = p.pam_dir == 0;
     for (int i = 0; i < 8; i++) gate.sets[i] = p.pam_sets[i];
+    const int k = (int)p.k;
     unsigned long long cand = 0, probes = 0;
     for (uint32_t tile = p.pos_begin / PROBE_TILE_POS + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t w0 = tile * PROBE_TILE_WORDS;
         __syncthreads();
-        if (threadIdx.x <= PROBE_TILE_WORDS) {  // planes are padded, w0 + 64 is always readable
-            sH[threadIdx.x] = p.H[w0 + threadIdx.x];
-            sL[threadIdx.x] = p.Lo[w0 + threadIdx.x];
-            sB[threadIdx.x] = p.B[w0 + threadIdx.x];
+        if (threadIdx.x < PROBE_SMEM_WORDS) {  // planes are padded by a whole tile (bc_api.cu)
+            const bool before = (w0 == 0 && threadIdx.x == 0);  // nothing precedes position 0
+            sH[threadIdx.x] = before ? 0u : p.H[w0 - 1 + threadIdx.x];
+            sL[threadIdx.x] = before ? 0u : p.Lo[w0 - 1 + threadIdx.x];
+            sB[threadIdx.x] = before ? 0xffffffffu : p.B[w0 - 1 + threadIdx.x];
         }
         __syncthreads();
 #pragma unroll 1
         for (uint32_t step = 0; step < PROBE_STEPS; step++) {
             const uint32_t t = step * PROBE_THREADS + threadIdx.x;
             const uint32_t pos = tile * PROBE_TILE_POS + t;
+            const uint32_t ts = t + 32;  // position inside the staged words
             if (pos < p.pos_begin || pos >= p.pos_end) continue;
-            if (bc_window(sB, t) & lm) continue;  // window touches a non-ACGT base or a contig end
-            if (p.gate_first && !bc_gate_window(gate, p.H, p.Lo, p.B, pos)) continue;
-            const uint32_t wh = bc_window(sH, t) & lm, wl = bc_window(sL, t) & lm;
-            for (uint32_t c = 0; c < p.n_combos; c++) {
-                const uint32_t slot = p.combo[c].dir_off + bc_combo_key(p.combo[c], wh, wl);
-                uint32_t e = p.dir[slot];
-                const uint32_t e_end = p.dir[slot + 1];
-                probes++;
-                for (; e < e_end; e++) {
-                    const uint2 q = p.ent_hl[e];
-                    const uint32_t m = (wh ^ q.x) | (wl ^ q.y);
-                    cand++;
-                    if (__popc(m) <= (int)p.k) {
-                        uint4 rec;
-                        if (bc_make_hit(p, c, pos, p.ent_id[e], m, &rec)) bc_stage_hit(p, &stage, rec);
+            if (bc_window(sB, ts) & lm) continue;  // window touches a non-ACGT base or a contig end
+            if (p.gate_first && !bc_gate_window(gate, sH, sL, sB, ts)) continue;
+            const uint32_t wh = bc_window(sH, ts) & lm, wl = bc_window(sL, ts) & lm;
+#pragma unroll 1
+            for (uint32_t c0 = 0; c0 < p.n_combos; c0 += PROBE_BATCH) {
+                // all directory reads of the batch are issued before the first one is consumed
+                uint32_t eb[PROBE_BATCH], ee[PROBE_BATCH];
+#pragma unroll
+                for (int j = 0; j < PROBE_BATCH; j++) {
+                    eb[j] = ee[j] = 0;
+                    if (c0 + j < p.n_combos) {
+                        const uint32_t slot = p.combo[c0 + j].dir_off + bc_combo_key(p.combo[c0 + j], wh, wl);
+                        eb[j] = __ldg(p.dir + slot);
+                        ee[j] = __ldg(p.dir + slot + 1);
+                    }
+                }
+                probes += min((uint32_t)PROBE_BATCH, p.n_combos - c0);
+#pragma unroll
+                for (int j = 0; j < PROBE_BATCH; j++) {
+                    for (uint32_t e = eb[j]; e < ee[j]; e++) {
+                        const uint2 q = __ldg(p.ent_hl + e);
+                        const uint32_t m = (wh ^ q.x) | (wl ^ q.y);
+                        cand++;
+                        if (__popc(m) <= k) {
+                            uint4 rec;
+                            if (bc_make_hit(p, c0 + j, pos, p.ent_id[e], m, &rec)) bc_stage_hit(p, &stage, rec);
+                        }
                     }
                 }
             }
