@@ -297,27 +297,45 @@ cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cud
 // verifies the bucket's entries with XOR + popcount.  Replaces bowtie align
 // (BowtieRunner.py:104-141) for libraries whose buckets are small.
 #define PROBE_THREADS 256
+#define PROBE_WARPS (PROBE_THREADS / 32)
 #define PROBE_STEPS 8
-#define PROBE_TILE_POS (PROBE_THREADS * PROBE_STEPS)  // 2048 windows
+#define PROBE_TILE_POS (PROBE_THREADS * PROBE_STEPS)  // 2048 windows per CTA tile, 256 per warp
 #define PROBE_TILE_WORDS (PROBE_TILE_POS / 32)        // 64 words per plane, + 1 halo word before, 2 after
 #define PROBE_SMEM_WORDS (PROBE_TILE_WORDS + 3)
 #define PROBE_BATCH 4                                 // combinations probed together (loads in flight)
+#define PROBE_L2_CAP 128                              // per-warp list of non-empty buckets
 
+// Three dense phases per warp and tile, so that no lane idles while a neighbour works (ncu on the
+// one-thread-per-window version: 8.5 active lanes per instruction with the PAM gate on, 23 without):
+//   A  every lane tests its 8 windows (valid, PAM gate) and the survivors are compacted;
+//   B  one survivor per lane: seed keys, directory probes (loads batched), non-empty buckets are
+//      pushed to a per-warp list {window, combination, begin, end};
+//   C  one bucket per lane: XOR/LOP3 + POPC over its entries, hits staged per CTA.
 __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_constant__ SearchParams p,
                                                               uint32_t n_tiles) {
     // plane words [w0 - 1, w0 + 66): the tile, the word before it (PAM left of the first window)
     // and two after it (window + PAM right of the last window)
     __shared__ uint32_t sH[PROBE_SMEM_WORDS], sL[PROBE_SMEM_WORDS], sB[PROBE_SMEM_WORDS];
     __shared__ HitStage stage;
+    __shared__ uint16_t s_l1[PROBE_WARPS][PROBE_THREADS];   // surviving windows of the warp (tile-local)
+    __shared__ uint4 s_l2[PROBE_WARPS][PROBE_L2_CAP];       // non-empty buckets of the warp
+    __shared__ uint32_t s_n2[PROBE_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) stage.n = 0;
+    if (lane == 0) s_n2[warp] = 0;
     const uint32_t lm = bc_lmask(p.L);
     PamGate gate;
     gate.P = p.P; gate.L = p.L; gate.right_for_plus = p.pam_dir == 0;
     for (int i = 0; i < 8; i++) gate.sets[i] = p.pam_sets[i];
     const int k = (int)p.k;
+    uint16_t* l1 = s_l1[warp];
+    uint4* l2 = s_l2[warp];
+    uint32_t* n2p = &s_n2[warp];
     unsigned long long cand = 0, probes = 0;
+
     for (uint32_t tile = p.pos_begin / PROBE_TILE_POS + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t w0 = tile * PROBE_TILE_WORDS;
+        const uint32_t tile_pos = tile * PROBE_TILE_POS;
         __syncthreads();
         if (threadIdx.x < PROBE_SMEM_WORDS) {  // planes are padded by a whole tile (bc_api.cu)
             const bool before = (w0 == 0 && threadIdx.x == 0);  // nothing precedes position 0
@@ -326,41 +344,81 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
             sB[threadIdx.x] = before ? 0xffffffffu : p.B[w0 - 1 + threadIdx.x];
         }
         __syncthreads();
+
+        // ---- phase A: compact the windows that can still produce a hit
+        uint32_t n1 = 0;
 #pragma unroll 1
-        for (uint32_t step = 0; step < PROBE_STEPS; step++) {
-            const uint32_t t = step * PROBE_THREADS + threadIdx.x;
-            const uint32_t pos = tile * PROBE_TILE_POS + t;
+        for (uint32_t i = 0; i < PROBE_STEPS; i++) {
+            const uint32_t t = warp * (PROBE_TILE_POS / PROBE_WARPS) + i * 32 + lane;
+            const uint32_t pos = tile_pos + t;
             const uint32_t ts = t + 32;  // position inside the staged words
-            if (pos < p.pos_begin || pos >= p.pos_end) continue;
-            if (bc_window(sB, ts) & lm) continue;  // window touches a non-ACGT base or a contig end
-            if (p.gate_first && !bc_gate_window(gate, sH, sL, sB, ts)) continue;
-            const uint32_t wh = bc_window(sH, ts) & lm, wl = bc_window(sL, ts) & lm;
+            bool ok = pos >= p.pos_begin && pos < p.pos_end && !(bc_window(sB, ts) & lm);
+            if (ok && p.gate_first) ok = bc_gate_window(gate, sH, sL, sB, ts);
+            const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+            if (ok) l1[n1 + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)t;
+            n1 += __popc(ballot);
+        }
+        __syncwarp();
+
+        // ---- phase B (+ C whenever the bucket list fills up)
+        for (uint32_t r = 0; r < n1 || *n2p; r += 32) {  // warp-uniform: n1 and *n2p are shared by the warp
+            if (r < n1) {
+                const bool have = r + lane < n1;
+                const uint32_t t = have ? l1[r + lane] : 0;
+                const uint32_t ts = t + 32;
+                const uint32_t wh = bc_window(sH, ts) & lm, wl = bc_window(sL, ts) & lm;
 #pragma unroll 1
-            for (uint32_t c0 = 0; c0 < p.n_combos; c0 += PROBE_BATCH) {
-                // all directory reads of the batch are issued before the first one is consumed
-                uint32_t eb[PROBE_BATCH], ee[PROBE_BATCH];
+                for (uint32_t c0 = 0; c0 < p.n_combos; c0 += PROBE_BATCH) {
+                    // all directory reads of the batch are issued before the first one is consumed
+                    uint32_t eb[PROBE_BATCH], ee[PROBE_BATCH];
 #pragma unroll
-                for (int j = 0; j < PROBE_BATCH; j++) {
-                    eb[j] = ee[j] = 0;
-                    if (c0 + j < p.n_combos) {
-                        const uint32_t slot = p.combo[c0 + j].dir_off + bc_combo_key(p.combo[c0 + j], wh, wl);
-                        eb[j] = __ldg(p.dir + slot);
-                        ee[j] = __ldg(p.dir + slot + 1);
-                    }
-                }
-                probes += min((uint32_t)PROBE_BATCH, p.n_combos - c0);
-#pragma unroll
-                for (int j = 0; j < PROBE_BATCH; j++) {
-                    for (uint32_t e = eb[j]; e < ee[j]; e++) {
-                        const uint2 q = __ldg(p.ent_hl + e);
-                        const uint32_t m = (wh ^ q.x) | (wl ^ q.y);
-                        cand++;
-                        if (__popc(m) <= k) {
-                            uint4 rec;
-                            if (bc_make_hit(p, c0 + j, pos, p.ent_id[e], m, &rec)) bc_stage_hit(p, &stage, rec);
+                    for (int j = 0; j < PROBE_BATCH; j++) {
+                        eb[j] = ee[j] = 0;
+                        if (have && c0 + j < p.n_combos) {
+                            const uint32_t slot = p.combo[c0 + j].dir_off + bc_combo_key(p.combo[c0 + j], wh, wl);
+                            eb[j] = __ldg(p.dir + slot);
+                            ee[j] = __ldg(p.dir + slot + 1);
                         }
                     }
+                    if (have) probes += min((uint32_t)PROBE_BATCH, p.n_combos - c0);
+#pragma unroll
+                    for (int j = 0; j < PROBE_BATCH; j++) {
+                        if (eb[j] < ee[j]) {
+                            const uint32_t s2 = atomicAdd(n2p, 1u);  // < PROBE_L2_CAP: drained below before it can fill
+                            l2[s2] = make_uint4(t, c0 + j, eb[j], ee[j]);
+                        }
+                    }
+                    __syncwarp();
+                    if (*n2p + 32 * PROBE_BATCH <= PROBE_L2_CAP && (c0 + PROBE_BATCH < p.n_combos || r + 32 < n1))
+                        continue;  // room for another batch: keep collecting
+                    // ---- phase C: one bucket per lane
+                    const uint32_t n2 = *n2p;
+                    for (uint32_t b0 = 0; b0 < n2; b0 += 32) {
+                        if (b0 + lane < n2) {
+                            const uint4 it = l2[b0 + lane];
+                            const uint32_t its = it.x + 32;
+                            const uint32_t bh = bc_window(sH, its) & lm, bl = bc_window(sL, its) & lm;
+                            cand += it.w - it.z;
+                            for (uint32_t e = it.z; e < it.w; e++) {
+                                const uint2 q = __ldg(p.ent_hl + e);
+                                const uint32_t m = (bh ^ q.x) | (bl ^ q.y);
+                                if (__popc(m) <= k) {
+                                    uint4 rec;
+                                    if (bc_make_hit(p, it.y, tile_pos + it.x, p.ent_id[e], m, &rec))
+                                        bc_stage_hit(p, &stage, rec);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) *n2p = 0;
+                    __syncwarp();
                 }
+            } else {
+                // nothing left to probe but buckets are pending (cannot happen with the drain rule
+                // above; kept so the loop condition is always safe)
+                if (lane == 0) *n2p = 0;
+                __syncwarp();
             }
         }
         bc_flush_hits(p, &stage);
