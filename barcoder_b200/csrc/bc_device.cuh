@@ -89,22 +89,35 @@ __device__ __forceinline__ uint32_t bc_rev_bits(uint32_t m, uint32_t L) { return
 // bc_make_hit decides those exactly (ambiguous PAMs are kept for the host, truncated ones dropped).
 struct PamGate {
     uint32_t P, L, right_for_plus;  // right_for_plus: '+' hits have their PAM right of the window
-    uint32_t sets[8];
+    uint32_t fwd[4];                // bit j set: base code c is allowed at window bit j ('+' strand reading)
+    uint32_t rc[4];                 // same for the reverse-complement reading ('-' strand hits)
 };
 
+// Build the bit masks from the per-position sets (pam_sets[i] over {A=1,C=2,G=4,T=8}).
+__device__ __forceinline__ void bc_gate_init(PamGate& g, uint32_t P, uint32_t L, uint32_t pam_dir,
+                                             const uint32_t* pam_sets) {
+    g.P = P; g.L = L; g.right_for_plus = pam_dir == 0;
+    for (int c = 0; c < 4; c++) g.fwd[c] = g.rc[c] = 0;
+    for (uint32_t i = 0; i < P; i++) {
+        for (uint32_t c = 0; c < 4; c++) {
+            if ((pam_sets[i] >> c) & 1u) {
+                g.fwd[c] |= 1u << i;                // PAM position i is window bit i
+                g.rc[3u - c] |= 1u << (P - 1 - i);  // read backwards, complemented
+            }
+        }
+    }
+}
+
+// All P positions at once: a position is satisfied when its (h, l) code is in its allowed set.
 __device__ __forceinline__ bool bc_gate_side(const PamGate& g, const uint32_t* __restrict__ H,
                                              const uint32_t* __restrict__ Lo, const uint32_t* __restrict__ B,
                                              uint32_t a, bool rc) {
     const uint32_t pm = (1u << g.P) - 1u;
     if (bc_window(B, a) & pm) return true;  // ambiguous or contig end: decided later
     const uint32_t h = bc_window(H, a), l = bc_window(Lo, a);
-    for (uint32_t i = 0; i < g.P; i++) {
-        const uint32_t j = rc ? g.P - 1 - i : i;
-        uint32_t code = (((h >> j) & 1u) << 1) | ((l >> j) & 1u);
-        if (rc) code = 3u - code;
-        if (!((g.sets[i] >> code) & 1u)) return false;
-    }
-    return true;
+    const uint32_t* m = rc ? g.rc : g.fwd;
+    const uint32_t sat = (~h & ~l & m[0]) | (~h & l & m[1]) | (h & ~l & m[2]) | (h & l & m[3]);
+    return (sat & pm) == pm;
 }
 
 __device__ __forceinline__ bool bc_gate_window(const PamGate& g, const uint32_t* __restrict__ H,

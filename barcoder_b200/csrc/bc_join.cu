@@ -28,7 +28,7 @@ struct BucketParams {
     const uint32_t* lib_dir;      // library directory (to skip windows whose bucket is empty)
     uint32_t pos_begin, pos_end;  // dev positions handled by this chunk of the genome
     uint32_t L, n_combos, prune, gate_first;
-    PamGate gate;
+    uint32_t P, pam_dir, pam_sets[8];
     ComboDesc combo[BC_MAX_COMBOS];
 };
 
@@ -49,10 +49,12 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
     const uint32_t lm = bc_lmask(gp.L);
     const uint32_t c = blockIdx.y;
     const ComboDesc& cd = gp.combo[c];
+    PamGate gate;
+    bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
     for (uint32_t pos = gp.pos_begin + blockIdx.x * blockDim.x + threadIdx.x; pos < gp.pos_end;
          pos += gridDim.x * blockDim.x) {
         if (bc_window(gp.B, pos) & lm) continue;
-        if (gp.gate_first && !bc_gate_window(gp.gate, gp.H, gp.Lo, gp.B, pos)) continue;
+        if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
         const uint32_t wh = bc_window(gp.H, pos) & lm, wl = bc_window(gp.Lo, pos) & lm;
         const uint32_t slot = cd.dir_off + bc_combo_key(cd, wh, wl);
         if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
@@ -373,8 +375,8 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     // Skipping windows whose library bucket is empty only pays when most buckets are empty.
     gp.prune = p.dir_entries < (dir_slots - 1) * 2 ? 1u : 0u;
     gp.gate_first = p.gate_first;
-    gp.gate.P = p.P; gp.gate.L = p.L; gp.gate.right_for_plus = p.pam_dir == 0;
-    for (int i = 0; i < 8; i++) gp.gate.sets[i] = p.pam_sets[i];
+    gp.P = p.P; gp.pam_dir = p.pam_dir;
+    for (int i = 0; i < 8; i++) gp.pam_sets[i] = p.pam_sets[i];
 
     for (uint64_t begin = p.pos_begin; begin < p.pos_end; begin += chunk) {
         gp.pos_begin = (uint32_t)begin;

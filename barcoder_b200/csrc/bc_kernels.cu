@@ -325,8 +325,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
     if (lane == 0) s_n2[warp] = 0;
     const uint32_t lm = bc_lmask(p.L);
     PamGate gate;
-    gate.P = p.P; gate.L = p.L; gate.right_for_plus = p.pam_dir == 0;
-    for (int i = 0; i < 8; i++) gate.sets[i] = p.pam_sets[i];
+    bc_gate_init(gate, p.P, p.L, p.pam_dir, p.pam_sets);
     const int k = (int)p.k;
     uint16_t* l1 = s_l1[warp];
     uint4* l2 = s_l2[warp];
