@@ -295,141 +295,6 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
 }
 #undef MV_CANDIDATE
 
-// ------------------------------------------------------------------------------ slot-major verify
-// One warp takes whole directory slots from a work queue.  For a slot, the genome bucket
-// gwin[gdir[slot] .. gdir[slot+1]) is cut into chunks of up to 32*ITEMS windows that all share
-// the library bucket ent[dir[slot] .. dir[slot+1]); every chunk walks that bucket once with the
-// software-pipelined 4-entry x ITEMS-window group loop.  Compared with fixed 128-record tiles this
-// never straddles two slots (no "sparse" remainder kernel) and adapts ITEMS to small buckets
-// (cfg 4 at b=6: ~95 windows per slot -> one chunk of 3 windows per lane).
-#define MV_SLOT_MAJOR 1   // 1: k_slot_verify; 0: k_merge_verify<dense> + <sparse> (fixed tiles)
-#define SV_UNIT 8         // slots claimed per queue transaction
-
-template <int ITEMS>
-static __device__ __noinline__ void sv_walk(const SearchParams& p, const uint2* __restrict__ ent, uint32_t ls,
-                                        uint32_t le, const uint4* __restrict__ gwin, uint32_t chunk, uint32_t ge,
-                                        int k, int k1, uint4* q, uint32_t* qn, uint32_t lane) {
-    uint4 wv[ITEMS];
-    uint32_t act = 0;
-#pragma unroll
-    for (int it = 0; it < ITEMS; it++) {
-        const uint32_t i = chunk + it * 32 + lane;
-        wv[it] = __ldcs(gwin + min(i, ge - 1));  // lanes past the end replicate the last window
-        act |= (i < ge ? 1u : 0u) << it;
-    }
-#define MV_CANDIDATE(E, Q)                                                                      \
-    do {                                                                                        \
-        const uint32_t m_ = (w.y ^ (Q).x) | (w.z ^ (Q).y);                                      \
-        const uint32_t qs = atomicAdd(qn, 1u);                                                  \
-        if (qs < MV_WQ) q[qs] = make_uint4(w.x, m_, (E), w.w);                                  \
-        else mv_overflow(p, w.x, m_, (E), w.w);                                                 \
-    } while (0)
-    const uint32_t n_groups = (le - ls) / MV_DENSE_ENTRIES;
-    const uint2* gp = ent + ls;
-    uint2 cur[MV_DENSE_ENTRIES];
-    if (n_groups) {
-#pragma unroll
-        for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = __ldg(gp + j);
-    }
-    uint32_t since_drain = 0;
-    for (uint32_t g = 0; g < n_groups; g++, gp += MV_DENSE_ENTRIES) {
-        uint2 nxt[MV_DENSE_ENTRIES];
-        if (g + 1 < n_groups) {  // warp-uniform
-#pragma unroll
-            for (int j = 0; j < MV_DENSE_ENTRIES; j++) nxt[j] = __ldg(gp + MV_DENSE_ENTRIES + j);
-        }
-        int d[ITEMS][MV_DENSE_ENTRIES];
-        int acc = 0;
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-#pragma unroll
-            for (int j = 0; j < MV_DENSE_ENTRIES; j++) {
-                d[it][j] = __popc((wv[it].y ^ cur[j].x) | (wv[it].z ^ cur[j].y)) - k1;
-                acc |= d[it][j];
-            }
-        }
-        if (acc < 0) {
-            const uint32_t e = ls + g * MV_DENSE_ENTRIES;
-#pragma unroll
-            for (int it = 0; it < ITEMS; it++) {
-                const uint4 w = wv[it];
-#pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                    if (d[it][j] < 0 && ((act >> it) & 1u)) MV_CANDIDATE(e + j, cur[j]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = nxt[j];
-        since_drain += MV_DENSE_ENTRIES;
-        if (since_drain >= 32) {  // warp-uniform
-            since_drain = 0;
-            mv_drain(p, q, qn, lane);
-        }
-    }
-    for (uint32_t e = ls + n_groups * MV_DENSE_ENTRIES; e < le; e++) {  // < MV_DENSE_ENTRIES entries
-        const uint2 qq = __ldg(ent + e);
-#pragma unroll
-        for (int it = 0; it < ITEMS; it++) {
-            const uint4 w = wv[it];
-            if (((act >> it) & 1u) && __popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
-        }
-    }
-    mv_drain(p, q, qn, lane);
-#undef MV_CANDIDATE
-}
-
-__global__ void __launch_bounds__(MV_THREADS, 2) k_slot_verify(const __grid_constant__ SearchParams p,
-                                                               const uint32_t* __restrict__ gdir,
-                                                               const uint4* __restrict__ gwin, uint32_t n_slots,
-                                                               uint32_t* __restrict__ work) {
-    __shared__ uint4 s_q[MV_WARPS][MV_WQ];
-    __shared__ uint32_t s_qn[MV_WARPS];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint4* q = s_q[warp];
-    uint32_t* qn = &s_qn[warp];
-    if (lane == 0) *qn = 0;
-    __syncwarp();
-    const int k = (int)p.k, k1 = k + 1;
-    const uint2* __restrict__ ent = p.ent_hl;
-    unsigned long long cand = 0;
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, (uint32_t)SV_UNIT);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_slots) break;
-        // lanes 0..SV_UNIT-1 fetch the four directory words of their slot; the loop below broadcasts them
-        uint32_t gs_l = 0, ge_l = 0, ls_l = 0, le_l = 0;
-        if (lane < SV_UNIT && base + lane < n_slots) {
-            gs_l = __ldg(gdir + base + lane);
-            ge_l = __ldg(gdir + base + lane + 1);
-            ls_l = __ldg(p.dir + base + lane);
-            le_l = __ldg(p.dir + base + lane + 1);
-        }
-#pragma unroll 1
-        for (int j = 0; j < SV_UNIT; j++) {
-            const uint32_t gs = __shfl_sync(0xffffffffu, gs_l, j), ge = __shfl_sync(0xffffffffu, ge_l, j);
-            const uint32_t ls = __shfl_sync(0xffffffffu, ls_l, j), le = __shfl_sync(0xffffffffu, le_l, j);
-            if (gs >= ge || ls >= le) continue;
-            cand += (unsigned long long)(le - ls) * (ge - gs) * (lane == 0);
-#pragma unroll 1
-            for (uint32_t chunk = gs; chunk < ge; chunk += 32 * MV_ITEMS) {
-                const uint32_t n = min(ge - chunk, (uint32_t)(32 * MV_ITEMS));
-                const uint32_t items = (n + 31) >> 5;
-                switch (items) {
-                    case 1: sv_walk<1>(p, ent, ls, le, gwin, chunk, ge, k, k1, q, qn, lane); break;
-                    case 2: sv_walk<2>(p, ent, ls, le, gwin, chunk, ge, k, k1, q, qn, lane); break;
-                    case 3: sv_walk<3>(p, ent, ls, le, gwin, chunk, ge, k, k1, q, qn, lane); break;
-                    default: sv_walk<4>(p, ent, ls, le, gwin, chunk, ge, k, k1, q, qn, lane); break;
-                }
-            }
-        }
-    }
-    __syncwarp();
-    const uint32_t nq = min(*qn, (uint32_t)MV_WQ);
-    if (nq) mv_resolve(p, q, nq);
-    if (p.count_candidates) atomicAdd(p.count + 1, cand);
-}
-
 // ------------------------------------------------------------------------------------------ host
 bool bc_join_supported(const ComboDesc*, uint32_t n_combos, uint64_t) { return n_combos > 0; }
 
@@ -439,7 +304,6 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_gwin) cudaFree(ws.d_gwin);
     if (ws.d_gtmp) cudaFree(ws.d_gtmp);
     if (ws.d_coarse_cursor) cudaFree(ws.d_coarse_cursor);
-    if (ws.d_work) cudaFree(ws.d_work);
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
@@ -540,18 +404,10 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         }
         JCK(cudaEventRecord(ws.ev_a, st));
         // the last directory slot is the end sentinel: after the scan it holds the record count
-        if (MV_SLOT_MAJOR) {
-            if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, 64));
-            JCK(cudaMemsetAsync(ws.d_work, 0, 4, st));
-            k_slot_verify<<<(uint32_t)sm_count * 2u, MV_THREADS, 0, st>>>(p, ws.d_gdir, ws.d_gwin,
-                                                                          (uint32_t)(dir_slots - 1), ws.d_work);
-            JCK(cudaGetLastError());
-        } else {
-            k_merge_verify<true><<<(uint32_t)sm_count * 8u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
-            JCK(cudaGetLastError());
-            k_merge_verify<false><<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
-            JCK(cudaGetLastError());
-        }
+        k_merge_verify<true><<<(uint32_t)sm_count * 8u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
+        JCK(cudaGetLastError());
+        k_merge_verify<false><<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
+        JCK(cudaGetLastError());
         JCK(cudaEventRecord(ws.ev_b, st));
         bc_launch_counter += 4;
         // events are reused per chunk, so read them before the next record
