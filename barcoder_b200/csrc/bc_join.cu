@@ -164,7 +164,7 @@ __device__ __forceinline__ void mv_drain(const SearchParams& p, uint4* q, uint32
 }
 
 template <bool DENSE>
-__global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_merge_verify(const __grid_constant__ SearchParams p,
+__global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_merge_verify(const __grid_constant__ SearchParams p,
                                                                 const uint4* __restrict__ gwin,
                                                                 const uint32_t* __restrict__ n_rec_ptr) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_merge_verify
         const bool uniform = (first + wtile <= n_rec) && (__ldg(&gwin[first].w) == __ldg(&gwin[last].w));
         if (uniform != DENSE) continue;
         uint4 wv[MV_ITEMS];
-        if (DENSE) {
 #pragma unroll
-            for (int it = 0; it < MV_ITEMS; it++) wv[it] = __ldcs(gwin + first + it * 32 + lane);
+        for (int it = 0; it < MV_ITEMS; it++) wv[it] = __ldcs(gwin + min(first + it * 32 + lane, n_rec - 1));
+        if (DENSE) {
             const uint32_t ls = __ldg(p.dir + wv[0].w), le = __ldg(p.dir + wv[0].w + 1);
             cand += (unsigned long long)(le - ls) * MV_ITEMS;
             // Software-pipelined walk over the bucket in groups of MV_DENSE_ENTRIES entries: the
@@ -251,85 +251,41 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_merge_verify
             }
             mv_drain(p, q, qn, lane);
         } else {
-            // Lane-blocked walk: every lane owns MV_ITEMS CONSECUTIVE records (re-read in that
-            // layout: 64 contiguous bytes per lane), which almost always share one slot even when
-            // the warp-tile spans several.  Such a lane walks its bucket once for all its windows
-            // with the same 4-entry x MV_ITEMS-window group loop as the dense kernel; lanes of the
-            // same slot read the same addresses (partial broadcasts).  The loop runs to the warp's
-            // longest bucket so the queue can be drained at warp-uniform points.
-            uint32_t act = 0;
+            // Issue the directory loads of all MV_ITEMS records before any dependent work.
+            uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
 #pragma unroll
             for (int it = 0; it < MV_ITEMS; it++) {
-                const uint32_t i = first + lane * MV_ITEMS + it;
-                wv[it] = __ldcs(gwin + min(i, n_rec - 1));
-                act |= (i < n_rec ? 1u : 0u) << it;
+                lsv[it] = __ldg(p.dir + wv[it].w);
+                lev[it] = first + it * 32 + lane < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
             }
-            const bool lane_uniform = act == (1u << MV_ITEMS) - 1u && wv[0].w == wv[MV_ITEMS - 1].w;
-            uint32_t ls = 0, le = 0;
-            if (lane_uniform) {
-                ls = __ldg(p.dir + wv[0].w);
-                le = __ldg(p.dir + wv[0].w + 1);
-                cand += (unsigned long long)(le - ls) * MV_ITEMS;
-            }
-            const uint32_t n_groups = (le - ls) / MV_DENSE_ENTRIES;
-            const uint32_t g_max = __reduce_max_sync(0xffffffffu, n_groups);
-            const uint32_t last_e = le > ls ? le - 1 : 0;  // clamp target for masked loads
-            uint2 cur[MV_DENSE_ENTRIES];
 #pragma unroll
-            for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = __ldg(ent + min(ls + j, last_e));
-            for (uint32_t g = 0; g < g_max; g++) {
-                const uint32_t e = ls + g * MV_DENSE_ENTRIES;
-                uint2 nxt[MV_DENSE_ENTRIES];
-#pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                    nxt[j] = __ldg(ent + min(e + MV_DENSE_ENTRIES + j, last_e));
-                int d[MV_ITEMS][MV_DENSE_ENTRIES];
-                int acc = 0;
-#pragma unroll
-                for (int it = 0; it < MV_ITEMS; it++) {
-#pragma unroll
-                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) {
-                        d[it][j] = __popc((wv[it].y ^ cur[j].x) | (wv[it].z ^ cur[j].y)) - k1;
-                        acc |= d[it][j];
+            for (int it = 0; it < MV_ITEMS; it++) {
+                const uint4 w = wv[it];
+                const uint32_t ls = lsv[it], le = lev[it];
+                cand += le - ls;
+                uint32_t e = ls;
+                // branch-free batches of 4: the sign bits of (count - (k+1)) are OR-ed, only a batch
+                // containing a candidate is re-examined
+                for (; e + 4 <= le; e += 4) {
+                    const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
+                                q3 = __ldg(ent + e + 3);
+                    const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
+                    const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
+                    const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
+                    const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
+                    if (((c0 - k1) | (c1 - k1) | (c2 - k1) | (c3 - k1)) < 0) {
+                        if (c0 <= k) MV_CANDIDATE(e, q0);
+                        if (c1 <= k) MV_CANDIDATE(e + 1, q1);
+                        if (c2 <= k) MV_CANDIDATE(e + 2, q2);
+                        if (c3 <= k) MV_CANDIDATE(e + 3, q3);
                     }
                 }
-                if (acc < 0 && g < n_groups) {
-#pragma unroll
-                    for (int it = 0; it < MV_ITEMS; it++) {
-                        const uint4 w = wv[it];
-#pragma unroll
-                        for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                            if (d[it][j] < 0) MV_CANDIDATE(e + j, cur[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = nxt[j];
-                if ((g & 7u) == 7u) mv_drain(p, q, qn, lane);  // warp-uniform
-            }
-            // bucket tails (< MV_DENSE_ENTRIES entries) of the uniform lanes
-            for (uint32_t e = ls + n_groups * MV_DENSE_ENTRIES; e < le; e++) {
-                const uint2 qq = __ldg(ent + e);
-#pragma unroll
-                for (int it = 0; it < MV_ITEMS; it++) {
-                    const uint4 w = wv[it];
+                for (; e < le; e++) {
+                    const uint2 qq = __ldg(ent + e);
                     if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
                 }
+                mv_drain(p, q, qn, lane);
             }
-            // lanes whose records straddle a slot boundary (or the end of the array): one walk per record
-            if (!lane_uniform) {
-#pragma unroll
-                for (int it = 0; it < MV_ITEMS; it++) {
-                    if (!((act >> it) & 1u)) continue;
-                    const uint4 w = wv[it];
-                    const uint32_t bs = __ldg(p.dir + w.w), be = __ldg(p.dir + w.w + 1);
-                    cand += be - bs;
-                    for (uint32_t e = bs; e < be; e++) {
-                        const uint2 qq = __ldg(ent + e);
-                        if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
-                    }
-                }
-            }
-            mv_drain(p, q, qn, lane);
         }
     }
     __syncwarp();
