@@ -26,12 +26,18 @@ struct bc_ctx {
     std::vector<uint64_t> coff;
     uint32_t *d_H = nullptr, *d_L = nullptr, *d_B = nullptr, *d_start_dev = nullptr;
     bool have_genome = false;
+    uint64_t plane_cap = 0, start_cap = 0;       // allocated plane words / contig slots (grow-only)
+    uint8_t* d_stage = nullptr;                  // grow-only staging buffer for host ASCII inputs
+    uint64_t stage_cap = 0;
+    uint64_t* d_coff = nullptr;
+    uint64_t coff_cap = 0;
 
     // library
     uint32_t n = 0, L = 0;
     uint32_t *d_qh = nullptr, *d_ql = nullptr, *d_sn = nullptr, *d_any_n = nullptr;
     uint32_t lib_has_n = 0;
     bool have_library = false;
+    uint64_t lib_cap = 0;                        // allocated spacers (grow-only)
 
     // PAM
     uint32_t P = 0, pam_dir = 0, pam_flags = 0, pam_sets[8] = {0};
@@ -129,7 +135,7 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B); dfree(ctx->d_start_dev);
+    dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B); dfree(ctx->d_start_dev); dfree(ctx->d_stage); dfree(ctx->d_coff);
     dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn); dfree(ctx->d_any_n);
     dfree(ctx->d_dir); dfree(ctx->d_cursor); dfree(ctx->d_scan_tmp); dfree(ctx->d_ent_id); dfree(ctx->d_ent_hl);
     dfree(ctx->d_ent_tmp); dfree(ctx->d_coarse_cursor);
@@ -162,15 +168,25 @@ static int set_genome_common(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t
     // whole probe tiles (2048 positions = 64 words) plus one halo tile: every kernel may read a
     // full tile and the word after it; the tail words are all-ambiguous padding
     ctx->n_words = ((ctx->n_pos + 2047) / 2048) * 64 + 64 + 4;
-    dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B); dfree(ctx->d_start_dev);
-    CK(cudaMalloc(&ctx->d_H, (size_t)ctx->n_words * 4));
-    CK(cudaMalloc(&ctx->d_L, (size_t)ctx->n_words * 4));
-    CK(cudaMalloc(&ctx->d_B, (size_t)ctx->n_words * 4));
-    CK(cudaMalloc(&ctx->d_start_dev, (size_t)(n_contigs + 1) * 4));
+    // device buffers are grow-only: repeated bc_set_genome calls (the e2e loop) pay no cudaMalloc/cudaFree
+    if (ctx->n_words > ctx->plane_cap) {
+        dfree(ctx->d_H); dfree(ctx->d_L); dfree(ctx->d_B);
+        ctx->plane_cap = 0;
+        CK(cudaMalloc(&ctx->d_H, (size_t)ctx->n_words * 4));
+        CK(cudaMalloc(&ctx->d_L, (size_t)ctx->n_words * 4));
+        CK(cudaMalloc(&ctx->d_B, (size_t)ctx->n_words * 4));
+        ctx->plane_cap = ctx->n_words;
+    }
+    if ((uint64_t)n_contigs + 1 > ctx->start_cap) {
+        dfree(ctx->d_start_dev); dfree(ctx->d_coff);
+        ctx->start_cap = 0;
+        CK(cudaMalloc(&ctx->d_start_dev, (size_t)(n_contigs + 1) * 4));
+        CK(cudaMalloc(&ctx->d_coff, (size_t)(n_contigs + 1) * 8));
+        ctx->start_cap = (uint64_t)n_contigs + 1;
+    }
     std::vector<uint32_t> start_dev(n_contigs + 1);
     for (uint32_t c = 0; c <= n_contigs; c++) start_dev[c] = (uint32_t)(contig_offsets[c] + c);
-    uint64_t* d_coff = nullptr;
-    CK(cudaMalloc(&d_coff, (size_t)(n_contigs + 1) * 8));
+    uint64_t* d_coff = ctx->d_coff;
     CK(cudaMemcpyAsync(d_coff, contig_offsets, (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_start_dev, start_dev.data(), (size_t)(n_contigs + 1) * 4, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev0, st));
@@ -179,7 +195,6 @@ static int set_genome_common(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaStreamSynchronize(st));  // start_dev / d_coff staging must outlive the kernel
     CK(cudaEventElapsedTime(&ctx->stats.ms_pack_genome, ctx->ev0, ctx->ev1));
-    cudaFree(d_coff);
     ctx->have_genome = true;
     ctx->stats.genome_bases = G;
     return BC_OK;
@@ -200,12 +215,14 @@ extern "C" int bc_set_genome(bc_ctx* ctx, const uint8_t* ascii, const uint64_t* 
     uint64_t G = contig_offsets[n_contigs];
     if (!ascii && G > 0) return fail(ctx, BC_EINVAL, "null genome pointer");
     CK(cudaSetDevice(ctx->device));
-    uint8_t* d_ascii = nullptr;
-    CK(cudaMalloc(&d_ascii, G ? G : 1));
-    if (G) CK(cudaMemcpyAsync(d_ascii, ascii, G, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = set_genome_common(ctx, d_ascii, contig_offsets, n_contigs, ctx->stream);
-    cudaFree(d_ascii);
-    return rc;
+    if (G + 1 > ctx->stage_cap) {
+        dfree(ctx->d_stage);
+        ctx->stage_cap = 0;
+        CK(cudaMalloc(&ctx->d_stage, G + 1));
+        ctx->stage_cap = G + 1;
+    }
+    if (G) CK(cudaMemcpyAsync(ctx->d_stage, ascii, G, cudaMemcpyHostToDevice, ctx->stream));
+    return set_genome_common(ctx, ctx->d_stage, contig_offsets, n_contigs, ctx->stream);
 }
 
 // --------------------------------------------------------------------------------------- library
@@ -216,11 +233,15 @@ static int set_library_common(bc_ctx* ctx, const uint8_t* d_ascii, uint32_t n, u
     ctx->have_index = false;
     ctx->n = n;
     ctx->L = L;
-    dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn);
-    size_t ne = (size_t)2 * n + 1;
-    CK(cudaMalloc(&ctx->d_qh, ne * 4));
-    CK(cudaMalloc(&ctx->d_ql, ne * 4));
-    CK(cudaMalloc(&ctx->d_sn, ((size_t)n + 1) * 4));
+    if ((uint64_t)n + 1 > ctx->lib_cap) {
+        dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn);
+        ctx->lib_cap = 0;
+        size_t ne = (size_t)2 * n + 2;
+        CK(cudaMalloc(&ctx->d_qh, ne * 4));
+        CK(cudaMalloc(&ctx->d_ql, ne * 4));
+        CK(cudaMalloc(&ctx->d_sn, ((size_t)n + 1) * 4));
+        ctx->lib_cap = (uint64_t)n + 1;
+    }
     CK(cudaMemsetAsync(ctx->d_any_n, 0, 4, st));
     CK(cudaEventRecord(ctx->ev0, st));
     CK(bc_launch_pack_library(d_ascii, n, L, ctx->d_qh, ctx->d_ql, ctx->d_sn, ctx->d_any_n, st));
@@ -246,13 +267,15 @@ extern "C" int bc_set_library(bc_ctx* ctx, const uint8_t* ascii, uint32_t n, uin
     if (!ascii && n > 0) return fail(ctx, BC_EINVAL, "null library pointer");
     if (L < 1 || L > 32) return fail(ctx, BC_ELIMIT, "spacer length must be 1..32");
     CK(cudaSetDevice(ctx->device));
-    uint8_t* d_ascii = nullptr;
     size_t bytes = (size_t)n * L;
-    CK(cudaMalloc(&d_ascii, bytes ? bytes : 1));
-    if (bytes) CK(cudaMemcpyAsync(d_ascii, ascii, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = set_library_common(ctx, d_ascii, n, L, ctx->stream);
-    cudaFree(d_ascii);
-    return rc;
+    if (bytes + 1 > ctx->stage_cap) {
+        dfree(ctx->d_stage);
+        ctx->stage_cap = 0;
+        CK(cudaMalloc(&ctx->d_stage, bytes + 1));
+        ctx->stage_cap = bytes + 1;
+    }
+    if (bytes) CK(cudaMemcpyAsync(ctx->d_stage, ascii, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return set_library_common(ctx, ctx->d_stage, n, L, ctx->stream);
 }
 
 // ------------------------------------------------------------------------------------------- PAM

@@ -281,14 +281,25 @@ def main():
 
     h_hits = {"buf": None}
 
+    e2e_phase = {"set_genome": 0.0, "set_library": 0.0, "build_index": 0.0, "search": 0.0, "copy_hits": 0.0}
+
     def step_e2e():
+        t0 = time.time()
         s.set_genome_array(h_genome.numpy(), off)            # H2D + pack
+        t1 = time.time()
         s.set_library(h_lib.numpy().reshape(n, L))           # H2D + pack
+        t2 = time.time()
         s.build_index(k)
+        t3 = time.time()
         nh = s.search(k)
+        t4 = time.time()
         if h_hits["buf"] is None or h_hits["buf"].shape[0] < nh:   # pinned result buffer, reused
             h_hits["buf"] = torch.empty((int(nh * 1.05) + 1024, 4), dtype=torch.int32).pin_memory()
+            t4 = time.time()
         s.hits_into(h_hits["buf"].data_ptr(), h_hits["buf"].shape[0])   # D2H of the records
+        t5 = time.time()
+        for key, dt in zip(e2e_phase, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            e2e_phase[key] += dt * 1e3
         return nh, h_hits["buf"]
 
     for _ in range(args.warmup):
@@ -338,6 +349,7 @@ def main():
         nh_e2e, out = step_e2e()
     ev1.record()
     barrier()
+    e2e_phase_ms = {key: round(v / (e2e_steps + 1), 2) for key, v in e2e_phase.items()} if e2e_steps else {}
     e2e_steps = max(e2e_steps, 1)
     ms_e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
     if world > 1:
@@ -434,7 +446,7 @@ def main():
                    "l2": "working set (window records + index) is far larger than the 126 MB L2; no flush needed",
                    "hits_per_step": int(total_hits)},
         "e2e": {"value": e2e_value, "unit": "guides*Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e.item() / e2e_steps},
+                "ms_per_step": ms_e.item() / e2e_steps, "host_phase_ms": e2e_phase_ms},
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
         "stage_ms": {k2: round(v, 4) for k2, v in acc.items()}, "step_wall_ms": step_wall,
