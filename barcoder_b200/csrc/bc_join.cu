@@ -325,15 +325,20 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     if (!ws.ev_b) JCK(cudaEventCreate(&ws.ev_b));
     if (!ws.ev_c) JCK(cudaEventCreate(&ws.ev_c));
 
-    // chunk the genome so the window records stay within the workspace budget
-    size_t free_b = 0, total_b = 0;
-    JCK(cudaMemGetInfo(&free_b, &total_b));
+    // chunk the genome so the window records stay within the workspace budget; the (slow)
+    // free-memory query only runs when the cached workspace cannot hold the whole range
     const uint32_t n_arrays = BC_WINDOWS_TWO_LEVEL ? 2 : 1;  // record arrays (coarse + final)
-    uint64_t budget = ((uint64_t)free_b + n_arrays * ws.gwin_cap * sizeof(uint4)) / 2;
-    if (budget > (96ull << 30)) budget = 96ull << 30;
-    uint64_t chunk = budget / (n_arrays * sizeof(uint4)) / p.n_combos;
-    if (chunk > p.n_pos) chunk = p.n_pos;
-    if (chunk < 1) chunk = 1;
+    const uint64_t span = (uint64_t)p.pos_end - p.pos_begin;
+    uint64_t chunk = span ? span : 1;
+    if (chunk * p.n_combos > ws.gwin_cap) {
+        size_t free_b = 0, total_b = 0;
+        JCK(cudaMemGetInfo(&free_b, &total_b));
+        uint64_t budget = ((uint64_t)free_b + n_arrays * ws.gwin_cap * sizeof(uint4)) / 2;
+        if (budget > (96ull << 30)) budget = 96ull << 30;
+        const uint64_t fit = budget / (n_arrays * sizeof(uint4)) / p.n_combos;
+        if (chunk > fit) chunk = fit;
+        if (chunk < 1) chunk = 1;
+    }
     if (chunk * p.n_combos >= (1ull << 32)) chunk = ((1ull << 32) - 1) / p.n_combos;  // 32-bit record indices
     const uint64_t rec_needed = chunk * p.n_combos;
     if (rec_needed > ws.gwin_cap) {
