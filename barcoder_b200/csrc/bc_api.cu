@@ -525,7 +525,6 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->ent_hl = ctx->d_ent_hl;
     p->ent_id = ctx->d_ent_id;
     p->dir_entries = 2ull * ctx->n * ctx->n_combos;
-    p->dir_slots = ctx->dir_slots;
     p->P = ctx->P;
     p->pam_dir = ctx->pam_dir;
     p->pam_flags = ctx->pam_flags;

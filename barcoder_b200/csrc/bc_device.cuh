@@ -52,7 +52,6 @@ struct SearchParams {
     const uint2* ent_hl;
     const uint32_t* ent_id;
     unsigned long long dir_entries;  // index entries over all combinations
-    unsigned long long dir_slots;    // directory slots over all combinations
     // PAM
     uint32_t P, pam_dir, pam_flags;
     uint32_t pam_sets[8];       // per PAM position: allowed set over {A=1,C=2,G=4,T=8}

@@ -311,12 +311,8 @@ cudaError_t bc_exclusive_scan(uint32_t* d_data, uint64_t n, uint32_t* d_tmp, cud
 //   B  one survivor per lane: seed keys, directory probes (loads batched), non-empty buckets are
 //      pushed to a per-warp list {window, combination, begin, end};
 //   C  one bucket per lane: XOR/LOP3 + POPC over its entries, hits staged per CTA.
-//
-// Combinations are visited in groups of `combos_per_pass`, group-major over the whole genome, so
-// that the directory + entries touched at any one time stay L2-resident (ncu on cfg 5 with all
-// three 11-nt combinations interleaved: 175 GB of DRAM reads for a 1.1 GB genome, 63 % L2 hits).
 __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_constant__ SearchParams p,
-                                                              uint32_t n_tiles, uint32_t combos_per_pass) {
+                                                              uint32_t n_tiles) {
     // plane words [w0 - 1, w0 + 66): the tile, the word before it (PAM left of the first window)
     // and two after it (window + PAM right of the last window)
     __shared__ uint32_t sH[PROBE_SMEM_WORDS], sL[PROBE_SMEM_WORDS], sB[PROBE_SMEM_WORDS];
@@ -336,8 +332,6 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
     uint32_t* n2p = &s_n2[warp];
     unsigned long long cand = 0, probes = 0;
 
-    for (uint32_t cb = 0; cb < p.n_combos; cb += combos_per_pass) {
-    const uint32_t ce = min(cb + combos_per_pass, p.n_combos);
     for (uint32_t tile = p.pos_begin / PROBE_TILE_POS + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t w0 = tile * PROBE_TILE_WORDS;
         const uint32_t tile_pos = tile * PROBE_TILE_POS;
@@ -373,19 +367,19 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
                 const uint32_t ts = t + 32;
                 const uint32_t wh = bc_window(sH, ts) & lm, wl = bc_window(sL, ts) & lm;
 #pragma unroll 1
-                for (uint32_t c0 = cb; c0 < ce; c0 += PROBE_BATCH) {
+                for (uint32_t c0 = 0; c0 < p.n_combos; c0 += PROBE_BATCH) {
                     // all directory reads of the batch are issued before the first one is consumed
                     uint32_t eb[PROBE_BATCH], ee[PROBE_BATCH];
 #pragma unroll
                     for (int j = 0; j < PROBE_BATCH; j++) {
                         eb[j] = ee[j] = 0;
-                        if (have && c0 + j < ce) {
+                        if (have && c0 + j < p.n_combos) {
                             const uint32_t slot = p.combo[c0 + j].dir_off + bc_combo_key(p.combo[c0 + j], wh, wl);
                             eb[j] = __ldg(p.dir + slot);
                             ee[j] = __ldg(p.dir + slot + 1);
                         }
                     }
-                    if (have) probes += min((uint32_t)PROBE_BATCH, ce - c0);
+                    if (have) probes += min((uint32_t)PROBE_BATCH, p.n_combos - c0);
 #pragma unroll
                     for (int j = 0; j < PROBE_BATCH; j++) {
                         if (eb[j] < ee[j]) {
@@ -394,7 +388,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
                         }
                     }
                     __syncwarp();
-                    if (*n2p + 32 * PROBE_BATCH <= PROBE_L2_CAP && (c0 + PROBE_BATCH < ce || r + 32 < n1))
+                    if (*n2p + 32 * PROBE_BATCH <= PROBE_L2_CAP && (c0 + PROBE_BATCH < p.n_combos || r + 32 < n1))
                         continue;  // room for another batch: keep collecting
                     // ---- phase C: one bucket per lane
                     const uint32_t n2 = *n2p;
@@ -428,7 +422,6 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
         }
         bc_flush_hits(p, &stage);
     }
-    }
     if (p.count_candidates) {
         atomicAdd(p.count + 1, cand);
         atomicAdd(p.count + 2, probes);
@@ -441,15 +434,7 @@ cudaError_t bc_launch_scan_probe(const SearchParams& p, int sm_count, cudaStream
     uint32_t my_tiles = n_tiles - p.pos_begin / PROBE_TILE_POS;
     uint32_t grid = (uint32_t)sm_count * 8u;
     if (grid > my_tiles) grid = my_tiles;
-    // group size: as many combinations as keep directory + entries of one pass under ~40 MB
-    uint32_t cpp = p.n_combos;
-    if (p.n_combos > 1) {
-        const double dir_bytes = 4.0 * (double)p.dir_slots / p.n_combos;
-        const double ent_bytes = 12.0 * (double)p.dir_entries / p.n_combos;
-        double fit = 40e6 / (dir_bytes + ent_bytes);
-        cpp = fit < 1.0 ? 1u : (fit >= (double)p.n_combos ? p.n_combos : (uint32_t)fit);
-    }
-    k_scan_probe<<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles, cpp);
+    k_scan_probe<<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
     bc_launch_counter += 1;
     return cudaGetLastError();
 }
