@@ -449,7 +449,10 @@ def main():
                 "ms_per_step": ms_e.item() / e2e_steps, "host_phase_ms": e2e_phase_ms},
         "gpu_launches": int(launches),
         "clocks": clocks, "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu,
-        "stage_ms": {k2: round(v, 4) for k2, v in acc.items()}, "step_wall_ms": step_wall,
+        "stage_ms": dict({k2: round(v, 4) for k2, v in acc.items()},
+                         ms_pack_genome=round(s.stats()["ms_pack_genome"], 4),
+                         ms_pack_library=round(s.stats()["ms_pack_library"], 4)),
+        "step_wall_ms": step_wall,
     }
     if verified is not None:
         line["verified_vs_oracle"] = verified
