@@ -77,10 +77,13 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 #endif
 #define MV_WQ 128     // per-warp candidate queue (entries)
 #ifndef MV_DENSE_ENTRIES
-#define MV_DENSE_ENTRIES 4    // index entries per group in the dense kernel
+#define MV_DENSE_ENTRIES 2    // index entries per group in the dense kernel
+#endif
+#ifndef MV_RECOMPUTE
+#define MV_RECOMPUTE 1      // dense kernel: re-evaluate a group on the rare path instead of keeping 16 counts live
 #endif
 #ifndef MV_DENSE_MINBLOCKS
-#define MV_DENSE_MINBLOCKS 2  // occupancy target of the dense kernel (CTAs per SM)
+#define MV_DENSE_MINBLOCKS 3  // occupancy target of the dense kernel (CTAs per SM): 24 warps beat 16
 #endif
 
 __device__ __forceinline__ uint32_t mv_combo_of_slot(const SearchParams& p, uint32_t slot) {
@@ -192,55 +195,56 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
         if (DENSE) {
             const uint32_t ls = __ldg(p.dir + wv[0].w), le = __ldg(p.dir + wv[0].w + 1);
             cand += (unsigned long long)(le - ls) * MV_ITEMS;
-            // Software-pipelined walk over the bucket in groups of MV_DENSE_ENTRIES entries: the
-            // entries of group g+1 are loaded while group g is evaluated (ncu: 27 % of the stall
-            // samples sat on the first use of the loaded words before this).
+            // Software-pipelined walk over the bucket in groups of MV_DENSE_ENTRIES entries, two
+            // groups per iteration with ping-pong register buffers: the entries of the next group
+            // are loaded while the current one is evaluated (ncu: 27 % of the stall samples sat on
+            // the first use of the loaded words before this) and no register moves are needed.
+            // One group = MV_DENSE_ENTRIES x MV_ITEMS independent LOP3/LOP3/POPC chains folded
+            // with 3-input integer min; about one group in five contains a candidate in SOME lane
+            // at cfg-4 density, so the follow-up stays short and inline: one compare+branch per
+            // count, a queue push where it fires.
+#define MV_GROUP(BUF, EBASE)                                                                   \
+    do {                                                                                       \
+        int c_[MV_ITEMS][MV_DENSE_ENTRIES];                                                    \
+        int best_ = 33;                                                                        \
+        _Pragma("unroll") for (int it = 0; it < MV_ITEMS; it++) {                              \
+            _Pragma("unroll") for (int j = 0; j < MV_DENSE_ENTRIES; j++) {                     \
+                c_[it][j] = __popc((wv[it].y ^ BUF[j].x) | (wv[it].z ^ BUF[j].y));             \
+                best_ = min(best_, c_[it][j]);                                                 \
+            }                                                                                  \
+        }                                                                                      \
+        if (best_ <= k) {                                                                      \
+            _Pragma("unroll") for (int it = 0; it < MV_ITEMS; it++) {                          \
+                uint4 w = wv[it];                                                              \
+                if (MV_RECOMPUTE) asm volatile("" : "+r"(w.y), "+r"(w.z)); /* no CSE: keeps c_ dead */ \
+                _Pragma("unroll") for (int j = 0; j < MV_DENSE_ENTRIES; j++) {                 \
+                    const int cc_ = MV_RECOMPUTE ? __popc((w.y ^ BUF[j].x) | (w.z ^ BUF[j].y)) : c_[it][j]; \
+                    if (cc_ <= k) MV_CANDIDATE((EBASE) + j, BUF[j]);                           \
+                }                                                                              \
+            }                                                                                  \
+        }                                                                                      \
+    } while (0)
             const uint32_t n_groups = (le - ls) / MV_DENSE_ENTRIES;
             const uint2* gp = ent + ls;
-            uint2 cur[MV_DENSE_ENTRIES];
+            uint2 bufA[MV_DENSE_ENTRIES], bufB[MV_DENSE_ENTRIES];
             if (n_groups) {
 #pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = __ldg(gp + j);
+                for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + j);
             }
-            uint32_t since_drain = 0;
-            for (uint32_t g = 0; g < n_groups; g++, gp += MV_DENSE_ENTRIES) {
-                uint2 nxt[MV_DENSE_ENTRIES];
-                if (g + 1 < n_groups) {  // warp-uniform
+            uint32_t g = 0;
+            for (; g + 2 <= n_groups; g += 2, gp += 2 * MV_DENSE_ENTRIES) {
 #pragma unroll
-                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) nxt[j] = __ldg(gp + MV_DENSE_ENTRIES + j);
+                for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufB[j] = __ldg(gp + MV_DENSE_ENTRIES + j);
+                MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);
+                if (g + 2 < n_groups) {  // warp-uniform
+#pragma unroll
+                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + 2 * MV_DENSE_ENTRIES + j);
                 }
-                // (count - (k+1)) is negative iff count <= k: OR-ing the differences keeps the sign
-                // bit of any candidate with plain IADD/LOP3.  About one group in five contains a
-                // candidate in SOME lane at cfg-4 density, so the follow-up stays short and
-                // inline: one compare+branch per count, a queue push where it fires.
-                int d[MV_ITEMS][MV_DENSE_ENTRIES];
-                int acc = 0;
-#pragma unroll
-                for (int it = 0; it < MV_ITEMS; it++) {
-#pragma unroll
-                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) {
-                        d[it][j] = __popc((wv[it].y ^ cur[j].x) | (wv[it].z ^ cur[j].y)) - k1;
-                        acc |= d[it][j];
-                    }
-                }
-                if (acc < 0) {
-                    const uint32_t e = ls + g * MV_DENSE_ENTRIES;
-#pragma unroll
-                    for (int it = 0; it < MV_ITEMS; it++) {
-                        const uint4 w = wv[it];
-#pragma unroll
-                        for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                            if (d[it][j] < 0) MV_CANDIDATE(e + j, cur[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++) cur[j] = nxt[j];
-                since_drain += MV_DENSE_ENTRIES;
-                if (since_drain >= 32) {  // warp-uniform
-                    since_drain = 0;
-                    mv_drain(p, q, qn, lane);
-                }
+                MV_GROUP(bufB, ls + (g + 1) * MV_DENSE_ENTRIES);
+                if ((g & 6u) == 6u) mv_drain(p, q, qn, lane);  // every 8 groups = 32 entries; warp-uniform
             }
+            if (g < n_groups) MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);  // odd group count
+#undef MV_GROUP
             for (uint32_t e = ls + n_groups * MV_DENSE_ENTRIES; e < le; e++) {  // < MV_DENSE_ENTRIES entries
                 const uint2 qq = __ldg(ent + e);
 #pragma unroll
