@@ -76,11 +76,13 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 #define MV_ITEMS 4    // records per lane per warp-tile
 #endif
 #define MV_WQ 128     // per-warp candidate queue (entries)
+#define MV_GQ 96      // per-warp queue of dense groups awaiting re-examination (31 + 2 * 32)
+#ifndef MV_DENSE_MIN
+#define MV_DENSE_MIN 48     // window records a slot needs to be walked by the dense kernel
+#endif
+#define MV_CHUNK_TILES 16   // warp-tiles per work chunk of the dense kernel
 #ifndef MV_DENSE_ENTRIES
 #define MV_DENSE_ENTRIES 2    // index entries per group in the dense kernel
-#endif
-#ifndef MV_RECOMPUTE
-#define MV_RECOMPUTE 1      // dense kernel: re-evaluate a group on the rare path instead of keeping 16 counts live
 #endif
 #ifndef MV_DENSE_MINBLOCKS
 #define MV_DENSE_MINBLOCKS 3  // occupancy target of the dense kernel (CTAs per SM): 24 warps beat 16
@@ -144,13 +146,6 @@ static __device__ __noinline__ void mv_overflow(const SearchParams& p, uint32_t 
         else mv_overflow(p, w.x, m_, (E), w.w);                                                 \
     } while (0)
 
-// rare path of the dense kernel: re-test one window against the two entries of a group
-static __device__ __noinline__ void mv_dense_candidates(const SearchParams& p, uint4* q, uint32_t* qn, const uint4 w,
-                                                        const uint2 qa, const uint2 qb, uint32_t e, int k) {
-    if (__popc((w.y ^ qa.x) | (w.z ^ qa.y)) <= k) MV_CANDIDATE(e, qa);
-    if (__popc((w.y ^ qb.x) | (w.z ^ qb.y)) <= k) MV_CANDIDATE(e + 1, qb);
-}
-
 // resolve full batches of 32 queued candidates; warp-uniform, called at warp-converged points
 __device__ __forceinline__ void mv_drain(const SearchParams& p, uint4* q, uint32_t* qn, uint32_t lane) {
     __syncwarp();
@@ -166,10 +161,185 @@ __device__ __forceinline__ void mv_drain(const SearchParams& p, uint4* q, uint32
     __syncwarp();
 }
 
-template <bool DENSE>
-__global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_merge_verify(const __grid_constant__ SearchParams p,
-                                                                const uint4* __restrict__ gwin,
-                                                                const uint32_t* __restrict__ n_rec_ptr) {
+// Dense kernel, second level: a queued GROUP = {first record of the lane that saw it, first entry
+// of the group} stands for MV_ITEMS x MV_DENSE_ENTRIES pairs of which at least one passed the
+// filter.  32 groups are re-examined at once, one per lane, so the per-pair compare+branch
+// sequence runs with full lanes instead of the 1-2 lanes that found something (that sequence was
+// ~35 % of the dense kernel's issued instructions when it ran where the group was found).
+// Records past the end of the lane's slot (ragged last tile of a slot) are skipped here.
+static __device__ __noinline__ void mv_resolve_groups(const SearchParams& p, const uint4* __restrict__ gwin,
+                                                      const uint32_t* __restrict__ gdir, const uint2* gq, uint32_t n,
+                                                      uint4* q, uint32_t* qn) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const int k = (int)p.k;
+    __syncwarp();
+    if (lane < n) {
+        const uint2 item = gq[lane];
+        uint2 qe[MV_DENSE_ENTRIES];
+#pragma unroll
+        for (int j = 0; j < MV_DENSE_ENTRIES; j++) qe[j] = __ldg(p.ent_hl + item.y + j);
+        const uint32_t slot_end = __ldg(gdir + __ldg(&gwin[item.x].w) + 1);
+#pragma unroll
+        for (int it = 0; it < MV_ITEMS; it++) {
+            const uint32_t idx = item.x + it * 32;
+            if (idx < slot_end) {
+                const uint4 w = __ldg(gwin + idx);
+#pragma unroll
+                for (int j = 0; j < MV_DENSE_ENTRIES; j++)
+                    if (__popc((w.y ^ qe[j].x) | (w.z ^ qe[j].y)) <= k) MV_CANDIDATE(item.y + j, qe[j]);
+            }
+        }
+    }
+    mv_drain(p, q, qn, lane);
+}
+
+// Dense verify: every slot with at least MV_DENSE_MIN window records is cut into warp-tiles of
+// 32*MV_ITEMS records ALIGNED TO THE SLOT START, so all windows of a tile share one library bucket
+// and the bucket is streamed once per tile as warp-uniform (broadcast) loads against MV_ITEMS
+// resident windows per lane.  Only the last tile of a slot is ragged (its missing windows are
+// copies that the second level skips); with fixed tiles over the record array every tile that
+// crossed a slot boundary (8 % of cfg 4's) had to take the lane-per-record kernel, which is ~3x
+// slower per pair.  Work distribution: the record array is cut into chunks of MV_CHUNK_TILES
+// tiles dealt round-robin to the warps; a warp owns the slot-aligned tiles that START in its
+// chunk and finds them from the first record of the chunk (its slot is in the record) and the
+// record directory gdir, so no tile list has to be built.
+__global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense(const __grid_constant__ SearchParams p,
+                                                                                 const uint4* __restrict__ gwin,
+                                                                                 const uint32_t* __restrict__ gdir,
+                                                                                 const uint32_t* __restrict__ n_rec_ptr) {
+    __shared__ uint4 s_q[MV_WARPS][MV_WQ];
+    __shared__ uint2 s_gq[MV_WARPS][MV_GQ];
+    __shared__ uint32_t s_qn[MV_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint2* gq = s_gq[warp];
+    uint32_t gn = 0;  // queued groups of this warp (warp-uniform; survives across tiles)
+    uint4* q = s_q[warp];
+    uint32_t* qn = &s_qn[warp];
+    if (lane == 0) *qn = 0;
+    __syncwarp();
+    const uint32_t n_rec = *n_rec_ptr;
+    const uint32_t wtile = 32 * MV_ITEMS, chunk = wtile * MV_CHUNK_TILES;
+    const uint32_t n_chunks = (n_rec + chunk - 1) / chunk;
+    const uint32_t n_warps = gridDim.x * MV_WARPS;
+    const int k = (int)p.k;
+    const uint2* __restrict__ ent = p.ent_hl;
+    unsigned long long cand = 0;
+    for (uint32_t ch = blockIdx.x * MV_WARPS + warp; ch < n_chunks; ch += n_warps) {
+        const uint32_t r0 = ch * chunk, r1 = r0 + min(chunk, n_rec - r0);
+        // all of these are warp-uniform (every lane loads the same words)
+        uint32_t slot = __ldg(&gwin[r0].w);
+        uint32_t a = __ldg(gdir + slot), b = __ldg(gdir + slot + 1);  // records of this slot
+        uint32_t t = a + (r0 - a + wtile - 1) / wtile * wtile;         // first tile start >= r0
+        for (;;) {
+            if (t >= b || b - a < MV_DENSE_MIN) {  // slot finished, or left to the sparse kernel
+                if (b >= r1) break;
+                slot = __ldg(&gwin[b].w);  // next non-empty slot starts where this one ends
+                a = b;
+                b = __ldg(gdir + slot + 1);
+                t = a;
+                continue;
+            }
+            if (t >= r1) break;
+            const uint32_t first = t;
+            t += wtile;
+            const uint32_t ls = __ldg(p.dir + slot), le = __ldg(p.dir + slot + 1);
+            if (ls == le) continue;
+            // lanes without a record of their own are switched off (threshold -1); the missing
+            // higher items of a live lane are copies of its first window
+            const bool live = first + lane < b;
+            const int kl = live ? k : -1;
+            uint4 wv[MV_ITEMS];
+            wv[0] = __ldcs(gwin + (live ? first + lane : b - 1));
+            uint32_t mine = live ? 1u : 0u;
+#pragma unroll
+            for (int it = 1; it < MV_ITEMS; it++) {
+                const bool ok = first + it * 32 + lane < b;
+                wv[it] = wv[0];
+                if (ok) wv[it] = __ldcs(gwin + first + it * 32 + lane);
+                mine += ok ? 1u : 0u;
+            }
+            cand += (unsigned long long)(le - ls) * mine;
+            // Software-pipelined walk over the bucket in groups of MV_DENSE_ENTRIES entries, two
+            // groups per iteration with ping-pong register buffers: the entries of the next group
+            // are loaded while the current one is evaluated (ncu: 27 % of the stall samples sat on
+            // the first use of the loaded words before this) and no register moves are needed.
+            // One group = MV_DENSE_ENTRIES x MV_ITEMS independent LOP3/LOP3/POPC chains folded
+            // with 3-input integer min.  A lane whose minimum passes only QUEUES the group (one
+            // ballot, one shared store); mv_resolve_groups re-examines 32 groups at a time.
+#define MV_GROUP(BUF, EBASE)                                                                   \
+    do {                                                                                       \
+        int best_ = 33;                                                                        \
+        _Pragma("unroll") for (int it = 0; it < MV_ITEMS; it++) {                              \
+            _Pragma("unroll") for (int j = 0; j < MV_DENSE_ENTRIES; j++)                       \
+                best_ = min(best_, __popc((wv[it].y ^ BUF[j].x) | (wv[it].z ^ BUF[j].y)));     \
+        }                                                                                      \
+        const uint32_t hit_ = __ballot_sync(0xffffffffu, best_ <= kl);                         \
+        if (hit_) { /* warp-uniform */                                                         \
+            if (best_ <= kl) gq[gn + __popc(hit_ & lt_mask)] = make_uint2(first + lane, (EBASE)); \
+            gn += __popc(hit_);                                                                \
+        }                                                                                      \
+    } while (0)
+            const uint32_t n_groups = (le - ls) / MV_DENSE_ENTRIES;
+            const uint2* gp = ent + ls;
+            uint2 bufA[MV_DENSE_ENTRIES], bufB[MV_DENSE_ENTRIES];
+            if (n_groups) {
+#pragma unroll
+                for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + j);
+            }
+            // The resolve calls sit OUTSIDE the pipelined loop (a call inside it made ptxas spill
+            // the window registers and reload them every iteration): the loop leaves when a full
+            // batch is queued and is re-entered afterwards.
+            uint32_t g = 0;
+            for (;;) {
+                for (; g + 2 <= n_groups && gn < 32; g += 2, gp += 2 * MV_DENSE_ENTRIES) {
+#pragma unroll
+                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufB[j] = __ldg(gp + MV_DENSE_ENTRIES + j);
+                    MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);
+                    if (g + 2 < n_groups) {  // warp-uniform
+#pragma unroll
+                        for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + 2 * MV_DENSE_ENTRIES + j);
+                    }
+                    MV_GROUP(bufB, ls + (g + 1) * MV_DENSE_ENTRIES);
+                }
+                if (gn < 32) break;
+                do {  // warp-uniform; at most 31 + 2 * 32 groups are queued here
+                    gn -= 32;
+                    mv_resolve_groups(p, gwin, gdir, gq + gn, 32, q, qn);
+                } while (gn >= 32);
+            }
+            if (g < n_groups) MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);  // odd group count (<= 63 queued: fits)
+#undef MV_GROUP
+            for (uint32_t e = ls + n_groups * MV_DENSE_ENTRIES; e < le; e++) {  // < MV_DENSE_ENTRIES entries
+                const uint2 qq = __ldg(ent + e);
+#pragma unroll
+                for (int it = 0; it < MV_ITEMS; it++) {
+                    if (first + it * 32 + lane < b) {
+                        const uint4 w = __ldg(gwin + first + it * 32 + lane);  // reloaded: keeps pos/slot out of the loop's registers
+                        if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+                    }
+                }
+            }
+            mv_drain(p, q, qn, lane);
+        }
+    }
+    while (gn) {  // up to MV_GQ - 1 groups are still queued
+        const uint32_t take = min(gn, 32u);
+        gn -= take;
+        mv_resolve_groups(p, gwin, gdir, gq + gn, take, q, qn);
+    }
+    __syncwarp();
+    const uint32_t nq = min(*qn, (uint32_t)MV_WQ);
+    if (nq) mv_resolve(p, q, nq);
+    if (p.count_candidates) atomicAdd(p.count + 1, cand);
+}
+
+// Sparse verify: the records of slots with fewer than MV_DENSE_MIN windows, one record per lane,
+// every lane walking the library bucket of its own record.
+__global__ void __launch_bounds__(MV_THREADS, 3) k_verify_sparse(const __grid_constant__ SearchParams p,
+                                                                 const uint4* __restrict__ gwin,
+                                                                 const uint32_t* __restrict__ gdir,
+                                                                 const uint32_t* __restrict__ n_rec_ptr) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
     __shared__ uint32_t s_qn[MV_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -185,111 +355,49 @@ __global__ void __launch_bounds__(MV_THREADS, DENSE ? MV_DENSE_MINBLOCKS : 3) k_
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
     for (uint32_t wt = blockIdx.x * MV_WARPS + warp; wt < n_wtiles; wt += n_warps) {
-        // records are sorted by slot: a full tile is uniform iff its first and last slots agree
-        const uint32_t first = wt * wtile, last = min(first + wtile, n_rec) - 1;
-        const bool uniform = (first + wtile <= n_rec) && (__ldg(&gwin[first].w) == __ldg(&gwin[last].w));
-        if (uniform != DENSE) continue;
+        // records are sorted by slot: a full tile whose first and last slots agree lies inside a
+        // slot of >= 32*MV_ITEMS >= MV_DENSE_MIN records, which the dense kernel owns
+        const uint32_t first = wt * wtile, last = first + min(wtile, n_rec - first) - 1;
+        if (last - first + 1 == wtile && __ldg(&gwin[first].w) == __ldg(&gwin[last].w)) continue;
         uint4 wv[MV_ITEMS];
 #pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) wv[it] = __ldcs(gwin + min(first + it * 32 + lane, n_rec - 1));
-        if (DENSE) {
-            const uint32_t ls = __ldg(p.dir + wv[0].w), le = __ldg(p.dir + wv[0].w + 1);
-            cand += (unsigned long long)(le - ls) * MV_ITEMS;
-            // Software-pipelined walk over the bucket in groups of MV_DENSE_ENTRIES entries, two
-            // groups per iteration with ping-pong register buffers: the entries of the next group
-            // are loaded while the current one is evaluated (ncu: 27 % of the stall samples sat on
-            // the first use of the loaded words before this) and no register moves are needed.
-            // One group = MV_DENSE_ENTRIES x MV_ITEMS independent LOP3/LOP3/POPC chains folded
-            // with 3-input integer min; about one group in five contains a candidate in SOME lane
-            // at cfg-4 density, so the follow-up stays short and inline: one compare+branch per
-            // count, a queue push where it fires.
-#define MV_GROUP(BUF, EBASE)                                                                   \
-    do {                                                                                       \
-        int c_[MV_ITEMS][MV_DENSE_ENTRIES];                                                    \
-        int best_ = 33;                                                                        \
-        _Pragma("unroll") for (int it = 0; it < MV_ITEMS; it++) {                              \
-            _Pragma("unroll") for (int j = 0; j < MV_DENSE_ENTRIES; j++) {                     \
-                c_[it][j] = __popc((wv[it].y ^ BUF[j].x) | (wv[it].z ^ BUF[j].y));             \
-                best_ = min(best_, c_[it][j]);                                                 \
-            }                                                                                  \
-        }                                                                                      \
-        if (best_ <= k) {                                                                      \
-            _Pragma("unroll") for (int it = 0; it < MV_ITEMS; it++) {                          \
-                uint4 w = wv[it];                                                              \
-                if (MV_RECOMPUTE) asm volatile("" : "+r"(w.y), "+r"(w.z)); /* no CSE: keeps c_ dead */ \
-                _Pragma("unroll") for (int j = 0; j < MV_DENSE_ENTRIES; j++) {                 \
-                    const int cc_ = MV_RECOMPUTE ? __popc((w.y ^ BUF[j].x) | (w.z ^ BUF[j].y)) : c_[it][j]; \
-                    if (cc_ <= k) MV_CANDIDATE((EBASE) + j, BUF[j]);                           \
-                }                                                                              \
-            }                                                                                  \
-        }                                                                                      \
-    } while (0)
-            const uint32_t n_groups = (le - ls) / MV_DENSE_ENTRIES;
-            const uint2* gp = ent + ls;
-            uint2 bufA[MV_DENSE_ENTRIES], bufB[MV_DENSE_ENTRIES];
-            if (n_groups) {
+        for (int it = 0; it < MV_ITEMS; it++) wv[it] = __ldcs(gwin + min(first + it * 32 + lane, last));
+        // Issue the directory loads of all MV_ITEMS records before any dependent work.
+        uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
 #pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + j);
-            }
-            uint32_t g = 0;
-            for (; g + 2 <= n_groups; g += 2, gp += 2 * MV_DENSE_ENTRIES) {
+        for (int it = 0; it < MV_ITEMS; it++) {
+            const bool mine = first + it * 32 + lane <= last &&
+                              __ldg(gdir + wv[it].w + 1) - __ldg(gdir + wv[it].w) < MV_DENSE_MIN;
+            lsv[it] = __ldg(p.dir + wv[it].w);
+            lev[it] = mine ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
+        }
 #pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufB[j] = __ldg(gp + MV_DENSE_ENTRIES + j);
-                MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);
-                if (g + 2 < n_groups) {  // warp-uniform
-#pragma unroll
-                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + 2 * MV_DENSE_ENTRIES + j);
+        for (int it = 0; it < MV_ITEMS; it++) {
+            const uint4 w = wv[it];
+            const uint32_t ls = lsv[it], le = lev[it];
+            cand += le - ls;
+            uint32_t e = ls;
+            // branch-free batches of 4: the sign bits of (count - (k+1)) are OR-ed, only a batch
+            // containing a candidate is re-examined
+            for (; e + 4 <= le; e += 4) {
+                const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
+                            q3 = __ldg(ent + e + 3);
+                const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
+                const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
+                const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
+                const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
+                if (((c0 - k1) | (c1 - k1) | (c2 - k1) | (c3 - k1)) < 0) {
+                    if (c0 <= k) MV_CANDIDATE(e, q0);
+                    if (c1 <= k) MV_CANDIDATE(e + 1, q1);
+                    if (c2 <= k) MV_CANDIDATE(e + 2, q2);
+                    if (c3 <= k) MV_CANDIDATE(e + 3, q3);
                 }
-                MV_GROUP(bufB, ls + (g + 1) * MV_DENSE_ENTRIES);
-                if ((g & 6u) == 6u) mv_drain(p, q, qn, lane);  // every 8 groups = 32 entries; warp-uniform
             }
-            if (g < n_groups) MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);  // odd group count
-#undef MV_GROUP
-            for (uint32_t e = ls + n_groups * MV_DENSE_ENTRIES; e < le; e++) {  // < MV_DENSE_ENTRIES entries
+            for (; e < le; e++) {
                 const uint2 qq = __ldg(ent + e);
-#pragma unroll
-                for (int it = 0; it < MV_ITEMS; it++) {
-                    const uint4 w = wv[it];
-                    if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
-                }
+                if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
             }
             mv_drain(p, q, qn, lane);
-        } else {
-            // Issue the directory loads of all MV_ITEMS records before any dependent work.
-            uint32_t lsv[MV_ITEMS], lev[MV_ITEMS];
-#pragma unroll
-            for (int it = 0; it < MV_ITEMS; it++) {
-                lsv[it] = __ldg(p.dir + wv[it].w);
-                lev[it] = first + it * 32 + lane < n_rec ? __ldg(p.dir + wv[it].w + 1) : lsv[it];
-            }
-#pragma unroll
-            for (int it = 0; it < MV_ITEMS; it++) {
-                const uint4 w = wv[it];
-                const uint32_t ls = lsv[it], le = lev[it];
-                cand += le - ls;
-                uint32_t e = ls;
-                // branch-free batches of 4: the sign bits of (count - (k+1)) are OR-ed, only a batch
-                // containing a candidate is re-examined
-                for (; e + 4 <= le; e += 4) {
-                    const uint2 q0 = __ldg(ent + e), q1 = __ldg(ent + e + 1), q2 = __ldg(ent + e + 2),
-                                q3 = __ldg(ent + e + 3);
-                    const int c0 = __popc((w.y ^ q0.x) | (w.z ^ q0.y));
-                    const int c1 = __popc((w.y ^ q1.x) | (w.z ^ q1.y));
-                    const int c2 = __popc((w.y ^ q2.x) | (w.z ^ q2.y));
-                    const int c3 = __popc((w.y ^ q3.x) | (w.z ^ q3.y));
-                    if (((c0 - k1) | (c1 - k1) | (c2 - k1) | (c3 - k1)) < 0) {
-                        if (c0 <= k) MV_CANDIDATE(e, q0);
-                        if (c1 <= k) MV_CANDIDATE(e + 1, q1);
-                        if (c2 <= k) MV_CANDIDATE(e + 2, q2);
-                        if (c3 <= k) MV_CANDIDATE(e + 3, q3);
-                    }
-                }
-                for (; e < le; e++) {
-                    const uint2 qq = __ldg(ent + e);
-                    if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
-                }
-                mv_drain(p, q, qn, lane);
-            }
         }
     }
     __syncwarp();
@@ -343,7 +451,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         if (chunk > fit) chunk = fit;
         if (chunk < 1) chunk = 1;
     }
-    if (chunk * p.n_combos >= (1ull << 32)) chunk = ((1ull << 32) - 1) / p.n_combos;  // 32-bit record indices
+    if (chunk * p.n_combos >= (1ull << 32) - 65536) chunk = ((1ull << 32) - 65536) / p.n_combos;  // 32-bit record indices (+ tile slack)
     const uint64_t rec_needed = chunk * p.n_combos;
     if (rec_needed > ws.gwin_cap) {
         if (ws.d_gwin) cudaFree(ws.d_gwin);
@@ -413,9 +521,11 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         }
         JCK(cudaEventRecord(ws.ev_a, st));
         // the last directory slot is the end sentinel: after the scan it holds the record count
-        k_merge_verify<true><<<(uint32_t)sm_count * 8u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
+        k_verify_dense<<<(uint32_t)sm_count * MV_DENSE_MINBLOCKS, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir,
+                                                                                       ws.d_gdir + (dir_slots - 1));
         JCK(cudaGetLastError());
-        k_merge_verify<false><<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir + (dir_slots - 1));
+        k_verify_sparse<<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir,
+                                                                        ws.d_gdir + (dir_slots - 1));
         JCK(cudaGetLastError());
         JCK(cudaEventRecord(ws.ev_b, st));
         bc_launch_counter += 4;
