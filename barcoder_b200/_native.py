@@ -34,7 +34,7 @@ HIT_DTYPE = np.dtype([("spacer_id", "<u4"), ("gpos", "<u4"), ("mm_mask", "<u4"),
 EXPORTS = (
     "bc_abi_version", "bc_create", "bc_destroy", "bc_set_genome", "bc_set_genome_dev", "bc_set_library",
     "bc_set_library_dev", "bc_set_pam", "bc_set_param", "bc_build_index", "bc_search", "bc_copy_hits",
-    "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
+    "bc_set_hit_sink", "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
 )
 
 
@@ -90,6 +90,7 @@ def load():
     L.bc_build_index.argtypes = [vp, i32]
     L.bc_search.argtypes = [vp, i32, ctypes.POINTER(u64)]
     L.bc_copy_hits.argtypes = [vp, vp, u64]
+    L.bc_set_hit_sink.argtypes = [vp, vp, u64]
     L.bc_hits_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.bc_get_stats.argtypes = [vp, ctypes.POINTER(BcStats)]
     L.bc_enumerate_guides.argtypes = [vp, u32, ctypes.c_char_p, i32, u32, ctypes.POINTER(u64)]
@@ -215,6 +216,11 @@ class Searcher:
     def hits_into(self, host_ptr, cap_records):
         """Copy the records into caller-owned host memory (e.g. a pinned buffer)."""
         self._check(self._L.bc_copy_hits(self._ctx, host_ptr, int(cap_records)))
+
+    def set_hit_sink(self, host_ptr, cap_records):
+        """Stream the records of every following search() into caller-owned host memory while the
+        search runs (pinned memory lets the copies overlap it); host_ptr=None removes the sink."""
+        self._check(self._L.bc_set_hit_sink(self._ctx, host_ptr or None, int(cap_records) if host_ptr else 0))
 
     def hits_device(self):
         ptr, n = ctypes.c_void_p(), ctypes.c_uint64()

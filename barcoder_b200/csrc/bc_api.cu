@@ -67,6 +67,7 @@ struct bc_ctx {
     bc_hit* d_hits = nullptr;
     uint64_t hit_cap = 0, n_hits = 0;
     unsigned long long* d_count = nullptr;
+    HitSink sink;                     // optional streamed delivery to host memory (bc_set_hit_sink)
 
     bc_stats stats;
 };
@@ -147,6 +148,10 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->sink.stream) cudaStreamDestroy(ctx->sink.stream);
+    if (ctx->sink.h_counts) cudaFreeHost(ctx->sink.h_counts);
+    for (int i = 0; i < BC_SINK_SLICES; i++)
+        if (ctx->sink.ev[i]) cudaEventDestroy(ctx->sink.ev[i]);
     delete ctx;
 }
 
@@ -570,8 +575,10 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         CK(cudaMemsetAsync(ctx->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream));
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         uint32_t launches = 0;
+        ctx->sink.copied = 0;
         if (ctx->stats.path == 2) {
-            CK(bc_join_search(ctx->join, p, ctx->dir_slots, ctx->sm_count, ctx->stream, &launches));
+            CK(bc_join_search(ctx->join, p, ctx->dir_slots, ctx->sm_count, ctx->stream, &launches,
+                              ctx->sink.host ? &ctx->sink : nullptr));
         } else {
             CK(cudaEventRecord(ctx->ev2, ctx->stream));
             CK(bc_launch_scan_probe(p, ctx->sm_count, ctx->stream));
@@ -608,6 +615,28 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
     ctx->stats.ms_scan_kernel = ms_scan;
     ctx->stats.ms_genome_bucket = ms_bucket;
     if (n_hits_out) *n_hits_out = ctx->n_hits;
+    if (ctx->sink.host) {
+        if (ctx->n_hits > ctx->sink.cap) return fail(ctx, BC_ELIMIT, "bc_search: more hits than the hit sink holds (use bc_copy_hits)");
+        if (ctx->n_hits > ctx->sink.copied)  // whatever the slices did not deliver yet (all of it on the probe path)
+            CK(cudaMemcpyAsync(ctx->sink.host + ctx->sink.copied, ctx->d_hits + ctx->sink.copied,
+                               (ctx->n_hits - ctx->sink.copied) * sizeof(bc_hit), cudaMemcpyDeviceToHost, ctx->sink.stream));
+        CK(cudaStreamSynchronize(ctx->sink.stream));
+    }
+    return BC_OK;
+}
+
+extern "C" int bc_set_hit_sink(bc_ctx* ctx, bc_hit* dst, uint64_t cap) {
+    if (!ctx) return BC_EINVAL;
+    if (dst && cap == 0) return fail(ctx, BC_EINVAL, "bc_set_hit_sink: zero capacity");
+    CK(cudaSetDevice(ctx->device));
+    if (dst && !ctx->sink.stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->sink.stream, cudaStreamNonBlocking));
+        CK(cudaHostAlloc((void**)&ctx->sink.h_counts, BC_SINK_SLICES * sizeof(unsigned long long), cudaHostAllocDefault));
+        for (int i = 0; i < BC_SINK_SLICES; i++) CK(cudaEventCreateWithFlags(&ctx->sink.ev[i], cudaEventDisableTiming));
+    }
+    ctx->sink.host = dst;
+    ctx->sink.cap = dst ? cap : 0;
+    ctx->sink.copied = 0;
     return BC_OK;
 }
 

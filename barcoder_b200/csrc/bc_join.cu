@@ -206,7 +206,8 @@ static __device__ __noinline__ void mv_resolve_groups(const SearchParams& p, con
 __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense(const __grid_constant__ SearchParams p,
                                                                                  const uint4* __restrict__ gwin,
                                                                                  const uint32_t* __restrict__ gdir,
-                                                                                 const uint32_t* __restrict__ n_rec_ptr) {
+                                                                                 const uint32_t* __restrict__ n_rec_ptr,
+                                                                                 uint32_t slice, uint32_t n_slices) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
     __shared__ uint2 s_gq[MV_WARPS][MV_GQ];
     __shared__ uint32_t s_qn[MV_WARPS];
@@ -225,7 +226,10 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
     const int k = (int)p.k;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
-    for (uint32_t ch = blockIdx.x * MV_WARPS + warp; ch < n_chunks; ch += n_warps) {
+    // a launch handles the slice-th of n_slices equal ranges of chunks (streamed result delivery)
+    const uint32_t ch_lo = (uint32_t)((unsigned long long)n_chunks * slice / n_slices);
+    const uint32_t ch_hi = (uint32_t)((unsigned long long)n_chunks * (slice + 1) / n_slices);
+    for (uint32_t ch = ch_lo + blockIdx.x * MV_WARPS + warp; ch < ch_hi; ch += n_warps) {
         const uint32_t r0 = ch * chunk, r1 = r0 + min(chunk, n_rec - r0);
         // all of these are warp-uniform (every lane loads the same words)
         uint32_t slot = __ldg(&gwin[r0].w);
@@ -430,7 +434,7 @@ void bc_join_free(JoinWorkspace& ws) {
     } while (0)
 
 cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, int sm_count,
-                           cudaStream_t st, uint32_t* launches) {
+                           cudaStream_t st, uint32_t* launches, HitSink* sink) {
     const uint32_t launches0 = bc_launch_counter;
     ws.ms_join_kernels = ws.ms_bucket_kernels = 0;
     if (!ws.ev_a) JCK(cudaEventCreate(&ws.ev_a));
@@ -521,13 +525,36 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         }
         JCK(cudaEventRecord(ws.ev_a, st));
         // the last directory slot is the end sentinel: after the scan it holds the record count
-        k_verify_dense<<<(uint32_t)sm_count * MV_DENSE_MINBLOCKS, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir,
-                                                                                       ws.d_gdir + (dir_slots - 1));
+        const uint32_t* n_rec_ptr = ws.d_gdir + (dir_slots - 1);
+        k_verify_sparse<<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir, n_rec_ptr);
         JCK(cudaGetLastError());
-        k_verify_sparse<<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir,
-                                                                        ws.d_gdir + (dir_slots - 1));
-        JCK(cudaGetLastError());
+        const uint32_t n_slices = sink ? BC_SINK_SLICES : 1;
+        for (uint32_t s = 0; s < n_slices; s++) {
+            k_verify_dense<<<(uint32_t)sm_count * MV_DENSE_MINBLOCKS, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir,
+                                                                                           n_rec_ptr, s, n_slices);
+            JCK(cudaGetLastError());
+            if (sink) {
+                JCK(cudaMemcpyAsync(sink->h_counts + s, p.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                JCK(cudaEventRecord(sink->ev[s], st));
+            }
+        }
         JCK(cudaEventRecord(ws.ev_b, st));
+        bc_launch_counter += n_slices - 1;
+        if (sink) {
+            // hits are appended through one atomic cursor, so everything below the counter value
+            // read after slice s is final once that slice has finished
+            for (uint32_t s = 0; s < n_slices; s++) {
+                JCK(cudaEventSynchronize(sink->ev[s]));
+                uint64_t done = sink->h_counts[s];
+                if (done > p.cap) done = p.cap;
+                if (done > sink->cap) done = sink->cap;
+                if (done > sink->copied) {
+                    JCK(cudaMemcpyAsync(sink->host + sink->copied, p.hits + sink->copied,
+                                        (done - sink->copied) * sizeof(bc_hit), cudaMemcpyDeviceToHost, sink->stream));
+                    sink->copied = done;
+                }
+            }
+        }
         bc_launch_counter += 4;
         // events are reused per chunk, so read them before the next record
         JCK(cudaEventSynchronize(ws.ev_b));

@@ -17,7 +17,19 @@ struct JoinWorkspace {
     float ms_bucket_kernels = 0;    // device time of the genome bucketing kernels (count, scan, scatter)
 };
 
+// Streamed result delivery (bc_set_hit_sink): while the verify kernels of later slices run, the
+// hit records of finished slices are copied to the caller's host buffer on a second stream.
+#define BC_SINK_SLICES 8
+struct HitSink {
+    bc_hit* host = nullptr;            // caller's destination (pinned memory makes the copies asynchronous)
+    uint64_t cap = 0;                  // records the destination can hold
+    uint64_t copied = 0;               // records already queued for copy in this search
+    cudaStream_t stream = nullptr;     // copy stream
+    unsigned long long* h_counts = nullptr;  // pinned: hit counter after every slice
+    cudaEvent_t ev[BC_SINK_SLICES] = {nullptr};
+};
+
 bool bc_join_supported(const ComboDesc* combo, uint32_t n_combos, uint64_t entries_per_combo);
 cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, int sm_count,
-                           cudaStream_t st, uint32_t* launches);
+                           cudaStream_t st, uint32_t* launches, HitSink* sink);
 void bc_join_free(JoinWorkspace& ws);

@@ -11,7 +11,8 @@ N x 10^7 library), the genome is replicated, hits are gathered to rank 0 over NC
 
 A step = seed-index build + genome scan (bucketing + verification, PAM fused) + hit gather, with
 the ASCII inputs already resident in HBM (`value`).  `e2e` is the same metric through the host
-C-ABI calls: pinned host ASCII buffers -> H2D -> pack -> index -> scan -> D2H of the hit records.
+C-ABI calls: pinned host ASCII buffers -> H2D -> pack -> index -> scan -> D2H of the hit records
+(streamed into a pinned buffer through bc_set_hit_sink while the scan runs).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -291,12 +292,16 @@ def main():
         t2 = time.time()
         s.build_index(k)
         t3 = time.time()
-        nh = s.search(k)
-        t4 = time.time()
-        if h_hits["buf"] is None or h_hits["buf"].shape[0] < nh:   # pinned result buffer, reused
+        if h_hits["buf"] is None:                              # first (untimed) call: size the pinned result buffer
+            nh = s.search(k)
             h_hits["buf"] = torch.empty((int(nh * 1.05) + 1024, 4), dtype=torch.int32).pin_memory()
             t4 = time.time()
-        s.hits_into(h_hits["buf"].data_ptr(), h_hits["buf"].shape[0])   # D2H of the records
+            s.hits_into(h_hits["buf"].data_ptr(), h_hits["buf"].shape[0])
+            # from now on the records are streamed to the pinned buffer while the search runs
+            s.set_hit_sink(h_hits["buf"].data_ptr(), h_hits["buf"].shape[0])
+        else:
+            nh = s.search(k)                                   # D2H of the records happens inside (hit sink)
+            t4 = time.time()
         t5 = time.time()
         for key, dt in zip(e2e_phase, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
             e2e_phase[key] += dt * 1e3
@@ -352,6 +357,7 @@ def main():
     ev1.record()
     barrier()
     e2e_phase_ms = {key: round(v / e2e_steps, 2) for key, v in e2e_phase.items()} if e2e_steps else {}
+    s.set_hit_sink(None, 0)
     e2e_steps = max(e2e_steps, 1)
     ms_e = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
     if world > 1:

@@ -138,6 +138,15 @@ int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out);
 /* Replaces reading the SAM file (PySamParser.py:16-19).  Order is unspecified. */
 int bc_copy_hits(bc_ctx* ctx, bc_hit* dst, uint64_t cap);
 
+/* Streamed delivery of the same records: with a sink set, bc_search copies the hit records to
+ * `dst` (host memory, `cap` records; page-locked memory lets the copies overlap the search)
+ * WHILE the search runs, so that when bc_search returns dst[0..n_hits) is complete and no
+ * bc_copy_hits is needed - the counterpart of bowtie writing the SAM file while it aligns
+ * (BowtieRunner.py:111-136, `-S ... sam_path`).  dst = NULL removes the sink.  If more than
+ * `cap` hits are found bc_search fails with BC_ELIMIT; the records stay on the device and
+ * bc_copy_hits still works. */
+int bc_set_hit_sink(bc_ctx* ctx, bc_hit* dst, uint64_t cap);
+
 /* Device-side view of the result buffer (valid until the next bc_search/bc_destroy),
  * for callers that gather across GPUs without a host round trip. */
 int bc_hits_device(bc_ctx* ctx, const bc_hit** d_hits, uint64_t* n_hits);

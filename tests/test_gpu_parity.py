@@ -206,3 +206,50 @@ def test_join_medium_both_paths_agree():
     gate_ref = run_oracle(genome, off, lib, 3, pam="NGG", gate=True)
     gpu, _ = run_gpu(genome, off, lib, 3, pam="NGG", gate=True, path=2)
     assert_same(gpu, gate_ref)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_hit_sink_streams_the_same_records(path):
+    """bc_set_hit_sink: records delivered to host memory during the search equal bc_copy_hits'."""
+    genome, off = synth.random_genome(1_500_000, seed=41, n_contigs=5, n_fraction=0.002)
+    lib = synth.random_library(60000, 20, seed=42)
+    synth.plant(lib, genome, 0.3, 2, seed=43)
+    ref = run_oracle(genome, off, lib, 2, pam="NGG")
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        s.set_param(_native.BC_PARAM_PATH, path)
+        sink = np.zeros(len(ref) + 100, dtype=_native.HIT_DTYPE)
+        s.set_hit_sink(sink.ctypes.data, len(sink))
+        for _ in range(2):              # the sink persists across searches
+            sink[:] = 0
+            n = s.search(2)
+            assert n == len(ref)
+            assert_same(_native.canonical_sort(sink[:n].copy()), ref)
+        assert_same(_native.canonical_sort(s.hits()), ref)   # the device copy is still there
+        # a sink that is too small is an error, but the records stay retrievable
+        small = np.zeros(len(ref) - 1, dtype=_native.HIT_DTYPE)
+        s.set_hit_sink(small.ctypes.data, len(small))
+        with pytest.raises(_native.NativeError):
+            s.search(2)
+        assert_same(_native.canonical_sort(s.hits()), ref)
+        s.set_hit_sink(None, 0)
+        assert s.search(2) == len(ref)
+
+
+def test_hit_sink_with_device_buffer_overflow_retry():
+    """The device buffer is grown and the search repeated; the sink must end up with the full set."""
+    genome, off, lib = small_case(20, 2, seed=77, n=2000, G=200000)
+    ref = run_oracle(genome, off, lib, 2, pam="NGG")
+    assert len(ref) > 64
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        s.set_param(_native.BC_PARAM_PATH, 2)
+        s.set_param(_native.BC_PARAM_HIT_CAPACITY, 16)
+        sink = np.zeros(len(ref), dtype=_native.HIT_DTYPE)
+        s.set_hit_sink(sink.ctypes.data, len(sink))
+        assert s.search(2) == len(ref)
+        assert_same(_native.canonical_sort(sink.copy()), ref)
