@@ -80,13 +80,26 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
 #ifndef MV_DENSE_MIN
 #define MV_DENSE_MIN 48     // window records a slot needs to be walked by the dense kernel
 #endif
+#ifndef MV_CHUNK_TILES
 #define MV_CHUNK_TILES 16   // warp-tiles per work chunk of the dense kernel
+#endif
+#ifndef MV_STAGE
+#define MV_STAGE 64         // library entries per shared-memory stage of the dense kernel (x2 buffers per warp)
+#endif
+
+__device__ __forceinline__ void mv_cp_async8(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
 #ifndef MV_DENSE_ENTRIES
-#define MV_DENSE_ENTRIES 2    // index entries per group in the dense kernel
+#define MV_DENSE_ENTRIES 8    // index entries per group in the dense kernel (one ballot per group)
 #endif
 #ifndef MV_DENSE_MINBLOCKS
-#define MV_DENSE_MINBLOCKS 3  // occupancy target of the dense kernel (CTAs per SM): 24 warps beat 16
+#define MV_DENSE_MINBLOCKS 4  // occupancy target of the dense kernel (CTAs per SM): 32 warps (64 registers) beat 24 and 16
 #endif
+
+static_assert(MV_DENSE_ENTRIES % 2 == 0 && MV_STAGE % MV_DENSE_ENTRIES == 0,
+              "the dense kernel reads the staged bucket two entries (16 bytes) at a time");
 
 __device__ __forceinline__ uint32_t mv_combo_of_slot(const SearchParams& p, uint32_t slot) {
     uint32_t c = 0;
@@ -166,7 +179,8 @@ __device__ __forceinline__ void mv_drain(const SearchParams& p, uint4* q, uint32
 // filter.  32 groups are re-examined at once, one per lane, so the per-pair compare+branch
 // sequence runs with full lanes instead of the 1-2 lanes that found something (that sequence was
 // ~35 % of the dense kernel's issued instructions when it ran where the group was found).
-// Records past the end of the lane's slot (ragged last tile of a slot) are skipped here.
+// Records past the end of the lane's slot (ragged last tile of a slot) and entries past the end
+// of the bucket (ragged last group) are skipped here.
 static __device__ __noinline__ void mv_resolve_groups(const SearchParams& p, const uint4* __restrict__ gwin,
                                                       const uint32_t* __restrict__ gdir, const uint2* gq, uint32_t n,
                                                       uint4* q, uint32_t* qn) {
@@ -175,18 +189,22 @@ static __device__ __noinline__ void mv_resolve_groups(const SearchParams& p, con
     __syncwarp();
     if (lane < n) {
         const uint2 item = gq[lane];
-        uint2 qe[MV_DENSE_ENTRIES];
+        const uint32_t slot = __ldg(&gwin[item.x].w);
+        const uint32_t slot_end = __ldg(gdir + slot + 1);
+        const uint32_t n_e = min((uint32_t)MV_DENSE_ENTRIES, __ldg(p.dir + slot + 1) - item.y);
+        uint4 w[MV_ITEMS];
 #pragma unroll
-        for (int j = 0; j < MV_DENSE_ENTRIES; j++) qe[j] = __ldg(p.ent_hl + item.y + j);
-        const uint32_t slot_end = __ldg(gdir + __ldg(&gwin[item.x].w) + 1);
+        for (int it = 0; it < MV_ITEMS; it++) w[it] = __ldg(gwin + min(item.x + it * 32, slot_end - 1));
+        for (uint32_t j = 0; j < n_e; j++) {
+            const uint2 qe = __ldg(p.ent_hl + item.y + j);
 #pragma unroll
-        for (int it = 0; it < MV_ITEMS; it++) {
-            const uint32_t idx = item.x + it * 32;
-            if (idx < slot_end) {
-                const uint4 w = __ldg(gwin + idx);
-#pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++)
-                    if (__popc((w.y ^ qe[j].x) | (w.z ^ qe[j].y)) <= k) MV_CANDIDATE(item.y + j, qe[j]);
+            for (int it = 0; it < MV_ITEMS; it++) {
+                if (item.x + it * 32 < slot_end && __popc((w[it].y ^ qe.x) | (w[it].z ^ qe.y)) <= k) {
+                    const uint32_t m_ = (w[it].y ^ qe.x) | (w[it].z ^ qe.y);
+                    const uint32_t qs = atomicAdd(qn, 1u);
+                    if (qs < MV_WQ) q[qs] = make_uint4(w[it].x, m_, item.y + j, slot);
+                    else mv_overflow(p, w[it].x, m_, item.y + j, slot);
+                }
             }
         }
     }
@@ -210,10 +228,12 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
                                                                                  uint32_t slice, uint32_t n_slices) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
     __shared__ uint2 s_gq[MV_WARPS][MV_GQ];
+    __shared__ __align__(16) uint2 s_ent[MV_WARPS][2 * MV_STAGE];
     __shared__ uint32_t s_qn[MV_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint2* gq = s_gq[warp];
+    uint2* sbuf = s_ent[warp];
     uint32_t gn = 0;  // queued groups of this warp (warp-uniform; survives across tiles)
     uint4* q = s_q[warp];
     uint32_t* qn = &s_qn[warp];
@@ -264,66 +284,70 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
                 mine += ok ? 1u : 0u;
             }
             cand += (unsigned long long)(le - ls) * mine;
-            // Software-pipelined walk over the bucket in groups of MV_DENSE_ENTRIES entries, two
-            // groups per iteration with ping-pong register buffers: the entries of the next group
-            // are loaded while the current one is evaluated (ncu: 27 % of the stall samples sat on
-            // the first use of the loaded words before this) and no register moves are needed.
-            // One group = MV_DENSE_ENTRIES x MV_ITEMS independent LOP3/LOP3/POPC chains folded
-            // with 3-input integer min.  A lane whose minimum passes only QUEUES the group (one
-            // ballot, one shared store); mv_resolve_groups re-examines 32 groups at a time.
-#define MV_GROUP(BUF, EBASE)                                                                   \
+            // The bucket is staged through shared memory in chunks of MV_STAGE entries, double
+            // buffered with cp.async one whole chunk ahead (ncu: the bucket words came from L2/DRAM
+            // more often than from L1 - global-load L1 hit rate 63 %, no reuse beyond the sector).
+            // One group = MV_DENSE_ENTRIES entries (16-byte broadcast LDS, two entries each) x
+            // MV_ITEMS windows = 32 independent LOP3/LOP3/POPC chains folded with 3-input integer
+            // min, then ONE ballot: a lane whose minimum passes only QUEUES the group (one shared
+            // store); mv_resolve_groups re-examines 32 groups at a time.  The last group of a
+            // bucket may read stale entries of the stage buffer; the second level bounds them.
+            const uint32_t n_ent = le - ls;
+            const uint32_t n_stage = (n_ent + MV_STAGE - 1) / MV_STAGE;
+            const uint2* bucket = ent + ls;
+#define MV_ISSUE(C)                                                                            \
     do {                                                                                       \
-        int best_ = 33;                                                                        \
-        _Pragma("unroll") for (int it = 0; it < MV_ITEMS; it++) {                              \
-            _Pragma("unroll") for (int j = 0; j < MV_DENSE_ENTRIES; j++)                       \
-                best_ = min(best_, __popc((wv[it].y ^ BUF[j].x) | (wv[it].z ^ BUF[j].y)));     \
+        uint2* dst_ = sbuf + ((C) & 1u) * MV_STAGE;                                            \
+        _Pragma("unroll") for (int h = 0; h < MV_STAGE / 32; h++) {                            \
+            const uint32_t i_ = (C) * MV_STAGE + h * 32 + lane;                                \
+            if (i_ < n_ent) mv_cp_async8(dst_ + h * 32 + lane, bucket + i_);                   \
         }                                                                                      \
-        const uint32_t hit_ = __ballot_sync(0xffffffffu, best_ <= kl);                         \
-        if (hit_) { /* warp-uniform */                                                         \
-            if (best_ <= kl) gq[gn + __popc(hit_ & lt_mask)] = make_uint2(first + lane, (EBASE)); \
-            gn += __popc(hit_);                                                                \
-        }                                                                                      \
+        asm volatile("cp.async.commit_group;" ::: "memory");                                   \
     } while (0)
-            const uint32_t n_groups = (le - ls) / MV_DENSE_ENTRIES;
-            const uint2* gp = ent + ls;
-            uint2 bufA[MV_DENSE_ENTRIES], bufB[MV_DENSE_ENTRIES];
-            if (n_groups) {
-#pragma unroll
-                for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + j);
-            }
-            // The resolve calls sit OUTSIDE the pipelined loop (a call inside it made ptxas spill
-            // the window registers and reload them every iteration): the loop leaves when a full
-            // batch is queued and is re-entered afterwards.
-            uint32_t g = 0;
-            for (;;) {
-                for (; g + 2 <= n_groups && gn < 32; g += 2, gp += 2 * MV_DENSE_ENTRIES) {
-#pragma unroll
-                    for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufB[j] = __ldg(gp + MV_DENSE_ENTRIES + j);
-                    MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);
-                    if (g + 2 < n_groups) {  // warp-uniform
-#pragma unroll
-                        for (int j = 0; j < MV_DENSE_ENTRIES; j++) bufA[j] = __ldg(gp + 2 * MV_DENSE_ENTRIES + j);
-                    }
-                    MV_GROUP(bufB, ls + (g + 1) * MV_DENSE_ENTRIES);
+            MV_ISSUE(0u);
+            for (uint32_t c = 0; c < n_stage; c++) {
+                if (c + 1 < n_stage) {
+                    MV_ISSUE(c + 1);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
-                if (gn < 32) break;
-                do {  // warp-uniform; at most 31 + 2 * 32 groups are queued here
-                    gn -= 32;
-                    mv_resolve_groups(p, gwin, gdir, gq + gn, 32, q, qn);
-                } while (gn >= 32);
-            }
-            if (g < n_groups) MV_GROUP(bufA, ls + g * MV_DENSE_ENTRIES);  // odd group count (<= 63 queued: fits)
-#undef MV_GROUP
-            for (uint32_t e = ls + n_groups * MV_DENSE_ENTRIES; e < le; e++) {  // < MV_DENSE_ENTRIES entries
-                const uint2 qq = __ldg(ent + e);
+                __syncwarp();
+                const uint4* sb = reinterpret_cast<const uint4*>(sbuf + (c & 1u) * MV_STAGE);
+                const uint32_t ng = (min((uint32_t)MV_STAGE, n_ent - c * MV_STAGE) + MV_DENSE_ENTRIES - 1) / MV_DENSE_ENTRIES;
+                const uint32_t ebase = ls + c * MV_STAGE;
+                // The resolve calls sit OUTSIDE the group loop (a call inside it made ptxas spill
+                // the window registers and reload them every iteration): the loop leaves when a
+                // full batch is queued and is re-entered afterwards.
+                uint32_t g = 0;
+                for (;;) {
+                    for (; g < ng && gn < 32; g++) {
+                        int best_ = 33;
 #pragma unroll
-                for (int it = 0; it < MV_ITEMS; it++) {
-                    if (first + it * 32 + lane < b) {
-                        const uint4 w = __ldg(gwin + first + it * 32 + lane);  // reloaded: keeps pos/slot out of the loop's registers
-                        if (__popc((w.y ^ qq.x) | (w.z ^ qq.y)) <= k) MV_CANDIDATE(e, qq);
+                        for (int j = 0; j < MV_DENSE_ENTRIES / 2; j++) {
+                            const uint4 e2 = sb[g * (MV_DENSE_ENTRIES / 2) + j];
+#pragma unroll
+                            for (int it = 0; it < MV_ITEMS; it++) {
+                                best_ = min(best_, __popc((wv[it].y ^ e2.x) | (wv[it].z ^ e2.y)));
+                                best_ = min(best_, __popc((wv[it].y ^ e2.z) | (wv[it].z ^ e2.w)));
+                            }
+                        }
+                        const uint32_t hit_ = __ballot_sync(0xffffffffu, best_ <= kl);
+                        if (hit_) {  // warp-uniform
+                            if (best_ <= kl)
+                                gq[gn + __popc(hit_ & lt_mask)] = make_uint2(first + lane, ebase + g * MV_DENSE_ENTRIES);
+                            gn += __popc(hit_);
+                        }
                     }
+                    if (gn < 32) break;
+                    do {  // warp-uniform; at most 31 + 32 groups are queued here
+                        gn -= 32;
+                        mv_resolve_groups(p, gwin, gdir, gq + gn, 32, q, qn);
+                    } while (gn >= 32);
                 }
+                __syncwarp();  // every lane is done with this buffer before chunk c+2 lands in it
             }
+#undef MV_ISSUE
             mv_drain(p, q, qn, lane);
         }
     }
