@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
                                                                                  const uint4* __restrict__ gwin,
                                                                                  const uint32_t* __restrict__ gdir,
                                                                                  const uint32_t* __restrict__ n_rec_ptr,
-                                                                                 uint32_t slice, uint32_t n_slices) {
+                                                                                 uint32_t* __restrict__ work, uint32_t slice,
+                                                                                 uint32_t n_slices) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
     __shared__ uint2 s_gq[MV_WARPS][MV_GQ];
     __shared__ __align__(16) uint2 s_ent[MV_WARPS][2 * MV_STAGE];
@@ -246,14 +247,20 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
     const uint32_t n_rec = *n_rec_ptr;
     const uint32_t wtile = 32 * MV_ITEMS, chunk = wtile * MV_CHUNK_TILES;
     const uint32_t n_chunks = (n_rec + chunk - 1) / chunk;
-    const uint32_t n_warps = gridDim.x * MV_WARPS;
     const int k = (int)p.k;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
     // a launch handles the slice-th of n_slices equal ranges of chunks (streamed result delivery)
     const uint32_t ch_lo = (uint32_t)((unsigned long long)n_chunks * slice / n_slices);
     const uint32_t ch_hi = (uint32_t)((unsigned long long)n_chunks * (slice + 1) / n_slices);
-    for (uint32_t ch = ch_lo + blockIdx.x * MV_WARPS + warp; ch < ch_hi; ch += n_warps) {
+    // Chunks are handed out through an atomic counter: with a static deal the warps the scheduler
+    // favours (XU arbitration is by warp id) finished at ~60 % of the kernel and the rest could not
+    // keep the POPC pipe full on their own (ncu: 24.5 of 32 warps resident on average).
+    for (;;) {
+        uint32_t ch = 0;
+        if (lane == 0) ch = ch_lo + atomicAdd(work + slice, 1u);
+        ch = __shfl_sync(0xffffffffu, ch, 0);
+        if (ch >= ch_hi) break;
         const uint32_t r0 = ch * chunk, r1 = r0 + min(chunk, n_rec - r0);
         // all of these are warp-uniform (every lane loads the same words)
         uint32_t slot = __ldg(&gwin[r0].w);
@@ -448,6 +455,7 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_gwin) cudaFree(ws.d_gwin);
     if (ws.d_gtmp) cudaFree(ws.d_gtmp);
     if (ws.d_coarse_cursor) cudaFree(ws.d_coarse_cursor);
+    if (ws.d_work) cudaFree(ws.d_work);
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
@@ -511,6 +519,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         JCK(cudaMalloc(&ws.d_scan_tmp, tmp_words * 4));
         ws.scan_tmp_cap = tmp_words;
     }
+    if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, BC_SINK_SLICES * sizeof(uint32_t)));
     if (!ws.d_coarse_cursor) JCK(cudaMalloc(&ws.d_coarse_cursor, ((size_t)BC_MAX_COMBOS << BC_COARSE_BITS) * 4 + 4));
     CoarsePlan pl;
     bc_make_coarse_plan(p.combo, p.n_combos, &pl);
@@ -557,9 +566,10 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         k_verify_sparse<<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir, n_rec_ptr);
         JCK(cudaGetLastError());
         const uint32_t n_slices = sink ? BC_SINK_SLICES : 1;
+        JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
             k_verify_dense<<<(uint32_t)sm_count * MV_DENSE_MINBLOCKS, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir,
-                                                                                           n_rec_ptr, s, n_slices);
+                                                                                           n_rec_ptr, ws.d_work, s, n_slices);
             JCK(cudaGetLastError());
             if (sink) {
                 JCK(cudaMemcpyAsync(sink->h_counts + s, p.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
