@@ -58,7 +58,7 @@ struct SearchParams {
     uint32_t gate_first;        // 1: evaluate the PAM gate before any index work
     // output
     bc_hit* hits;
-    unsigned long long* count;  // [0] hits, [1] candidates, [2] probes
+    unsigned long long* count;  // [0] hits, [1] candidates, [2] probes, [3] next tile of the probe kernel
     unsigned long long cap;
     uint32_t count_candidates;
     uint32_t spacer_id_base;

@@ -332,10 +332,18 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
     uint32_t* n2p = &s_n2[warp];
     unsigned long long cand = 0, probes = 0;
 
-    for (uint32_t tile = p.pos_begin / PROBE_TILE_POS + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // Tiles are handed out through an atomic counter (p.count[3], zeroed with the other counters):
+    // CTAs whose warps the scheduler favours would otherwise finish their static share early and
+    // leave their SM under-occupied for the rest of the kernel.
+    __shared__ uint32_t s_tile;
+    for (;;) {
+        __syncthreads();  // the previous tile is done with the shared planes and with s_tile
+        if (threadIdx.x == 0) s_tile = p.pos_begin / PROBE_TILE_POS + (uint32_t)atomicAdd(p.count + 3, 1ull);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;
         const uint32_t w0 = tile * PROBE_TILE_WORDS;
         const uint32_t tile_pos = tile * PROBE_TILE_POS;
-        __syncthreads();
         if (threadIdx.x < PROBE_SMEM_WORDS) {  // planes are padded by a whole tile (bc_api.cu)
             const bool before = (w0 == 0 && threadIdx.x == 0);  // nothing precedes position 0
             sH[threadIdx.x] = before ? 0u : p.H[w0 - 1 + threadIdx.x];
