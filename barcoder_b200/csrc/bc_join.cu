@@ -7,11 +7,13 @@
 //   pass 1  k_bucket<0/1>   every genome window, for every seed combination c, becomes a 16-byte
 //                           record {dev position, wh, wl, directory slot} placed in slot order:
 //                           histogram -> exclusive scan -> scatter (counting sort, not stable).
-//   pass 2  k_merge_verify  one thread per sorted record.  Neighbouring lanes hold windows of the
-//                           same slot, so the library bucket [dir[slot], dir[slot+1]) is read as
-//                           warp-uniform (broadcast) 8-byte loads that hit L1, and one candidate
-//                           costs 2 LOP3 + POPC + a min-reduce; only batches that contain a hit
-//                           take the slow path (ownership, PAM, staged record).
+//   pass 2  k_verify_dense  slots with many windows: warp-tiles of sorted records aligned to the
+//                           slot start; the library bucket [dir[slot], dir[slot+1]) is staged
+//                           through shared memory and streamed once per tile against the resident
+//                           windows of every lane: 2 LOP3 + POPC + a min-reduce per pair.
+//           k_verify_sparse the records of small slots, one record per lane.
+//                           Pairs that pass are queued per warp and resolved 32 at a time
+//                           (ownership, PAM, one atomic per batch, coalesced 16-byte records).
 //
 // Algorithmic HBM traffic: one 16 B write + one 16 B read per (window, combination), the three
 // genome planes twice per combination, the library index once.

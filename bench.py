@@ -386,7 +386,7 @@ def main():
         alg_bytes = {"genome_bucket": 2 * combos * (3 * G / 8) + 16.0 * records,
                      "verify": 16.0 * records + 12.0 * 2 * n * combos + 16.0 * st["hits"],
                      "index_build": (8 + 16 + 16 + 12) * 2.0 * n * combos}
-        names = {"verify": "k_merge_verify<dense>+<sparse>", "genome_bucket": "k_bucket<0>+scan+k_bucket<1>",
+        names = {"verify": "k_verify_dense+k_verify_sparse", "genome_bucket": "k_bucket<0>+scan+k_bucket<1>",
                  "index_build": "k_index_count+scan+k_index_scatter+k_fine_scatter"}
     else:
         alg_bytes = {"verify": 3 * G / 8 + 16.0 * st["hits"], "genome_bucket": 0.0,
