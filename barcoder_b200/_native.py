@@ -23,6 +23,7 @@ BC_PARAM_COUNT_CANDIDATES = 3
 BC_PARAM_HIT_CAPACITY = 4
 BC_PARAM_SPACER_ID_BASE = 5
 BC_PARAM_SCAN_PART = 6
+BC_PARAM_WINDOW_SORT = 7
 PATH_AUTO, PATH_PROBE, PATH_JOIN = 0, 1, 2
 
 META_PAM_OK = 1 << 3

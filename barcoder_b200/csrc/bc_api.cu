@@ -44,7 +44,7 @@ struct bc_ctx {
 
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
-    int64_t par_scan_rank = 0, par_scan_world = 1;
+    int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0;
 
     // index
     bool have_index = false;
@@ -325,6 +325,9 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
             if (world < 1 || rank >= world) return fail(ctx, BC_EINVAL, "scan part must be rank | world << 16 with rank < world");
             ctx->par_scan_rank = rank; ctx->par_scan_world = world; return BC_OK;
         }
+        case BC_PARAM_WINDOW_SORT:
+            if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "window sort must be 0, 1 or 2");
+            ctx->par_window_sort = value; return BC_OK;
         default: return fail(ctx, BC_EINVAL, "unknown parameter");
     }
 }
@@ -535,6 +538,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->pam_flags = ctx->pam_flags;
     memcpy(p->pam_sets, ctx->pam_sets, sizeof p->pam_sets);
     p->gate_first = ((ctx->pam_flags & BC_PAM_GATE) && ctx->P > 0) ? 1u : 0u;
+    p->window_sort = (uint32_t)ctx->par_window_sort;
     p->hits = ctx->d_hits;
     p->count = ctx->d_count;
     p->cap = ctx->hit_cap;

@@ -76,6 +76,172 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Radix form of the window scatter (BC_PARAM_WINDOW_SORT = 2, chosen automatically for dense
+// directories).  The direct scatter above pays one returning global atomic and one isolated
+// 16-byte store per record (22 ps per record at cfg 4, bound by the L2's atomic + partial-sector
+// store rate, LSU queue full).  Here the exact slot offsets still come from the count pass, but
+// the records reach their slots in two passes that sort RB_CHUNK records at a time in shared
+// memory, so global atomics drop to one per (chunk, bin) and the stores leave as runs:
+//   pass A  k_window_bin    windows -> records grouped by BIN = slot >> 8 (the top key bits), each
+//                           bin region at its final place in a scratch array;
+//   pass B  k_window_place  bin regions -> final slots (low 8 key bits), cursor per slot.
+// Needs every combination's key to be at least 4 nt (directory offsets are multiples of 256 then,
+// so `slot >> 8` is a global bin index) and at most 8 nt (<= 256 bins per combination).
+#define RB_THREADS 256
+#ifndef RB_ITEMS
+#define RB_ITEMS 8
+#endif
+#define RB_CHUNK (RB_THREADS * RB_ITEMS)
+#ifndef RB_MINBLOCKS
+#define RB_MINBLOCKS 6
+#endif
+
+// exclusive scan of one value per thread over the CTA (256 threads); s_warp: 8 words of scratch
+__device__ __forceinline__ uint32_t rb_block_scan(uint32_t v, uint32_t* s_warp) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < RB_THREADS / 32; w++) before += (uint32_t)w < warp ? s_warp[w] : 0u;
+    return before + incl - v;
+}
+
+__global__ void k_bin_init(const uint32_t* __restrict__ gdir, uint32_t* __restrict__ bin_cursor, uint32_t n_bins) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_bins) bin_cursor[g] = gdir[(size_t)g << 8];
+}
+
+__global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS) k_window_bin(const __grid_constant__ BucketParams gp,
+                                                                        uint32_t* __restrict__ bin_cursor,
+                                                                        uint4* __restrict__ tmp) {
+    __shared__ uint32_t s_hist[256], s_lstart[256], s_gbase[256], s_warp[RB_THREADS / 32];
+    __shared__ uint4 s_rec[RB_CHUNK];
+    const uint32_t lm = bc_lmask(gp.L);
+    PamGate gate;
+    bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
+    const uint32_t tid = threadIdx.x;
+    // position-major: the windows of a chunk are read and validated once and then binned for
+    // every combination in turn (they were 40 % of this kernel's instructions when every
+    // combination re-read them)
+    for (uint64_t c0 = (uint64_t)gp.pos_begin + (uint64_t)blockIdx.x * RB_CHUNK; c0 < gp.pos_end;
+         c0 += (uint64_t)gridDim.x * RB_CHUNK) {
+        uint32_t wh[RB_ITEMS], wl[RB_ITEMS], ok = 0;
+#pragma unroll
+        for (int i = 0; i < RB_ITEMS; i++) {
+            const uint64_t pos64 = c0 + tid + (uint32_t)i * RB_THREADS;
+            wh[i] = wl[i] = 0;
+            if (pos64 >= gp.pos_end) continue;
+            const uint32_t pos = (uint32_t)pos64;
+            if (bc_window(gp.B, pos) & lm) continue;
+            if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
+            wh[i] = bc_window(gp.H, pos) & lm;
+            wl[i] = bc_window(gp.Lo, pos) & lm;
+            ok |= 1u << i;
+        }
+        for (uint32_t c = 0; c < gp.n_combos; c++) {
+            const ComboDesc& cd = gp.combo[c];
+            const uint32_t bin0 = cd.dir_off >> 8;
+            s_hist[tid] = 0;
+            __syncthreads();
+            uint32_t slot[RB_ITEMS], rank[RB_ITEMS];
+#pragma unroll
+            for (int i = 0; i < RB_ITEMS; i++) {
+                slot[i] = 0xffffffffu;
+                if (!((ok >> i) & 1u)) continue;
+                const uint32_t sl = cd.dir_off + bc_combo_key(cd, wh[i], wl[i]);
+                if (gp.prune && gp.lib_dir[sl] == gp.lib_dir[sl + 1]) continue;
+                slot[i] = sl;
+                rank[i] = atomicAdd(&s_hist[(sl >> 8) - bin0], 1u);
+            }
+            __syncthreads();
+            const uint32_t cnt = s_hist[tid];
+            s_lstart[tid] = rb_block_scan(cnt, s_warp);
+            if (cnt) s_gbase[tid] = atomicAdd(&bin_cursor[bin0 + tid], cnt);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < RB_ITEMS; i++) {
+                if (slot[i] != 0xffffffffu)
+                    s_rec[s_lstart[(slot[i] >> 8) - bin0] + rank[i]] =
+                        make_uint4((uint32_t)(c0 + tid + (uint32_t)i * RB_THREADS), wh[i], wl[i], slot[i]);
+            }
+            __syncthreads();
+            const uint32_t total = s_lstart[255] + s_hist[255];
+            for (uint32_t i = tid; i < total; i += RB_THREADS) {
+                const uint4 r = s_rec[i];
+                const uint32_t bl = (r.w >> 8) - bin0;
+                tmp[s_gbase[bl] + (i - s_lstart[bl])] = r;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS) k_window_place(const uint4* __restrict__ tmp,
+                                                            const uint32_t* __restrict__ gdir,
+                                                            uint32_t* __restrict__ gcursor, uint4* __restrict__ gwin,
+                                                            const uint32_t* __restrict__ n_rec_ptr,
+                                                            uint32_t* __restrict__ work) {
+    __shared__ uint32_t s_hist[256], s_lstart[256], s_gbase[256], s_warp[RB_THREADS / 32];
+    __shared__ uint4 s_rec[RB_CHUNK];
+    __shared__ uint32_t s_chunk;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_rec = *n_rec_ptr;
+    const uint32_t n_chunks = (n_rec + RB_CHUNK - 1) / RB_CHUNK;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_chunk = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t ch = s_chunk;
+        if (ch >= n_chunks) break;
+        const uint32_t r0 = ch * RB_CHUNK, r1 = r0 + min((uint32_t)RB_CHUNK, n_rec - r0);
+        // a chunk of the scratch array may straddle bin regions: one shared-memory sort per piece
+        uint32_t seg = r0;
+        while (seg < r1) {
+            const uint32_t g = __ldg(&tmp[seg].w) >> 8;
+            const uint32_t s1 = min(r1, __ldg(gdir + (((size_t)g + 1) << 8)));
+            s_hist[tid] = 0;
+            __syncthreads();
+            uint4 rec[RB_ITEMS];
+            uint32_t rank[RB_ITEMS];
+#pragma unroll
+            for (int i = 0; i < RB_ITEMS; i++) {
+                const uint32_t idx = seg + tid + (uint32_t)i * RB_THREADS;
+                if (idx < s1) {
+                    rec[i] = __ldcs(tmp + idx);
+                    rank[i] = atomicAdd(&s_hist[rec[i].w & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            const uint32_t cnt = s_hist[tid];
+            s_lstart[tid] = rb_block_scan(cnt, s_warp);
+            if (cnt) s_gbase[tid] = atomicAdd(&gcursor[((size_t)g << 8) + tid], cnt);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < RB_ITEMS; i++) {
+                const uint32_t idx = seg + tid + (uint32_t)i * RB_THREADS;
+                if (idx < s1) s_rec[s_lstart[rec[i].w & 255u] + rank[i]] = rec[i];
+            }
+            __syncthreads();
+            const uint32_t n = s1 - seg;
+            for (uint32_t i = tid; i < n; i += RB_THREADS) {
+                const uint4 r = s_rec[i];
+                const uint32_t sub = r.w & 255u;
+                gwin[s_gbase[sub] + (i - s_lstart[sub])] = r;
+            }
+            __syncthreads();
+            seg = s1;
+        }
+    }
+}
+
 #define MV_THREADS 256
 #define MV_WARPS (MV_THREADS / 32)
 #ifndef MV_ITEMS
@@ -458,6 +624,7 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_gtmp) cudaFree(ws.d_gtmp);
     if (ws.d_coarse_cursor) cudaFree(ws.d_coarse_cursor);
     if (ws.d_work) cudaFree(ws.d_work);
+    if (ws.d_bin_cursor) cudaFree(ws.d_bin_cursor);
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
@@ -481,7 +648,15 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
 
     // chunk the genome so the window records stay within the workspace budget; the (slow)
     // free-memory query only runs when the cached workspace cannot hold the whole range
-    const uint32_t n_arrays = BC_WINDOWS_TWO_LEVEL ? 2 : 1;  // record arrays (coarse + final)
+    // Radix scatter: possible when every key is 4..8 nt; worth it when the bins are well filled
+    // (each shared-memory sort then emits long runs).
+    bool radix_ok = true;
+    for (uint32_t c = 0; c < p.n_combos; c++) radix_ok = radix_ok && p.combo[c].key_nt >= 4 && p.combo[c].key_nt <= 8;
+    const uint64_t span0 = (uint64_t)p.pos_end - p.pos_begin;
+    const bool radix = !BC_WINDOWS_TWO_LEVEL && radix_ok &&
+                       (p.window_sort == 2 ||
+                        (p.window_sort == 0 && span0 * p.n_combos / ((dir_slots >> 8) + 1) >= 16ull * RB_CHUNK));
+    const uint32_t n_arrays = (BC_WINDOWS_TWO_LEVEL || radix) ? 2 : 1;  // record arrays (scratch + final)
     const uint64_t span = (uint64_t)p.pos_end - p.pos_begin;
     uint64_t chunk = span ? span : 1;
     if (chunk * p.n_combos > ws.gwin_cap) {
@@ -503,6 +678,14 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         JCK(cudaMalloc(&ws.d_gwin, (chunk * p.n_combos + 1) * sizeof(uint4)));
         if (BC_WINDOWS_TWO_LEVEL) JCK(cudaMalloc(&ws.d_gtmp, (chunk * p.n_combos + 1) * sizeof(uint4)));
         ws.gwin_cap = chunk * p.n_combos;
+    }
+    if (radix && !ws.d_gtmp) JCK(cudaMalloc(&ws.d_gtmp, (ws.gwin_cap + 1) * sizeof(uint4)));
+    if (radix && (dir_slots >> 8) + 1 > ws.bin_cap) {
+        if (ws.d_bin_cursor) cudaFree(ws.d_bin_cursor);
+        ws.d_bin_cursor = nullptr;
+        ws.bin_cap = 0;
+        JCK(cudaMalloc(&ws.d_bin_cursor, ((dir_slots >> 8) + 1) * sizeof(uint32_t)));
+        ws.bin_cap = (dir_slots >> 8) + 1;
     }
     if (dir_slots > ws.gdir_cap) {
         if (ws.d_gdir) cudaFree(ws.d_gdir);
@@ -558,6 +741,19 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
             JCK(cudaGetLastError());
             JCK(bc_launch_fine_scatter(0, ws.d_gtmp, ws.d_gdir + (dir_slots - 1), ws.d_gcursor, ws.d_gwin, nullptr,
                                        nullptr, sm_count, st));
+        } else if (radix) {
+            const uint32_t n_bins = (uint32_t)((dir_slots - 1) >> 8);
+            k_bin_init<<<(n_bins + 255) / 256, 256, 0, st>>>(ws.d_gdir, ws.d_bin_cursor, n_bins);
+            JCK(cudaGetLastError());
+            uint32_t bx = (npos + RB_CHUNK - 1) / RB_CHUNK;
+            if (bx > (uint32_t)sm_count * RB_MINBLOCKS) bx = (uint32_t)sm_count * RB_MINBLOCKS;
+            k_window_bin<<<bx, RB_THREADS, 0, st>>>(gp, ws.d_bin_cursor, ws.d_gtmp);
+            JCK(cudaGetLastError());
+            JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
+            k_window_place<<<(uint32_t)sm_count * RB_MINBLOCKS, RB_THREADS, 0, st>>>(ws.d_gtmp, ws.d_gdir, ws.d_gcursor, ws.d_gwin,
+                                                                        ws.d_gdir + (dir_slots - 1), ws.d_work);
+            JCK(cudaGetLastError());
+            bc_launch_counter += 2;
         } else {
             k_bucket<1><<<grid, 256, 0, st>>>(gp, pl, ws.d_gcursor, ws.d_gwin);
             JCK(cudaGetLastError());

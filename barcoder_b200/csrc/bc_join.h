@@ -9,6 +9,8 @@ struct JoinWorkspace {
     uint4* d_gwin = nullptr;        // {dev position, wh, wl, slot} window records in slot order
     uint4* d_gtmp = nullptr;        // the same records after the coarse (level-1) scatter
     uint32_t* d_coarse_cursor = nullptr;
+    uint32_t* d_bin_cursor = nullptr;  // radix window scatter: write cursor of every bin (slot >> 8)
+    uint64_t bin_cap = 0;
     uint32_t* d_work = nullptr;      // per-slice chunk counters of the dense verify kernel (dynamic work distribution)
     uint32_t* d_scan_tmp = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;

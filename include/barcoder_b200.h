@@ -70,6 +70,8 @@ typedef struct {
 #define BC_PARAM_SPACER_ID_BASE 5   /* added to every spacer_id (global ids of a library shard) */
 #define BC_PARAM_SCAN_PART 6         /* genome-range sharding: value = rank | world << 16; this
                                        context scans only its 1/world slice of window starts  */
+#define BC_PARAM_WINDOW_SORT 7       /* bucket-join path, genome-side sort: 0 auto, 1 direct scatter,
+                                        2 two-pass shared-memory radix scatter                    */
 
 typedef struct {
     uint64_t genome_bases;    /* G                                                   */

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gpu(genome, off, lib, k, pam="", direction="downstream", iupac=False, gate=False, blocks=0, path=0,
-            hit_cap=0):
+            hit_cap=0, window_sort=0):
     with _native.Searcher(0) as s:
         s.set_genome_array(genome, off)
         s.set_library(lib)
@@ -23,6 +23,8 @@ def run_gpu(genome, off, lib, k, pam="", direction="downstream", iupac=False, ga
             s.set_param(_native.BC_PARAM_PATH, path)
         if hit_cap:
             s.set_param(_native.BC_PARAM_HIT_CAPACITY, hit_cap)
+        if window_sort:
+            s.set_param(_native.BC_PARAM_WINDOW_SORT, window_sort)
         n = s.search(k)
         hits = s.hits()
         assert len(hits) == n
@@ -253,3 +255,38 @@ def test_hit_sink_with_device_buffer_overflow_retry():
         s.set_hit_sink(sink.ctypes.data, len(sink))
         assert s.search(2) == len(ref)
         assert_same(_native.canonical_sort(sink.copy()), ref)
+
+
+# ------------------------------------------------ radix form of the genome-side sort (pass A/B)
+@pytest.mark.parametrize("k,blocks", [(0, 1), (1, 2), (1, 4), (2, 3), (2, 5), (3, 4), (3, 5), (3, 6)])
+@pytest.mark.parametrize("L", [20, 32])
+def test_join_radix_window_sort_every_seed_scheme(k, blocks, L):
+    """BC_PARAM_WINDOW_SORT=2 must give the same records as the direct scatter wherever it applies
+    (keys of 4..8 nt) and fall back silently elsewhere."""
+    genome, off, lib = small_case(L, k, seed=13 * blocks + k + L, n=400, G=90000)
+    ref = run_oracle(genome, off, lib, k, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, k, pam="NGG", blocks=blocks, path=2, window_sort=2)
+    assert st["path"] == 2
+    assert_same(gpu, ref)
+
+
+@pytest.mark.parametrize("gate", [False, True])
+def test_join_radix_window_sort_medium(gate):
+    """Several 2048-record chunks per bin, ragged last chunk, N runs, many contigs, PAM gate."""
+    genome, off = synth.random_genome(2_500_000, seed=51, n_contigs=9, n_fraction=0.003)
+    lib = synth.random_library(150000, 20, seed=52)
+    synth.plant(lib, genome, 0.2, 3, seed=53)
+    ref = run_oracle(genome, off, lib, 3, pam="NGG", gate=gate)
+    for ws in (1, 2):
+        gpu, st = run_gpu(genome, off, lib, 3, pam="NGG", gate=gate, blocks=5, path=2, window_sort=ws)
+        assert_same(gpu, ref)
+
+
+def test_join_radix_window_sort_short_keys_and_dense_slots():
+    """4-nt keys (one bin per combination), huge slots, duplicate spacers."""
+    genome, off = synth.random_genome(300000, seed=61, n_contigs=3, n_fraction=0.01, n_run=5)
+    lib = synth.random_library(3000, 8, seed=62, distinct=False)
+    ref = run_oracle(genome, off, lib, 1, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=2, window_sort=2)
+    assert len(ref) > 100000
+    assert_same(gpu, ref)
