@@ -15,6 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BARCODER_B200_LIB") or os.path.join(_PKG, "libbarcoder_b200.so")
 
 BC_OK = 0
+BC_EINVAL, BC_ECUDA, BC_ENODEV, BC_ENOMEM, BC_ELIMIT = -1, -2, -3, -4, -5
 BC_PAM_IUPAC = 1
 BC_PAM_GATE = 2
 BC_PARAM_BLOCKS = 1
@@ -35,8 +36,12 @@ HIT_DTYPE = np.dtype([("spacer_id", "<u4"), ("gpos", "<u4"), ("mm_mask", "<u4"),
 EXPORTS = (
     "bc_abi_version", "bc_create", "bc_destroy", "bc_set_genome", "bc_set_genome_dev", "bc_set_library",
     "bc_set_library_dev", "bc_set_pam", "bc_set_param", "bc_build_index", "bc_search", "bc_copy_hits",
-    "bc_set_hit_sink", "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
+    "bc_set_hit_sink", "bc_set_slice_callback", "bc_peer_export", "bc_peer_open", "bc_peer_close", "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
 )
+
+
+# void fn(void* user, const bc_hit* d_hits, uint64_t begin, uint64_t end)
+SLICE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64)
 
 
 class NativeLibraryError(RuntimeError):
@@ -92,6 +97,10 @@ def load():
     L.bc_search.argtypes = [vp, i32, ctypes.POINTER(u64)]
     L.bc_copy_hits.argtypes = [vp, vp, u64]
     L.bc_set_hit_sink.argtypes = [vp, vp, u64]
+    L.bc_set_slice_callback.argtypes = [vp, SLICE_FN, vp]
+    L.bc_peer_export.argtypes = [vp, u64, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.bc_peer_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.bc_peer_close.argtypes = [vp, vp, ctypes.c_int]
     L.bc_hits_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.bc_get_stats.argtypes = [vp, ctypes.POINTER(BcStats)]
     L.bc_enumerate_guides.argtypes = [vp, u32, ctypes.c_char_p, i32, u32, ctypes.POINTER(u64)]
@@ -222,6 +231,33 @@ class Searcher:
         """Stream the records of every following search() into caller-owned host memory while the
         search runs (pinned memory lets the copies overlap it); host_ptr=None removes the sink."""
         self._check(self._L.bc_set_hit_sink(self._ctx, host_ptr or None, int(cap_records) if host_ptr else 0))
+
+    def set_slice_callback(self, fn):
+        """fn(d_hits_base_pointer, begin, end) is called from inside search() whenever records
+        [begin, end) of the device hit buffer are final; None removes it.  With a callback a hit
+        buffer overflow is an error (code BC_ELIMIT, stats()['hits'] = needed capacity)."""
+        if fn is None:
+            self._slice_cb = SLICE_FN()   # NULL function pointer
+        else:
+            self._slice_cb = SLICE_FN(lambda user, base, begin, end: fn(base or 0, begin, end))
+        self._check(self._L.bc_set_slice_callback(self._ctx, self._slice_cb, None))
+
+    def peer_export(self, n_records):
+        """Allocate a device buffer of n_records hit records and export it: (pointer, 64-byte CUDA IPC
+        handle).  Other processes of the box open it with peer_open() and use a slice of it as their
+        hit sink."""
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self._check(self._L.bc_peer_export(self._ctx, int(n_records), ctypes.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def peer_open(self, handle):
+        ptr = ctypes.c_void_p()
+        self._check(self._L.bc_peer_open(self._ctx, bytes(handle), ctypes.byref(ptr)))
+        return ptr.value
+
+    def peer_close(self, ptr, owner):
+        self._check(self._L.bc_peer_close(self._ctx, ptr, 1 if owner else 0))
 
     def hits_device(self):
         ptr, n = ctypes.c_void_p(), ctypes.c_uint64()

@@ -579,10 +579,10 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         CK(cudaMemsetAsync(ctx->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream));
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         uint32_t launches = 0;
-        ctx->sink.copied = 0;
+        ctx->sink.copied = ctx->sink.reported = 0;
         if (ctx->stats.path == 2) {
             CK(bc_join_search(ctx->join, p, ctx->dir_slots, ctx->sm_count, ctx->stream, &launches,
-                              ctx->sink.host ? &ctx->sink : nullptr));
+                              (ctx->sink.host || ctx->sink.fn) ? &ctx->sink : nullptr));
         } else {
             CK(cudaEventRecord(ctx->ev2, ctx->stream));
             CK(bc_launch_scan_probe(p, ctx->sm_count, ctx->stream));
@@ -607,6 +607,10 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
             break;
         }
         // The buffer was too small: the kernel kept counting, so the exact size is known now.
+        if (ctx->sink.fn) {  // parts of this attempt were already handed over: the caller restarts
+            ctx->stats.hits = counts[0];
+            return fail(ctx, BC_ELIMIT, "bc_search: hit buffer overflow with a slice callback installed (raise BC_PARAM_HIT_CAPACITY)");
+        }
         uint64_t need = counts[0] + counts[0] / 16 + 1024;
         dfree(ctx->d_hits);
         ctx->hit_cap = 0;
@@ -619,28 +623,87 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
     ctx->stats.ms_scan_kernel = ms_scan;
     ctx->stats.ms_genome_bucket = ms_bucket;
     if (n_hits_out) *n_hits_out = ctx->n_hits;
+    if (ctx->sink.fn && ctx->n_hits > ctx->sink.reported) {  // the rest (all of it on the probe path)
+        ctx->sink.fn(ctx->sink.fn_user, ctx->d_hits, ctx->sink.reported, ctx->n_hits);
+        ctx->sink.reported = ctx->n_hits;
+    }
     if (ctx->sink.host) {
         if (ctx->n_hits > ctx->sink.cap) return fail(ctx, BC_ELIMIT, "bc_search: more hits than the hit sink holds (use bc_copy_hits)");
         if (ctx->n_hits > ctx->sink.copied)  // whatever the slices did not deliver yet (all of it on the probe path)
             CK(cudaMemcpyAsync(ctx->sink.host + ctx->sink.copied, ctx->d_hits + ctx->sink.copied,
-                               (ctx->n_hits - ctx->sink.copied) * sizeof(bc_hit), cudaMemcpyDeviceToHost, ctx->sink.stream));
+                               (ctx->n_hits - ctx->sink.copied) * sizeof(bc_hit), cudaMemcpyDefault, ctx->sink.stream));
         CK(cudaStreamSynchronize(ctx->sink.stream));
     }
+    return BC_OK;
+}
+
+static int sink_resources(bc_ctx* ctx) {
+    if (ctx->sink.stream) return BC_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamCreateWithFlags(&ctx->sink.stream, cudaStreamNonBlocking));
+    CK(cudaHostAlloc((void**)&ctx->sink.h_counts, BC_SINK_SLICES * sizeof(unsigned long long), cudaHostAllocDefault));
+    for (int i = 0; i < BC_SINK_SLICES; i++) CK(cudaEventCreateWithFlags(&ctx->sink.ev[i], cudaEventDisableTiming));
+    return BC_OK;
+}
+
+extern "C" int bc_set_slice_callback(bc_ctx* ctx, bc_slice_fn fn, void* user) {
+    if (!ctx) return BC_EINVAL;
+    if (fn) {
+        int rc = sink_resources(ctx);
+        if (rc != BC_OK) return rc;
+    }
+    ctx->sink.fn = fn;
+    ctx->sink.fn_user = fn ? user : nullptr;
     return BC_OK;
 }
 
 extern "C" int bc_set_hit_sink(bc_ctx* ctx, bc_hit* dst, uint64_t cap) {
     if (!ctx) return BC_EINVAL;
     if (dst && cap == 0) return fail(ctx, BC_EINVAL, "bc_set_hit_sink: zero capacity");
-    CK(cudaSetDevice(ctx->device));
-    if (dst && !ctx->sink.stream) {
-        CK(cudaStreamCreateWithFlags(&ctx->sink.stream, cudaStreamNonBlocking));
-        CK(cudaHostAlloc((void**)&ctx->sink.h_counts, BC_SINK_SLICES * sizeof(unsigned long long), cudaHostAllocDefault));
-        for (int i = 0; i < BC_SINK_SLICES; i++) CK(cudaEventCreateWithFlags(&ctx->sink.ev[i], cudaEventDisableTiming));
+    if (dst) {
+        int rc = sink_resources(ctx);
+        if (rc != BC_OK) return rc;
     }
     ctx->sink.host = dst;
     ctx->sink.cap = dst ? cap : 0;
     ctx->sink.copied = 0;
+    return BC_OK;
+}
+
+extern "C" int bc_peer_export(bc_ctx* ctx, uint64_t n_records, bc_hit** d_ptr, unsigned char handle[64]) {
+    if (!ctx || !d_ptr || !handle || n_records == 0) return ctx ? fail(ctx, BC_EINVAL, "bc_peer_export: bad argument") : BC_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, n_records * sizeof(bc_hit)));   // a whole allocation of its own: IPC handles name allocations
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        CK(e);
+    }
+    memcpy(handle, &h, sizeof h);
+    *d_ptr = (bc_hit*)p;
+    return BC_OK;
+}
+
+extern "C" int bc_peer_open(bc_ctx* ctx, const unsigned char handle[64], bc_hit** d_ptr) {
+    if (!ctx || !d_ptr || !handle) return ctx ? fail(ctx, BC_EINVAL, "bc_peer_open: bad argument") : BC_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = (bc_hit*)p;
+    return BC_OK;
+}
+
+extern "C" int bc_peer_close(bc_ctx* ctx, bc_hit* d_ptr, int owner) {
+    if (!ctx) return BC_EINVAL;
+    if (!d_ptr) return BC_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (owner) CK(cudaFree(d_ptr));
+    else CK(cudaIpcCloseMemHandle(d_ptr));
     return BC_OK;
 }
 

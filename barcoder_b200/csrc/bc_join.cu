@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
                                                                                  const uint32_t* __restrict__ gdir,
                                                                                  const uint32_t* __restrict__ n_rec_ptr,
                                                                                  uint32_t* __restrict__ work, uint32_t slice,
-                                                                                 uint32_t n_slices) {
+                                                                                 uint32_t frac_lo, uint32_t frac_hi) {
     __shared__ uint4 s_q[MV_WARPS][MV_WQ];
     __shared__ uint2 s_gq[MV_WARPS][MV_GQ];
     __shared__ __align__(16) uint2 s_ent[MV_WARPS][2 * MV_STAGE];
@@ -418,9 +418,9 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
     const int k = (int)p.k;
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
-    // a launch handles the slice-th of n_slices equal ranges of chunks (streamed result delivery)
-    const uint32_t ch_lo = (uint32_t)((unsigned long long)n_chunks * slice / n_slices);
-    const uint32_t ch_hi = (uint32_t)((unsigned long long)n_chunks * (slice + 1) / n_slices);
+    // a launch handles the chunks [frac_lo, frac_hi) / 65536 of the record array (streamed result delivery)
+    const uint32_t ch_lo = (uint32_t)(((unsigned long long)n_chunks * frac_lo) >> 16);
+    const uint32_t ch_hi = (uint32_t)(((unsigned long long)n_chunks * frac_hi) >> 16);
     // Chunks are handed out through an atomic counter: with a static deal the warps the scheduler
     // favours (XU arbitration is by warp id) finished at ~60 % of the kernel and the rest could not
     // keep the POPC pipe full on their own (ncu: 24.5 of 32 warps resident on average).
@@ -763,11 +763,15 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         const uint32_t* n_rec_ptr = ws.d_gdir + (dir_slots - 1);
         k_verify_sparse<<<(uint32_t)sm_count * 6u, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir, n_rec_ptr);
         JCK(cudaGetLastError());
+        // Streamed delivery: the slices halve (1/2, 1/4, ... and the last one repeated), so most
+        // of the result is on its way early, only 1/2^(S-1) of it is still to be copied when the
+        // last kernel ends, and there are few launch tails to pay for.
         const uint32_t n_slices = sink ? BC_SINK_SLICES : 1;
         JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
-            k_verify_dense<<<(uint32_t)sm_count * MV_DENSE_MINBLOCKS, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir,
-                                                                                           n_rec_ptr, ws.d_work, s, n_slices);
+            const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));
+            k_verify_dense<<<(uint32_t)sm_count * MV_DENSE_MINBLOCKS, MV_THREADS, 0, st>>>(
+                p, ws.d_gwin, ws.d_gdir, n_rec_ptr, ws.d_work, s, n_slices == 1 ? 0u : f_lo, f_hi);
             JCK(cudaGetLastError());
             if (sink) {
                 JCK(cudaMemcpyAsync(sink->h_counts + s, p.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -783,10 +787,15 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
                 JCK(cudaEventSynchronize(sink->ev[s]));
                 uint64_t done = sink->h_counts[s];
                 if (done > p.cap) done = p.cap;
+                if (sink->fn && done >= sink->reported) {  // also called for an empty part: callers count calls
+                    sink->fn(sink->fn_user, p.hits, sink->reported, done);
+                    sink->reported = done;
+                }
+                if (!sink->host) continue;
                 if (done > sink->cap) done = sink->cap;
                 if (done > sink->copied) {
                     JCK(cudaMemcpyAsync(sink->host + sink->copied, p.hits + sink->copied,
-                                        (done - sink->copied) * sizeof(bc_hit), cudaMemcpyDeviceToHost, sink->stream));
+                                        (done - sink->copied) * sizeof(bc_hit), cudaMemcpyDefault, sink->stream));
                     sink->copied = done;
                 }
             }

@@ -20,11 +20,15 @@ struct JoinWorkspace {
     float ms_bucket_kernels = 0;    // device time of the genome bucketing kernels (count, scan, scatter)
 };
 
-// Streamed result delivery (bc_set_hit_sink): while the verify kernels of later slices run, the
-// hit records of finished slices are copied to the caller's host buffer on a second stream.
-#define BC_SINK_SLICES 8
+// Streamed result delivery (bc_set_hit_sink / bc_set_slice_callback): while the verify kernels of
+// later slices run, the hit records of finished slices are copied to the caller's host buffer on
+// a second stream and/or reported to the caller's callback.
+#define BC_SINK_SLICES 5
 struct HitSink {
-    bc_hit* host = nullptr;            // caller's destination (pinned memory makes the copies asynchronous)
+    bc_slice_fn fn = nullptr;          // bc_set_slice_callback: told about every finished part of the buffer
+    void* fn_user = nullptr;
+    uint64_t reported = 0;             // records already reported to fn in this search
+    bc_hit* host = nullptr;            // caller's destination: pinned host memory, or device memory of this / a peer GPU
     uint64_t cap = 0;                  // records the destination can hold
     uint64_t copied = 0;               // records already queued for copy in this search
     cudaStream_t stream = nullptr;     // copy stream

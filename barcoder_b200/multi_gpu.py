@@ -67,6 +67,163 @@ def gather_hits(local, group=None, dst=0):
     return None, counts_host
 
 
+class PeerGather:
+    """The merge the north star asks for, without a collective in the data path: `dst` owns one
+    device buffer with a fixed region of `cap_per_rank` records per rank and exports it (CUDA
+    IPC); every rank names its region as the hit sink of its searcher, so its records cross
+    NVLink through the copy engines WHILE its search runs (bc_set_hit_sink streams finished parts
+    of the hit buffer).  After search(), finish() exchanges the per-rank counts (one small
+    all_gather, which is also the completion barrier).  On dst, segments() / merged() view the
+    result.  Measured at 8 GPUs (cfg 4): the NCCL gather-v after the search costs ~10 ms per step,
+    an NCCL gather overlapped slice by slice is slower still (its kernels wait for SM slots behind
+    the persistent verify CTAs); copy-engine peer writes hide the transfer."""
+
+    def __init__(self, searcher, device, cap_per_rank, group=None, dst=0):
+        import torch.distributed as dist
+        self.searcher, self.device, self.group, self.dst = searcher, device, group, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.cap = int(cap_per_rank)
+        box = [None]
+        if self.rank == dst:
+            self.base, handle = searcher.peer_export(self.cap * self.world)
+            box[0] = handle
+        dist.broadcast_object_list(box, src=dst, group=group)
+        if self.rank != dst:
+            self.base = searcher.peer_open(box[0])
+        self.counts = [0] * self.world
+        searcher.set_hit_sink(self.base + 16 * self.cap * self.rank, self.cap)
+
+    def finish(self, n_local):
+        """Collective.  n_local = what this rank's search() returned.  Returns the per-rank counts."""
+        import torch
+        import torch.distributed as dist
+        mine = torch.tensor([int(n_local)], dtype=torch.int64, device=self.device)
+        allc = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        self.counts = allc.cpu().tolist()
+        return self.counts
+
+    def segments(self):
+        """dst only: one zero-copy int32 [n_r, 4] view per rank."""
+        import torch
+        assert self.rank == self.dst
+        return [torch.as_tensor(_DeviceBuffer(self.base + 16 * self.cap * r, c), device=self.device) if c
+                else torch.empty((0, 4), dtype=torch.int32, device=self.device) for r, c in enumerate(self.counts)]
+
+    def merged(self):
+        import torch
+        return torch.cat(self.segments())
+
+    def close(self):
+        import torch.distributed as dist
+        self.searcher.set_hit_sink(None, 0)
+        dist.barrier(group=self.group)      # nobody may still be writing when the owner frees the buffer
+        self.searcher.peer_close(self.base, self.rank == self.dst)
+        self.base = 0
+
+
+class StreamedGather:
+    """gather_hits in pieces.  Every rank calls push() with the records that became final since its
+    last call; the pieces travel to `dst` (grouped send/recv, asynchronous) while the caller keeps
+    searching.  Ranks may push different numbers of pieces: a rank that is finished keeps calling
+    push(empty, done=True) until push() returns True (= every rank is done), then finish()."""
+
+    def __init__(self, device, group=None, dst=0, capacity=0):
+        import torch
+        import torch.distributed as dist
+        self.device, self.group, self.dst = device, group, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.out = torch.empty((int(capacity), 4), dtype=torch.int32, device=device) if self.rank == dst else None
+        self.total = 0
+        self.per_rank = [0] * self.world
+        self.works, self.keep = [], []
+
+    def _wait(self):
+        for w in self.works:
+            w.wait()
+        self.works, self.keep = [], []
+
+    def push(self, piece, done=False):
+        import torch
+        import torch.distributed as dist
+        mine = torch.tensor([int(piece.shape[0]), 1 if done else 0], dtype=torch.int64, device=self.device)
+        allm = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allm, mine, group=self.group)
+        m = allm.cpu().tolist()
+        counts, dones = m[0::2], m[1::2]
+        ops = []
+        if self.rank == self.dst:
+            need = self.total + sum(counts)
+            if need > self.out.shape[0]:     # grow: earlier pieces may still be landing in the old buffer
+                self._wait()
+                bigger = torch.empty((int(need * 1.5) + 1024, 4), dtype=torch.int32, device=self.device)
+                bigger[:self.total].copy_(self.out[:self.total])
+                self.out = bigger
+            off = self.total
+            for r, c in enumerate(counts):
+                if r == self.dst:
+                    if c:
+                        self.out[off:off + c].copy_(piece)
+                elif c:
+                    ops.append(dist.P2POp(dist.irecv, self.out[off:off + c], r, self.group))
+                off += c
+        elif counts[self.rank]:
+            piece = piece.contiguous()
+            self.keep.append(piece)
+            ops.append(dist.P2POp(dist.isend, piece, self.dst, self.group))
+        if ops:
+            self.works += dist.batch_isend_irecv(ops)
+        for r, c in enumerate(counts):
+            self.per_rank[r] += c
+        self.total += sum(counts)
+        return all(dones)
+
+    def finish(self):
+        self._wait()
+        return (self.out[:self.total] if self.rank == self.dst else None), self.per_rank
+
+
+def search_and_gather(searcher, k, device, group=None, dst=0, capacity=0, _attempt=0):
+    """search() + gather_hits() with the transfer overlapped: the searcher reports every finished
+    part of its device hit buffer (bc_set_slice_callback) and the part is sent to `dst` while the
+    verify kernels of the later parts are still running.  Returns (merged int32 [n, 4] tensor on
+    dst / None elsewhere, per-rank counts)."""
+    import torch
+    import torch.distributed as dist
+    from . import _native
+
+    sg = StreamedGather(device, group, dst, capacity)
+    empty = torch.empty((0, 4), dtype=torch.int32, device=device)
+
+    def on_slice(base, begin, end):
+        n = int(end - begin)
+        piece = torch.as_tensor(_DeviceBuffer(base + 16 * int(begin), n), device=device) if n else empty
+        sg.push(piece)
+
+    overflow = 0
+    searcher.set_slice_callback(on_slice)
+    try:
+        searcher.search(k)
+    except _native.NativeError as e:
+        if e.code != _native.BC_ELIMIT or "overflow" not in e.message:
+            raise
+        overflow = int(searcher.stats()["hits"])
+    finally:
+        searcher.set_slice_callback(None)
+    while not sg.push(empty, done=True):
+        pass
+    merged, per_rank = sg.finish()
+    flag = torch.tensor([1 if overflow else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if flag.item():     # some rank's hit buffer overflowed: its pieces were partial, everybody repeats
+        if _attempt >= 3:
+            raise RuntimeError("hit buffer kept overflowing")
+        if overflow:
+            searcher.set_param(_native.BC_PARAM_HIT_CAPACITY, overflow + overflow // 16 + 1024)
+        return search_and_gather(searcher, k, device, group, dst, capacity, _attempt + 1)
+    return merged, per_rank
+
+
 def records_from_tensor(t):
     """int32 [n, 4] tensor -> structured numpy hit records on the host."""
     from ._native import HIT_DTYPE

@@ -270,14 +270,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    peer = {"g": None}
+
     def step_resident():
         s.build_index(k)
         nh = s.search(k)
         if world > 1:
-            local = multi_gpu.hits_as_tensor(s, device)
-            merged, _ = multi_gpu.gather_hits(local)
-            torch.cuda.synchronize()
-            return merged.shape[0] if merged is not None else nh
+            if peer["g"] is None:
+                # first (warm-up) step: size the per-rank regions of rank 0's peer buffer from the
+                # largest shard; from now on the records reach rank 0 while the search runs
+                m = torch.tensor([nh], dtype=torch.int64, device=device)
+                dist.all_reduce(m, op=dist.ReduceOp.MAX)
+                peer["g"] = multi_gpu.PeerGather(s, device, int(m.item() * 1.05) + 1024)
+                nh = s.search(k)
+            counts = peer["g"].finish(nh)
+            return sum(counts)
         return nh
 
     h_hits = {"buf": None}
@@ -342,6 +349,8 @@ def main():
     for key in acc:
         acc[key] /= args.steps
     st = s.stats()
+    if peer["g"] is not None:
+        peer["g"].close()
 
     # ---- end-to-end arm: host buffers in, host records out
     e2e_steps = max(2, min(args.steps, 3)) if not args.no_e2e else 0

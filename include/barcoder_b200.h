@@ -144,10 +144,34 @@ int bc_copy_hits(bc_ctx* ctx, bc_hit* dst, uint64_t cap);
  * `dst` (host memory, `cap` records; page-locked memory lets the copies overlap the search)
  * WHILE the search runs, so that when bc_search returns dst[0..n_hits) is complete and no
  * bc_copy_hits is needed - the counterpart of bowtie writing the SAM file while it aligns
- * (BowtieRunner.py:111-136, `-S ... sam_path`).  dst = NULL removes the sink.  If more than
+ * (BowtieRunner.py:111-136, `-S ... sam_path`).  `dst` may also be device memory of this or a
+ * peer GPU (see bc_peer_open).  dst = NULL removes the sink.  If more than
  * `cap` hits are found bc_search fails with BC_ELIMIT; the records stay on the device and
  * bc_copy_hits still works. */
 int bc_set_hit_sink(bc_ctx* ctx, bc_hit* dst, uint64_t cap);
+
+/* Streamed hand-over on the device: `fn(user, d_hits, begin, end)` is called on the calling host
+ * thread, from inside bc_search, every time another part [begin, end) of the device hit buffer
+ * is final (the bucket-join path reports after each of its verify slices while the later slices
+ * are still running; the probe path reports once).  `d_hits` is the buffer base; the records
+ * stay valid until the next bc_search.  Used by the multi-GPU merge to send finished records to
+ * the gathering rank while the search continues (the NCCL gather the reference has no
+ * counterpart for; BASELINE north star).  With a callback installed bc_search does not repeat a
+ * search whose hit buffer overflowed: it fails with BC_ELIMIT, bc_stats.hits holds the needed
+ * capacity and the caller raises BC_PARAM_HIT_CAPACITY.  fn = NULL removes the callback. */
+typedef void (*bc_slice_fn)(void* user, const bc_hit* d_hits, uint64_t begin, uint64_t end);
+int bc_set_slice_callback(bc_ctx* ctx, bc_slice_fn fn, void* user);
+
+/* Peer result buffers: the multi-GPU merge without a collective.  The gathering process exports a
+ * device buffer (bc_peer_export: allocation + CUDA IPC handle, 64 bytes, to be shipped to the
+ * other processes of the box by any means); every other process opens it (bc_peer_open) and
+ * names ITS slice of it as its hit sink (bc_set_hit_sink accepts any unified-address pointer:
+ * host memory or peer device memory).  Its records then cross NVLink through the copy engines
+ * while its search is still running - no SMs, no rendezvous.  bc_peer_close releases a mapping
+ * (owner = 0) or the allocation itself (owner = 1). */
+int bc_peer_export(bc_ctx* ctx, uint64_t n_records, bc_hit** d_ptr, unsigned char handle[64]);
+int bc_peer_open(bc_ctx* ctx, const unsigned char handle[64], bc_hit** d_ptr);
+int bc_peer_close(bc_ctx* ctx, bc_hit* d_ptr, int owner);
 
 /* Device-side view of the result buffer (valid until the next bc_search/bc_destroy),
  * for callers that gather across GPUs without a host round trip. */

@@ -200,6 +200,62 @@ def test_two_shards_on_one_gpu_equal_one_shard():
     assert merged.tobytes() == whole.tobytes()
 
 
+@pytest.mark.parametrize("path", [1, 2])
+def test_search_and_gather_single_rank_group(path):
+    """multi_gpu.search_and_gather through a one-rank NCCL group: the slice callbacks deliver every
+    record exactly once (also across a hit-buffer overflow, which repeats the search)."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        dev = torch.device("cuda", 0)
+        genome, off = synth.random_genome(800_000, seed=71, n_contigs=4, n_fraction=0.002)
+        lib = synth.random_library(40_000, 20, seed=72)
+        synth.plant(lib, genome, 0.3, 2, seed=73)
+        with _native.Searcher(0) as s:
+            s.set_genome_array(genome, off)
+            s.set_library(lib)
+            s.set_pam("NGG")
+            s.set_param(_native.BC_PARAM_PATH, path)
+            s.search(2)
+            whole = _native.canonical_sort(s.hits())
+            assert len(whole) > 5000
+            calls = []
+            s.set_slice_callback(lambda base, b, e: calls.append((b, e)))
+            s.search(2)
+            s.set_slice_callback(None)
+            assert calls[0][0] == 0 and calls[-1][1] == len(whole)
+            assert all(calls[i][1] == calls[i + 1][0] for i in range(len(calls) - 1))
+            merged, per_rank = multi_gpu.search_and_gather(s, 2, dev, capacity=16)
+            assert per_rank == [len(whole)]
+            got = _native.canonical_sort(multi_gpu.records_from_tensor(merged))
+            assert got.tobytes() == whole.tobytes()
+            # peer-buffer merge (world of one: the owner's own region, filled through the hit sink)
+            pg = multi_gpu.PeerGather(s, dev, len(whole) + 10)
+            n = s.search(2)
+            assert pg.finish(n) == [len(whole)]
+            got = _native.canonical_sort(multi_gpu.records_from_tensor(pg.merged()))
+            assert got.tobytes() == whole.tobytes()
+            pg.close()
+        with _native.Searcher(0) as s:
+            s.set_genome_array(genome, off)
+            s.set_library(lib)
+            s.set_pam("NGG")
+            s.set_param(_native.BC_PARAM_PATH, path)
+            s.set_param(_native.BC_PARAM_HIT_CAPACITY, 1000)
+            merged, per_rank = multi_gpu.search_and_gather(s, 2, dev)
+            got = _native.canonical_sort(multi_gpu.records_from_tensor(merged))
+            assert got.tobytes() == whole.tobytes()
+    finally:
+        dist.destroy_process_group()
+
+
 def test_targets_script_records_match_fixture(golden_dir, plasmids):
     """the targets.py-shaped records (circular overhang, direction-aware PAM, per-gene rows,
     origin-spanning gene) reproduce every plasmid row of the reference's CN-32-zmo.tsv."""

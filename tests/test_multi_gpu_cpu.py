@@ -68,3 +68,47 @@ def test_gather_hits_world_size_2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert int(open(tmp_path / "ok").read()) > 50
+
+
+def _worker_streamed(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        n_pieces = 3 if rank == 0 else 5               # ranks report different numbers of pieces
+        sizes = [int(x) for x in rng.integers(0, 700, n_pieces)]
+        if rank == 1:
+            sizes[2] = 0                               # an empty piece in the middle
+        pieces = [torch.from_numpy(rng.integers(0, 2**31 - 1, (sz, 4)).astype(np.int32)) for sz in sizes]
+        sg = multi_gpu.StreamedGather(torch.device("cpu"), capacity=64)   # small: forces growth on dst
+        for p in pieces:
+            assert sg.push(p) is False
+        empty = torch.empty((0, 4), dtype=torch.int32)
+        while not sg.push(empty, done=True):
+            pass
+        merged, per_rank = sg.finish()
+        mine = torch.cat(pieces)
+        totals = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(totals, torch.tensor([mine.shape[0]], dtype=torch.int64))
+        assert per_rank == [int(t.item()) for t in totals]
+        # rank 0 checks content: the multiset of records equals the union of all ranks' pieces
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine.numpy())
+        if rank == 0:
+            want = np.concatenate(gathered)
+            got = merged.numpy()
+            assert got.shape == want.shape
+            key = lambda a: a[np.lexsort(a.T[::-1])]
+            assert (key(got) == key(want)).all()
+            with open(os.path.join(tmpdir, "ok2"), "w") as h:
+                h.write(str(len(want)))
+        else:
+            assert merged is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_streamed_gather_world_size_2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_streamed, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert int(open(tmp_path / "ok2").read()) > 100
