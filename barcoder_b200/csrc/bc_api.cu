@@ -424,7 +424,7 @@ static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_o
         double join_cost = (c_sort + 20.0) * records + 0.42 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
         for (uint32_t path = 1; path <= 2; path++) {
             if (ctx->par_path && (uint32_t)ctx->par_path != path) continue;
-            if (path == 2 && !bc_join_supported(s.combo, s.n_combos, E)) continue;
+            if (path == 2 && s.n_combos == 0) continue;
             double cost = path == 1 ? probe_cost : join_cost;
             if (!found || cost < best_cost) {
                 found = true;

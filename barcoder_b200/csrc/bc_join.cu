@@ -34,23 +34,17 @@ struct BucketParams {
     ComboDesc combo[BC_MAX_COMBOS];
 };
 
-// Pass 1.  PASS 0 counts, PASS 1 scatters.  Windows touching a non-ACGT base or a contig end
-// are dropped here, so pass 2 never sees them.
-// Pass 1 variants: PASS 0 counts (RED), PASS 1 scatters straight to the final slot (one returning
-// atomic per record), PASS 2 scatters to a coarse partition (level 1 of the two-level scatter in
-// bc_kernels.h; level 2 is k_fine_scatter).  Measured on cfg 4, b=6 (2e9 records): count 9 ms;
-// direct scatter 70 ms (3.4x DRAM write amplification, but only one returning-atomic pass);
-// two-level 37 + 37 ms (clean writes, two returning-atomic passes at ~5.5e10/s each).  The direct
-// scatter is the default for windows; the library index uses the two-level form (28.7 -> 17.5 ms).
+// Pass 1.  PASS 0 counts (RED), PASS 1 scatters straight to the final slot (one returning atomic
+// and one isolated 16-byte store per record).  Windows touching a non-ACGT base or a contig end are
+// dropped here, so pass 2 never sees them.  PASS 1 is the fallback of the radix scatter below.
 // The grid is (x = genome chunks, y = combination) and CTAs are dispatched x-fastest, so the
 // persistent CTAs of ONE combination run at a time: its 4^key_nt write fronts (2 MB of sectors at
-// cfg 4) stay in L2.  A position-major variant (one thread = one window through all combinations,
-// 5-10 independent atomics in flight) was measured at 35-38 ms against 27.7 ms for this form.
-#define BC_WINDOWS_TWO_LEVEL 0
-
+// cfg 4) stay in L2.  A position-major variant of PASS 1 (one thread = one window through all
+// combinations, 5-10 independent atomics in flight) was measured at 35-38 ms against 27.7 ms for
+// this form; a two-level coarse/fine scatter with returning atomics in both levels at 37 + 37 ms
+// against 70 ms (cfg 4 at b=6).
 template <int PASS>
 __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketParams gp,
-                                                const __grid_constant__ CoarsePlan pl,
                                                 uint32_t* __restrict__ gdir_or_cursor, uint4* __restrict__ gwin) {
     const uint32_t lm = bc_lmask(gp.L);
     const uint32_t c = blockIdx.y;
@@ -66,11 +60,8 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
         if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
         if (PASS == 0) {
             atomicAdd(&gdir_or_cursor[slot], 1u);
-        } else if (PASS == 1) {
-            const uint32_t dst = atomicAdd(&gdir_or_cursor[slot], 1u);
-            gwin[dst] = make_uint4(pos, wh, wl, slot);
         } else {
-            const uint32_t dst = atomicAdd(&gdir_or_cursor[bc_coarse_of(pl, c, slot)], 1u);
+            const uint32_t dst = atomicAdd(&gdir_or_cursor[slot], 1u);
             gwin[dst] = make_uint4(pos, wh, wl, slot);
         }
     }
@@ -615,14 +606,11 @@ __global__ void __launch_bounds__(MV_THREADS, 3) k_verify_sparse(const __grid_co
 #undef MV_CANDIDATE
 
 // ------------------------------------------------------------------------------------------ host
-bool bc_join_supported(const ComboDesc*, uint32_t n_combos, uint64_t) { return n_combos > 0; }
-
 void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_gdir) cudaFree(ws.d_gdir);
     if (ws.d_gcursor) cudaFree(ws.d_gcursor);
     if (ws.d_gwin) cudaFree(ws.d_gwin);
     if (ws.d_gtmp) cudaFree(ws.d_gtmp);
-    if (ws.d_coarse_cursor) cudaFree(ws.d_coarse_cursor);
     if (ws.d_work) cudaFree(ws.d_work);
     if (ws.d_bin_cursor) cudaFree(ws.d_bin_cursor);
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
@@ -653,10 +641,10 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     bool radix_ok = true;
     for (uint32_t c = 0; c < p.n_combos; c++) radix_ok = radix_ok && p.combo[c].key_nt >= 4 && p.combo[c].key_nt <= 8;
     const uint64_t span0 = (uint64_t)p.pos_end - p.pos_begin;
-    const bool radix = !BC_WINDOWS_TWO_LEVEL && radix_ok &&
+    const bool radix = radix_ok &&
                        (p.window_sort == 2 ||
                         (p.window_sort == 0 && span0 * p.n_combos / ((dir_slots >> 8) + 1) >= 16ull * RB_CHUNK));
-    const uint32_t n_arrays = (BC_WINDOWS_TWO_LEVEL || radix) ? 2 : 1;  // record arrays (scratch + final)
+    const uint32_t n_arrays = radix ? 2 : 1;  // record arrays (scratch + final)
     const uint64_t span = (uint64_t)p.pos_end - p.pos_begin;
     uint64_t chunk = span ? span : 1;
     if (chunk * p.n_combos > ws.gwin_cap) {
@@ -676,7 +664,6 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         ws.d_gwin = ws.d_gtmp = nullptr;
         ws.gwin_cap = 0;
         JCK(cudaMalloc(&ws.d_gwin, (chunk * p.n_combos + 1) * sizeof(uint4)));
-        if (BC_WINDOWS_TWO_LEVEL) JCK(cudaMalloc(&ws.d_gtmp, (chunk * p.n_combos + 1) * sizeof(uint4)));
         ws.gwin_cap = chunk * p.n_combos;
     }
     if (radix && !ws.d_gtmp) JCK(cudaMalloc(&ws.d_gtmp, (ws.gwin_cap + 1) * sizeof(uint4)));
@@ -705,9 +692,6 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         ws.scan_tmp_cap = tmp_words;
     }
     if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, BC_SINK_SLICES * sizeof(uint32_t)));
-    if (!ws.d_coarse_cursor) JCK(cudaMalloc(&ws.d_coarse_cursor, ((size_t)BC_MAX_COMBOS << BC_COARSE_BITS) * 4 + 4));
-    CoarsePlan pl;
-    bc_make_coarse_plan(p.combo, p.n_combos, &pl);
     BucketParams gp;
     memset(&gp, 0, sizeof gp);
     gp.H = p.H; gp.Lo = p.Lo; gp.B = p.B;
@@ -731,17 +715,11 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         dim3 grid(gx, p.n_combos);
         JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
         JCK(cudaEventRecord(ws.ev_c, st));
-        k_bucket<0><<<grid, 256, 0, st>>>(gp, pl, ws.d_gdir, nullptr);
+        k_bucket<0><<<grid, 256, 0, st>>>(gp, ws.d_gdir, nullptr);
         JCK(cudaGetLastError());
         JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
         JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
-        if (BC_WINDOWS_TWO_LEVEL) {
-            JCK(bc_launch_coarse_init(pl, ws.d_gdir, ws.d_coarse_cursor, st));
-            k_bucket<2><<<grid, 256, 0, st>>>(gp, pl, ws.d_coarse_cursor, ws.d_gtmp);
-            JCK(cudaGetLastError());
-            JCK(bc_launch_fine_scatter(0, ws.d_gtmp, ws.d_gdir + (dir_slots - 1), ws.d_gcursor, ws.d_gwin, nullptr,
-                                       nullptr, sm_count, st));
-        } else if (radix) {
+        if (radix) {
             const uint32_t n_bins = (uint32_t)((dir_slots - 1) >> 8);
             k_bin_init<<<(n_bins + 255) / 256, 256, 0, st>>>(ws.d_gdir, ws.d_bin_cursor, n_bins);
             JCK(cudaGetLastError());
@@ -755,7 +733,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
             JCK(cudaGetLastError());
             bc_launch_counter += 2;
         } else {
-            k_bucket<1><<<grid, 256, 0, st>>>(gp, pl, ws.d_gcursor, ws.d_gwin);
+            k_bucket<1><<<grid, 256, 0, st>>>(gp, ws.d_gcursor, ws.d_gwin);
             JCK(cudaGetLastError());
         }
         JCK(cudaEventRecord(ws.ev_a, st));

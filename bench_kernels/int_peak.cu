@@ -1,6 +1,6 @@
 // int_peak.cu - measurement-only microbenchmarks (not part of the product ABI): the chip's
 // sustained POPC issue rate and the rate of the verification atom of k_join_verify
-// (2 LOP3 + POPC + min), used by bench.py as the integer-pipe roofline denominator.
+// (2 LOP3 + POPC + min3 folding), used by bench.py as the integer-pipe roofline denominator.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,11 +25,13 @@ __global__ void __launch_bounds__(256) k_popc_stream(uint32_t* out, uint32_t see
     if (acc == 0x12345678u) out[0] = acc;
 }
 
-// the verify atom: a library word pair (q) from shared memory broadcast against CHAINS resident
-// windows; every result feeds a compare so nothing can be hoisted
+// the verify atom of k_verify_dense: two library entries per 16-byte shared-memory broadcast
+// against CHAINS resident windows, 2 LOP3 + POPC per pair folded with integer min, one compare
+// per group; every result feeds the compare so nothing can be hoisted
 __global__ void __launch_bounds__(256) k_verify_atom(uint32_t* out, uint32_t seed, int k) {
-    __shared__ uint2 s_lib[256];
-    s_lib[threadIdx.x] = make_uint2(seed * (threadIdx.x + 3u), ~seed * (threadIdx.x + 7u));
+    __shared__ uint4 s_lib[256];
+    s_lib[threadIdx.x] = make_uint4(seed * (threadIdx.x + 3u), ~seed * (threadIdx.x + 7u),
+                                    seed * (threadIdx.x + 11u), ~seed * (threadIdx.x + 13u));
     __syncthreads();
     uint32_t gh[CHAINS], gl[CHAINS];
 #pragma unroll
@@ -38,13 +40,15 @@ __global__ void __launch_bounds__(256) k_verify_atom(uint32_t* out, uint32_t see
         gl[i] = gh[i] * 0x85ebca6bu;
     }
     uint32_t hits = 0;
-    for (int it = 0; it < ITERS; it++) {
-        const uint2 q = s_lib[it & 255];
+    for (int it = 0; it < ITERS / 2; it++) {
+        const uint4 q = s_lib[it & 255];
+        int best = 33;
 #pragma unroll
         for (int i = 0; i < CHAINS; i++) {
-            uint32_t m = (gh[i] ^ q.x) | (gl[i] ^ q.y);
-            if (__popc(m) <= k) hits += m;
+            best = min(best, __popc((gh[i] ^ q.x) | (gl[i] ^ q.y)));
+            best = min(best, __popc((gh[i] ^ q.z) | (gl[i] ^ q.w)));
         }
+        if (best <= k) hits += best + it;
     }
     if (hits == 77u) out[0] = hits;
 }
