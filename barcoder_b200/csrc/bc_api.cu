@@ -585,7 +585,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
                               (ctx->sink.host || ctx->sink.fn) ? &ctx->sink : nullptr));
         } else {
             CK(cudaEventRecord(ctx->ev2, ctx->stream));
-            CK(bc_launch_scan_probe(p, ctx->sm_count, ctx->stream));
+            CK(bc_launch_scan_probe(p, ctx->dir_slots * 4ull, ctx->sm_count, ctx->stream));
             CK(cudaEventRecord(ctx->ev3, ctx->stream));
             launches = 1;
         }
@@ -593,6 +593,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         unsigned long long counts[4] = {0, 0, 0, 0};
         CK(cudaMemcpyAsync(counts, ctx->d_count, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->stats.path != 2) bc_probe_release_l2();
         float a = 0, b2 = 0;
         CK(cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1));
         if (ctx->stats.path == 2) { b2 = ctx->join.ms_join_kernels; ms_bucket += ctx->join.ms_bucket_kernels; }

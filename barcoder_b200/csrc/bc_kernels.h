@@ -55,4 +55,8 @@ cudaError_t bc_launch_pack_library(const uint8_t* d_ascii, uint32_t n, uint32_t 
 cudaError_t bc_launch_index_build(const IndexParams& ip, uint32_t n_combos, uint32_t* d_dir, uint64_t dir_slots,
                                   uint32_t* d_cursor, uint32_t* d_scan_tmp, uint4* ent_tmp, uint32_t* coarse_cursor,
                                   uint2* ent_hl, uint32_t* ent_id, int sm_count, cudaStream_t st);
-cudaError_t bc_launch_scan_probe(const SearchParams& p, int sm_count, cudaStream_t st);
+#ifndef BC_PROBE_PIN_DIRECTORY
+#define BC_PROBE_PIN_DIRECTORY 1   // probe path: keep the seed directory in the persisting L2 set-aside
+#endif
+cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int sm_count, cudaStream_t st);
+void bc_probe_release_l2();
