@@ -246,6 +246,9 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS) k_window_place(const
 #ifndef MV_CHUNK_TILES
 #define MV_CHUNK_TILES 16   // warp-tiles per work chunk of the dense kernel
 #endif
+#ifndef MV_ALU_PAIRS
+#define MV_ALU_PAIRS 4      // of the MV_DENSE_ENTRIES x MV_ITEMS pairs of a group, how many are tested on the ALU pipe instead of POPC
+#endif
 #ifndef MV_STAGE
 #define MV_STAGE 64         // library entries per shared-memory stage of the dense kernel (x2 buffers per warp)
 #endif
@@ -384,6 +387,7 @@ static __device__ __noinline__ void mv_resolve_groups(const SearchParams& p, con
 // tiles dealt round-robin to the warps; a warp owns the slot-aligned tiles that START in its
 // chunk and finds them from the first record of the chunk (its slot is in the record) and the
 // record directory gdir, so no tile list has to be built.
+template <int K>
 __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense(const __grid_constant__ SearchParams p,
                                                                                  const uint4* __restrict__ gwin,
                                                                                  const uint32_t* __restrict__ gdir,
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
     const uint32_t n_rec = *n_rec_ptr;
     const uint32_t wtile = 32 * MV_ITEMS, chunk = wtile * MV_CHUNK_TILES;
     const uint32_t n_chunks = (n_rec + chunk - 1) / chunk;
-    const int k = (int)p.k;
+    const int k = K;  // == p.k (host dispatch)
     const uint2* __restrict__ ent = p.ent_hl;
     unsigned long long cand = 0;
     // a launch handles the chunks [frac_lo, frac_hi) / 65536 of the record array (streamed result delivery)
@@ -493,18 +497,29 @@ __global__ void __launch_bounds__(MV_THREADS, MV_DENSE_MINBLOCKS) k_verify_dense
                 for (;;) {
                     for (; g < ng && gn < 32; g++) {
                         int best_ = 33;
+                        uint32_t rest_ = 0xffffffffu;  // min over the ALU-tested pairs of (mismatch mask with its K lowest bits cleared)
 #pragma unroll
                         for (int j = 0; j < MV_DENSE_ENTRIES / 2; j++) {
                             const uint4 e2 = sb[g * (MV_DENSE_ENTRIES / 2) + j];
 #pragma unroll
                             for (int it = 0; it < MV_ITEMS; it++) {
                                 best_ = min(best_, __popc((wv[it].y ^ e2.x) | (wv[it].z ^ e2.y)));
-                                best_ = min(best_, __popc((wv[it].y ^ e2.z) | (wv[it].z ^ e2.w)));
+                                if ((MV_DENSE_ENTRIES / 2 - 1 - j) * MV_ITEMS + it < MV_ALU_PAIRS) {
+                                    // popc(m) <= K  <=>  m with its K lowest set bits cleared is 0: the same
+                                    // test on the ALU pipe, which has head-room while POPC saturates the XU pipe
+                                    uint32_t m = (wv[it].y ^ e2.z) | (wv[it].z ^ e2.w);
+#pragma unroll
+                                    for (int c = 0; c < K; c++) m &= m - 1u;
+                                    rest_ = min(rest_, m);
+                                } else {
+                                    best_ = min(best_, __popc((wv[it].y ^ e2.z) | (wv[it].z ^ e2.w)));
+                                }
                             }
                         }
-                        const uint32_t hit_ = __ballot_sync(0xffffffffu, best_ <= kl);
+                        const bool pass_ = best_ <= kl || (MV_ALU_PAIRS && kl >= 0 && rest_ == 0u);
+                        const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_);
                         if (hit_) {  // warp-uniform
-                            if (best_ <= kl)
+                            if (pass_)
                                 gq[gn + __popc(hit_ & lt_mask)] = make_uint2(first + lane, ebase + g * MV_DENSE_ENTRIES);
                             gn += __popc(hit_);
                         }
@@ -748,8 +763,13 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
             const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));
-            k_verify_dense<<<(uint32_t)sm_count * MV_DENSE_MINBLOCKS, MV_THREADS, 0, st>>>(
-                p, ws.d_gwin, ws.d_gdir, n_rec_ptr, ws.d_work, s, n_slices == 1 ? 0u : f_lo, f_hi);
+            const uint32_t dgrid = (uint32_t)sm_count * MV_DENSE_MINBLOCKS, lo = n_slices == 1 ? 0u : f_lo;
+            switch (p.k) {
+                case 0: k_verify_dense<0><<<dgrid, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir, n_rec_ptr, ws.d_work, s, lo, f_hi); break;
+                case 1: k_verify_dense<1><<<dgrid, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir, n_rec_ptr, ws.d_work, s, lo, f_hi); break;
+                case 2: k_verify_dense<2><<<dgrid, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir, n_rec_ptr, ws.d_work, s, lo, f_hi); break;
+                default: k_verify_dense<3><<<dgrid, MV_THREADS, 0, st>>>(p, ws.d_gwin, ws.d_gdir, n_rec_ptr, ws.d_work, s, lo, f_hi); break;
+            }
             JCK(cudaGetLastError());
             if (sink) {
                 JCK(cudaMemcpyAsync(sink->h_counts + s, p.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

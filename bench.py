@@ -430,7 +430,9 @@ def main():
                         "frac": rate / ipk["popc_per_s"], "frac_of_verify_atom": rate / ipk["verify_atom_per_s"],
                         "verify_atom_peak": ipk["verify_atom_per_s"] / 1e12, "candidates": cand,
                         "share_of_step": acc["ms_scan_kernel"] / max(ms_per_step, 1e-9),
-                        "peak_source": "bench_kernels/int_peak.cu measured in this run (POPC: 16/clk/SM)"}
+                        "peak_source": "bench_kernels/int_peak.cu measured in this run (POPC: 16/clk/SM)",
+                        "note": "peak = one POPC per pair; k_verify_dense tests 1 pair in 8 on the ALU pipe instead "
+                                "(clear-lowest-bit test), so the POPC pipe itself sees 7/8 of `achieved`"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
