@@ -407,21 +407,26 @@ static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_o
         // (bench_kernels/scatter_lab.cu for the scatter terms):
         //   probe path: a directory probe costs ~17 ps while the directories stay L2-resident and
         //               ~58 ps once they live in HBM; a candidate is an uncoalesced 8-byte read, ~3 ps;
-        //   join path : the window sort costs ~28 ps per (window, combination) record with <= 2^16
-        //               slots per combination and ~6 ps more per doubling beyond that (open write
-        //               fronts outgrow L2); verify costs ~20 ps per record plus ~0.42 ps per candidate;
-        //   both      : the library index costs ~40 ps per (entry, combination); directories are
+        //   join path : the window sort costs ~20 ps per (window, combination) record when the radix
+        //               scatter applies (keys of 4..8 nt), else ~28 ps with <= 2^16 slots per
+        //               combination and ~6 ps more per doubling beyond that (open write fronts
+        //               outgrow L2); verify costs ~0.25 ps per candidate plus ~3 ps per record in
+        //               well-filled slots (dense kernel) or ~20 ps per record otherwise;
+        //   both      : the library index costs ~32 ps per (entry, combination); directories are
         //               cleared, scanned and copied at ~5 ps per slot; fixed launch floor ~100 us.
         const double dir_bytes = 4.0 * (double)s.dir_slots;
         const double records = windows * s.n_combos;
         const double entries = (double)E * s.n_combos;
         const double cands = windows * s.cand_per_window;
-        const double common = 40.0 * entries + 5.0 * (double)s.dir_slots;
+        const double common = 32.0 * entries + 5.0 * (double)s.dir_slots;
         const double c_probe = dir_bytes < 100e6 ? 17.0 : 58.0;
-        double slots_per_combo = (double)s.dir_slots / s.n_combos, c_sort = 28.0;
-        while (slots_per_combo > 65536.0) { c_sort += 6.0; slots_per_combo *= 0.5; }
+        bool radix = true;
+        for (uint32_t c = 0; c < s.n_combos; c++) radix = radix && s.combo[c].key_nt >= 4 && s.combo[c].key_nt <= 8;
+        double slots_per_combo = (double)s.dir_slots / s.n_combos, c_sort = radix ? 20.0 : 28.0;
+        const double c_rec = windows / slots_per_combo >= 256.0 ? 3.0 : 20.0;  // windows per slot: dense or sparse verify
+        while (!radix && slots_per_combo > 65536.0) { c_sort += 6.0; slots_per_combo *= 0.5; }
         double probe_cost = c_probe * records + 3.0 * cands + common;
-        double join_cost = (c_sort + 20.0) * records + 0.42 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
+        double join_cost = (c_sort + c_rec) * records + 0.25 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
         for (uint32_t path = 1; path <= 2; path++) {
             if (ctx->par_path && (uint32_t)ctx->par_path != path) continue;
             if (path == 2 && s.n_combos == 0) continue;
