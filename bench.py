@@ -467,7 +467,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "guides*Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e.item() / e2e_steps, "host_phase_ms": e2e_phase_ms},
         "gpu_launches": int(launches),
-        "clocks": clocks, "roofline": roofline, "roofline_int": roofline_int,
+        "clocks": clocks, "roofline": dict(roofline, int_pipe_frac=(roofline_int["frac"] if roofline_int else None)),
+        "roofline_int": roofline_int,
         "roofline_best": ("roofline_int" if roofline_int and roofline_int["frac"] > roofline["frac"] else "roofline"),
         "cpu_baseline": cpu,
         "stage_ms": dict({k2: round(v, 4) for k2, v in acc.items()},
