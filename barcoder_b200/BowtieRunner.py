@@ -251,12 +251,16 @@ class BowtieRunner(Logger):
         P = len(pam)
         meta = hits["meta"]
         codes = (meta >> 16).astype(np.uint32)
-        letters = np.frombuffer(b"ACGT", dtype="S1")
-        chars = np.empty((len(hits), P), dtype="S1")
-        for i in range(P):
-            chars[:, i] = letters[(codes >> (2 * i)) & 3]
-        pam_str = np.array([b"".join(row).decode() for row in chars], dtype=object) if P else \
-            np.full(len(hits), "", dtype=object)
+        if P:
+            # at most 4^P distinct PAMs: decode each distinct code once, then index (one Python
+            # string per distinct PAM instead of one per hit)
+            uniq, inv = np.unique(codes & np.uint32((1 << (2 * P)) - 1), return_inverse=True)
+            table = np.empty(len(uniq), dtype=object)
+            for t, code in enumerate(uniq.tolist()):
+                table[t] = "".join("ACGT"[(code >> (2 * i)) & 3] for i in range(P))
+            pam_str = table[inv] if len(hits) else np.zeros(0, dtype=object)
+        else:
+            pam_str = np.full(len(hits), "", dtype=object)
         targeting = (meta & _native.META_PAM_OK) != 0
         lower = any(c != c.upper() for c in self._contigs) if not hasattr(self, "_has_lower") else self._has_lower
         self._has_lower = lower
