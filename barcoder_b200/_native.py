@@ -25,6 +25,7 @@ BC_PARAM_HIT_CAPACITY = 4
 BC_PARAM_SPACER_ID_BASE = 5
 BC_PARAM_SCAN_PART = 6
 BC_PARAM_WINDOW_SORT = 7
+BC_PARAM_JOIN_CHUNK = 8
 PATH_AUTO, PATH_PROBE, PATH_JOIN = 0, 1, 2
 
 META_PAM_OK = 1 << 3

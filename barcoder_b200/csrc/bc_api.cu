@@ -44,7 +44,7 @@ struct bc_ctx {
 
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
-    int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0;
+    int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0, par_join_chunk = 0;
 
     // index
     bool have_index = false;
@@ -328,6 +328,9 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
         case BC_PARAM_WINDOW_SORT:
             if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "window sort must be 0, 1 or 2");
             ctx->par_window_sort = value; return BC_OK;
+        case BC_PARAM_JOIN_CHUNK:
+            if (value < 0) return fail(ctx, BC_EINVAL, "join chunk must be >= 0");
+            ctx->par_join_chunk = value; return BC_OK;
         default: return fail(ctx, BC_EINVAL, "unknown parameter");
     }
 }
@@ -544,6 +547,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     memcpy(p->pam_sets, ctx->pam_sets, sizeof p->pam_sets);
     p->gate_first = ((ctx->pam_flags & BC_PAM_GATE) && ctx->P > 0) ? 1u : 0u;
     p->window_sort = (uint32_t)ctx->par_window_sort;
+    p->join_chunk = (uint32_t)(ctx->par_join_chunk > 0xffffffffll ? 0xffffffffll : ctx->par_join_chunk);
     p->hits = ctx->d_hits;
     p->count = ctx->d_count;
     p->cap = ctx->hit_cap;

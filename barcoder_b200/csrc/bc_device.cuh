@@ -57,6 +57,7 @@ struct SearchParams {
     uint32_t pam_sets[8];       // per PAM position: allowed set over {A=1,C=2,G=4,T=8}
     uint32_t gate_first;        // 1: evaluate the PAM gate before any index work
     uint32_t window_sort;       // bucket-join path: 0 auto, 1 direct scatter, 2 radix scatter (BC_PARAM_WINDOW_SORT)
+    uint32_t join_chunk;        // bucket-join path: max window positions per pass over the genome, 0 = as many as fit (BC_PARAM_JOIN_CHUNK)
     // output
     bc_hit* hits;
     unsigned long long* count;  // [0] hits, [1] candidates, [2] probes, [3] next tile of the probe kernel

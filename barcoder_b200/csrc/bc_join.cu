@@ -662,6 +662,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     const uint32_t n_arrays = radix ? 2 : 1;  // record arrays (scratch + final)
     const uint64_t span = (uint64_t)p.pos_end - p.pos_begin;
     uint64_t chunk = span ? span : 1;
+    if (p.join_chunk && chunk > p.join_chunk) chunk = p.join_chunk;  // forced small passes (tests of the multi-pass branch)
     if (chunk * p.n_combos > ws.gwin_cap) {
         size_t free_b = 0, total_b = 0;
         JCK(cudaMemGetInfo(&free_b, &total_b));

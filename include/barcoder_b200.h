@@ -72,6 +72,9 @@ typedef struct {
                                        context scans only its 1/world slice of window starts  */
 #define BC_PARAM_WINDOW_SORT 7       /* bucket-join path, genome-side sort: 0 auto, 1 direct scatter,
                                         2 two-pass shared-memory radix scatter                    */
+#define BC_PARAM_JOIN_CHUNK 8        /* bucket-join path: upper bound on the window positions sorted per
+                                        pass over the genome (0 = as many as the workspace holds); the
+                                        passes append to one hit buffer                              */
 
 typedef struct {
     uint64_t genome_bases;    /* G                                                   */

@@ -54,6 +54,8 @@ def lib():
             f = getattr(L, name)
             f.argtypes = sig
             f.restype = ctypes.c_int64
+        L.orc_search_seeded_b.argtypes = sig + [ctypes.c_int]
+        L.orc_search_seeded_b.restype = ctypes.c_int64
         L.orc_annotate_pam.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_void_p,
                                        ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_int,
                                        ctypes.c_uint]
@@ -77,15 +79,25 @@ def canonical_sort(hits):
 
 
 def search(contigs, spacers, k, pam="", direction="downstream", flags=0, threads=None,
-           mode="seeded", cap=None):
-    """Run the C oracle.  `spacers`: list[str] of equal length.  Returns canonical-sorted hits."""
+           mode="seeded", cap=None, blocks=0):
+    """Run the C oracle.  `spacers`: list[str] of equal length, or a uint8 array [n, L] of ASCII
+    rows.  Returns canonical-sorted hits.
+    `blocks` forces the number of pigeonhole blocks of the seeded strategy (0 = cost model)."""
     genome, off = concat_genome(contigs)
     n = len(spacers)
-    L = len(spacers[0]) if n else 0
-    assert all(len(s) == L for s in spacers), "oracle.search needs equal-length spacers"
-    sp = "".join(spacers).encode()
+    if isinstance(spacers, np.ndarray):   # uint8 ASCII rows [n, L]: no per-spacer Python strings
+        L = spacers.shape[1] if n else 0
+        sp = np.ascontiguousarray(spacers, dtype=np.uint8).tobytes()
+    else:
+        L = len(spacers[0]) if n else 0
+        assert all(len(s) == L for s in spacers), "oracle.search needs equal-length spacers"
+        sp = "".join(spacers).encode()
     threads = threads or os.cpu_count() or 1
-    f = lib().orc_search_seeded if mode == "seeded" else lib().orc_search_brute
+    if mode == "seeded":
+        def f(*a):
+            return lib().orc_search_seeded_b(*a, int(blocks))
+    else:
+        f = lib().orc_search_brute
     cap = cap or max(1 << 16, 64 * n)
     while True:
         out = np.zeros(cap, dtype=HIT_DTYPE)

@@ -30,7 +30,7 @@ def gpu_search(genome, off, lib, k, pam, iupac=False, gate=False, path=0, blocks
 def oracle_search(genome, off, lib, k, pam, iupac=False, gate=False):
     contigs = [bytes(genome[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
     flags = (oracle.PAM_FLAG_IUPAC if iupac else 0) | (oracle.PAM_FLAG_GATE if gate else 0)
-    return oracle.search(contigs, synth.rows_to_strings(lib), k, pam=pam, flags=flags)
+    return oracle.search(contigs, np.ascontiguousarray(lib), k, pam=pam, flags=flags)
 
 
 def planted_library(genome, n, L, k, seed, frac=0.01):
@@ -194,3 +194,94 @@ def test_genome_range_parts_equal_whole(path):
     assert sum(len(p) for p in parts) == len(whole)
     assert _native.canonical_sort(np.concatenate(parts)).tobytes() == whole.tobytes()
     assert all(len(p) > 0 for p in parts)
+
+
+# ------------------------------------------------------------- the configs at their stated sizes
+def _subsample_equal(gpu_hits, sub, ref):
+    got = gpu_hits[np.isin(gpu_hits["spacer_id"], sub)].copy()
+    got["spacer_id"] = np.searchsorted(sub, got["spacer_id"]).astype(np.uint32)
+    got = _native.canonical_sort(got)
+    assert len(got) == len(ref), (len(got), len(ref))
+    assert got.tobytes() == ref.tobytes()
+
+
+def test_cfg4_full_size_bench_workload():
+    """cfg 4 exactly as bench.py times it (BASELINE.json configs[3]): 10^7 distinct 20-mers (1 % planted)
+    x 100 Mbp, k<=3, NGG, scheme chosen by the cost model.  Checked against (a) the oracle on a
+    2,500-spacer subsample that contains planted spacers, bit-exact; (b) the closed-form expected
+    number of random hits 2*G*n*P[Binomial(20, 3/4) <= 3] plus the planted ones."""
+    from math import comb
+    G, n, L, k = 100_000_000, 10_000_000, 20, 3
+    genome, off = synth.random_genome(G, seed=4)
+    lib = synth.random_library(n, L, seed=40)
+    planted = synth.plant(lib, genome, 0.01, k, seed=1040)
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        nh = s.search(k)
+        st = s.stats()
+        hits = s.hits()
+    assert st["path"] == 2
+    p_le_k = sum(comb(L, j) * 0.75 ** j * 0.25 ** (L - j) for j in range(k + 1))
+    expect = 2.0 * (G - L + 1) * n * p_le_k + len(planted)
+    assert abs(nh - expect) < 6 * expect ** 0.5 + 0.002 * expect, (nh, expect)
+    # every planted spacer is found at least once
+    found = np.zeros(n, dtype=bool)
+    found[hits["spacer_id"]] = True
+    assert found[planted].all()
+    rng = synth.rng_for(7)
+    sub = np.unique(np.concatenate([planted[:500], rng.choice(n, size=2000, replace=False)]))
+    ref = oracle_search(genome, off, lib[sub], k, "NGG")
+    _subsample_equal(hits, sub, ref)
+
+
+def test_cfg4_full_size_forced_multi_pass_join():
+    """Same job with the genome forced into 3 join passes (BC_PARAM_JOIN_CHUNK) and a hit sink that
+    receives the records across the passes: identical record set."""
+    G, n, L, k = 100_000_000, 2_000_000, 20, 3
+    genome, off = synth.random_genome(G, seed=4)
+    lib = synth.random_library(n, L, seed=44)
+    synth.plant(lib, genome, 0.01, k, seed=1044)
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        s.set_param(_native.BC_PARAM_PATH, 2)
+        s.search(k)
+        whole = _native.canonical_sort(s.hits())
+        s.set_param(_native.BC_PARAM_JOIN_CHUNK, 37_000_001)
+        sink = np.zeros(len(whole) + 16, dtype=_native.HIT_DTYPE)
+        s.set_hit_sink(sink.ctypes.data, len(sink))
+        nh = s.search(k)
+        assert nh == len(whole)
+        assert _native.canonical_sort(sink[:nh].copy()).tobytes() == whole.tobytes()
+        assert _native.canonical_sort(s.hits()).tobytes() == whole.tobytes()
+
+
+def test_cfg5_full_size():
+    """cfg 5 at its stated size: 10^6 32-mers (1 % planted) x 3 Gbp in 24 contigs with N runs, k<=2,
+    NNGRRT with IUPAC expansion.  Oracle on a subsample containing planted spacers, bit-exact; every
+    planted spacer recovered at its planted site."""
+    genome, off = synth.random_genome(3_000_000_000, seed=5, n_contigs=24, n_fraction=0.001)
+    lib, idx, pos, flip = planted_library(genome, 1_000_000, 32, 2, seed=50)
+    gpu, st = gpu_search(genome, off, lib, 2, "NNGRRT", iupac=True)
+    assert_planted_found(gpu, idx, pos, flip, off)
+    sub = np.unique(np.concatenate([idx[:500], np.arange(0, 2000)]))
+    ref = oracle_search(genome, off, lib[sub], 2, "NNGRRT", iupac=True)
+    _subsample_equal(gpu, sub, ref)
+    assert ((gpu["meta"] & 8) != 0).sum() > 0
+
+
+def test_join_dense_path_many_stages_and_tiles():
+    """Dense verify with >= 3 shared-memory stages per bucket (> 128 entries) and >= 3 warp-tiles per
+    slot (> 384 windows) on purpose: 6-nt keys (b=2 of L=12 at k=1), 6*10^5 entries, 3*10^6 windows."""
+    genome, off = synth.random_genome(3_000_000, seed=71, n_contigs=3, n_fraction=0.001)
+    lib = synth.random_library(300_000, 12, seed=72)
+    synth.plant(lib, genome, 0.05, 1, seed=73)
+    ref = oracle_search(genome, off, lib, 1, "NGG")
+    gpu, st = gpu_search(genome, off, lib, 1, "NGG", path=2, blocks=2)
+    assert st["path"] == 2 and st["blocks"] == 2
+    # 4^6 slots per combination: ~146 entries (3 stages of 64) and ~732 windows (6 tiles of 128) per slot
+    assert 2 * len(lib) / 4096 > 128 and len(genome) / 4096 > 384
+    assert gpu.tobytes() == ref.tobytes()

@@ -117,3 +117,22 @@ def test_pam_annotation_matches_string_rules():
         gated = oracle.search(contigs, spacers, 1, pam="NGG", direction=direction, flags=oracle.PAM_FLAG_GATE)
         keep = hits[((hits["meta"] & oracle.META_PAM_OK) != 0) | ((hits["meta"] & oracle.META_PAM_AMB) != 0)]
         assert np.array_equal(gated, keep)
+
+
+@pytest.mark.parametrize("L,k", [(20, 3), (20, 2), (32, 2), (12, 1), (9, 3)])
+def test_seeded_every_block_count_equals_brute(L, k):
+    """The seeded strategy must give the exhaustive answer under every seed scheme it can choose
+    (b = k+1 .. k+4 blocks), including spacers with non-ACGT characters and N runs in the genome."""
+    genome, off = synth.random_genome(6000, seed=L + 3 * k, n_contigs=4, n_fraction=0.02, n_run=6)
+    lib = synth.random_library(80, L, seed=15)
+    synth.plant(lib, genome, 0.7, k, seed=16)
+    lib[2, 0] = ord("N")
+    lib[7, L - 1] = ord("n")
+    lib[9, :] = ord("N")
+    contigs = [bytes(genome[int(off[i]):int(off[i + 1])]).decode() for i in range(4)]
+    spacers = synth.rows_to_strings(lib)
+    want = oracle.search(contigs, spacers, k, mode="brute", threads=4)
+    assert len(want) > 0
+    for b in range(k + 1, min(k + 4, 8, L) + 1):
+        got = oracle.search(contigs, spacers, k, mode="seeded", threads=3, blocks=b)
+        assert np.array_equal(want, got), b
