@@ -26,7 +26,8 @@ BC_PARAM_SPACER_ID_BASE = 5
 BC_PARAM_SCAN_PART = 6
 BC_PARAM_WINDOW_SORT = 7
 BC_PARAM_JOIN_CHUNK = 8
-PATH_AUTO, PATH_PROBE, PATH_JOIN = 0, 1, 2
+BC_PARAM_KEY_NT = 9
+PATH_AUTO, PATH_PROBE, PATH_JOIN, PATH_CJOIN = 0, 1, 2, 3
 
 META_PAM_OK = 1 << 3
 META_PAM_FULL = 1 << 4
@@ -58,7 +59,7 @@ class BcStats(ctypes.Structure):
         ("ms_pack_genome", ctypes.c_float), ("ms_pack_library", ctypes.c_float),
         ("ms_build_index", ctypes.c_float), ("ms_search", ctypes.c_float),
         ("ms_scan_kernel", ctypes.c_float), ("ms_genome_bucket", ctypes.c_float),
-        ("index_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 6),
+        ("index_launches", ctypes.c_uint32), ("key_nt", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 5),
     ]
 
     def as_dict(self):

@@ -44,12 +44,12 @@ struct bc_ctx {
 
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
-    int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0, par_join_chunk = 0;
+    int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0, par_join_chunk = 0, par_key_nt = 0;
 
     // index
     bool have_index = false;
     int index_k = -1;
-    uint32_t b = 0, n_combos = 0;
+    uint32_t b = 0, n_combos = 0, n_bins = 0;
     uint32_t block_mask[BC_MAX_BLOCKS] = {0};
     ComboDesc combo[BC_MAX_COMBOS];
     uint64_t dir_slots = 0;
@@ -315,7 +315,7 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
     switch (key) {
         case BC_PARAM_BLOCKS: ctx->par_blocks = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_PATH:
-            if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "path must be 0, 1 or 2");
+            if (value < 0 || value > 3) return fail(ctx, BC_EINVAL, "path must be 0, 1, 2 or 3");
             ctx->par_path = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_COUNT_CANDIDATES: ctx->par_count = value; return BC_OK;
         case BC_PARAM_HIT_CAPACITY: ctx->par_hit_cap = value; return BC_OK;
@@ -328,6 +328,9 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
         case BC_PARAM_WINDOW_SORT:
             if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "window sort must be 0, 1 or 2");
             ctx->par_window_sort = value; return BC_OK;
+        case BC_PARAM_KEY_NT:
+            if (value < 0 || value > BC_KEY_MAX_NT) return fail(ctx, BC_EINVAL, "key length must be 0..12");
+            ctx->par_key_nt = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_JOIN_CHUNK:
             if (value < 0) return fail(ctx, BC_EINVAL, "join chunk must be >= 0");
             ctx->par_join_chunk = value; return BC_OK;
@@ -336,22 +339,96 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
 }
 
 // ----------------------------------------------------------------------------------- seed scheme
-// Generalised pigeonhole: split the L query positions into b blocks.  An alignment with <= k
-// mismatches leaves >= b-k blocks exact, so indexing every (b-k)-subset of blocks ("seed
-// combination") finds every alignment.  b = k+1 is the classic k+1-seed scheme; larger b means
-// more directory look-ups per window but geometrically fewer candidates.
+// A seed scheme is a family of position masks (one per seed combination) such that every set of
+// k mismatch positions is avoided by at least one mask; the library is indexed, and the genome
+// windows are probed or sorted, under each mask.  Two families are offered:
+//   block schemes   generalised pigeonhole: the L query positions are split into b blocks and
+//                   every (b-k)-subset of blocks is a mask (b = k+1 is the classic k+1-seed filter);
+//   designs         covering designs found offline (tools/make_designs.py -> bc_designs.inc): fewer
+//                   masks for the same key length (L=20, k=3: 15 masks of 10 nt against b=6's 20
+//                   masks of 9..11 nt; 12 masks of 9 nt), so fewer records to sort and fewer pairs.
+struct BcDesignRow {
+    uint8_t L, k, key_nt, n_masks;
+    uint16_t first;
+};
+#include "bc_designs.inc"
+
 struct Scheme {
-    uint32_t b, n_combos;
+    uint32_t b, n_combos, key_nt_min, key_nt_max;
     uint32_t block_mask[BC_MAX_BLOCKS];
     ComboDesc combo[BC_MAX_COMBOS];
     uint64_t dir_slots;
     double cand_per_window;  // expected candidates per genome window on uniform data
+    bool compact_ok;         // every combination fits the 8-byte record of the compact join path
+    uint32_t n_bins;         // compact join path: pass-A bins over all combinations
 };
 
-static bool make_scheme(uint32_t L, uint32_t k, uint32_t b, uint32_t key_cap_nt, uint64_t n_entries, Scheme* s) {
+// pieces (runs) of the key mask and of its complement, directory offsets, compact-path bit split
+static bool finish_scheme(Scheme* s, uint32_t L, uint64_t n_entries) {
+    uint64_t slots = 0;
+    double cand = 0;
+    uint32_t bins = 0;
+    s->compact_ok = true;
+    s->key_nt_min = 99;
+    s->key_nt_max = 0;
+    const uint32_t lm = L >= 32 ? 0xffffffffu : ((1u << L) - 1u);
+    for (uint32_t c = 0; c < s->n_combos; c++) {
+        ComboDesc& cd = s->combo[c];
+        const uint32_t km = cd.key_mask & lm;
+        cd.key_mask = km;
+        uint32_t np = 0, nr = 0, knt = 0;
+        for (uint32_t pos = 0; pos < L;) {
+            const bool in_key = (km >> pos) & 1u;
+            uint32_t end = pos;
+            while (end < L && (((km >> end) & 1u) != 0) == in_key) end++;
+            if (in_key) {
+                if (np == BC_MAX_PIECES) return false;
+                cd.start[np] = (uint8_t)pos;
+                cd.len[np] = (uint8_t)(end - pos);
+                knt += end - pos;
+                np++;
+            } else {
+                if (nr == BC_MAX_PIECES + 1) return false;
+                cd.rstart[nr] = (uint8_t)pos;
+                cd.rlen[nr] = (uint8_t)(end - pos);
+                nr++;
+            }
+            pos = end;
+        }
+        if (knt == 0 || knt > BC_KEY_MAX_NT) return false;
+        cd.n_pieces = (uint8_t)np;
+        cd.key_nt = (uint8_t)knt;
+        cd.n_rem = (uint8_t)nr;
+        cd.rem_nt = (uint8_t)(L - knt);
+        if (knt < s->key_nt_min) s->key_nt_min = knt;
+        if (knt > s->key_nt_max) s->key_nt_max = knt;
+        if (slots >= (1ull << 32)) return false;
+        cd.dir_off = (uint32_t)slots;
+        slots += 1ull << (2 * knt);
+        cand += (double)n_entries / (double)(1ull << (2 * knt));
+        // compact join path: record = {dev position, x}; x = low key bits | rem planes (2 * rem_nt bits).
+        // The key's top bits select the pass-A bin (<= 1024 bins per combination), the low bits the
+        // sub-slot inside the bin (<= 4096); both passes like a balanced split.
+        const uint32_t kb = 2 * knt, rem2 = 2 * (L - knt);
+        uint32_t top = (kb + 1) / 2;
+        if (kb <= 10) top = kb;
+        while (top < kb && top < 10 && (kb - top) + rem2 > 32) top++;
+        if (top > 10) top = 10;
+        const uint32_t low = kb - top;
+        if (low > 12 || low + rem2 > 32 || L - knt > 16) s->compact_ok = false;
+        cd.top_bits = (uint8_t)top;
+        cd.bin_off = bins;
+        bins += 1u << top;
+    }
+    s->n_bins = bins;
+    s->dir_slots = slots + 1;  // +1: end sentinel of the last bucket
+    s->cand_per_window = cand;
+    return slots + 1 < (1ull << 32);
+}
+
+static bool make_block_scheme(uint32_t L, uint32_t k, uint32_t b, uint32_t key_cap_nt, uint64_t n_entries, Scheme* s) {
     if (b < k + 1 || b > BC_MAX_BLOCKS || b > L) return false;
     uint32_t pick = b - k;
-    if (pick > BC_MAX_PIECES) return false;
     memset(s, 0, sizeof *s);
     s->b = b;
     uint32_t bstart[BC_MAX_BLOCKS + 1];
@@ -360,80 +437,85 @@ static bool make_scheme(uint32_t L, uint32_t k, uint32_t b, uint32_t key_cap_nt,
         uint32_t len = bstart[j + 1] - bstart[j];
         s->block_mask[j] = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << bstart[j];
     }
-    uint64_t slots = 0;
-    double cand = 0;
     uint32_t nc = 0;
     for (uint32_t mask = 0; mask < (1u << b); mask++) {  // ascending mask = deterministic combo order
         if ((uint32_t)__builtin_popcount(mask) != pick) continue;
         if (nc == BC_MAX_COMBOS) return false;
         ComboDesc& cd = s->combo[nc];
         cd.blocks_mask = mask;
-        uint32_t budget = key_cap_nt, np = 0, knt = 0;
-        for (uint32_t j = 0; j < b && budget; j++) {
+        uint32_t budget = key_cap_nt;
+        for (uint32_t j = 0; j < b && budget; j++) {  // the key = the first key_cap_nt bases of the chosen blocks
             if (!(mask >> j & 1u)) continue;
             uint32_t len = bstart[j + 1] - bstart[j];
             if (len > budget) len = budget;
-            cd.start[np] = (uint8_t)bstart[j];
-            cd.len[np] = (uint8_t)len;
-            cd.key_mask |= ((1u << len) - 1u) << bstart[j];
+            cd.key_mask |= (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << bstart[j];
             budget -= len;
-            knt += len;
-            np++;
         }
-        cd.n_pieces = (uint8_t)np;
-        cd.key_nt = (uint8_t)knt;
-        if (slots >= (1ull << 32)) return false;
-        cd.dir_off = (uint32_t)slots;
-        slots += 1ull << (2 * knt);
-        cand += (double)n_entries / (double)(1ull << (2 * knt));
         nc++;
     }
     s->n_combos = nc;
-    s->dir_slots = slots + 1;  // +1: end sentinel of the last bucket
-    s->cand_per_window = cand;
-    return slots + 1 < (1ull << 32);
+    return finish_scheme(s, L, n_entries);
+}
+
+static bool make_design_scheme(uint32_t L, const BcDesignRow& row, uint64_t n_entries, Scheme* s) {
+    if (row.n_masks > BC_MAX_COMBOS) return false;
+    memset(s, 0, sizeof *s);
+    s->b = 0;
+    s->n_combos = row.n_masks;
+    for (uint32_t c = 0; c < row.n_masks; c++) s->combo[c].key_mask = bc_design_masks[row.first + c];
+    return finish_scheme(s, L, n_entries);
+}
+
+// Cost model in picoseconds of B200 time per unit, fitted to measurements (DESIGN.md section 4;
+// bench_kernels/scatter_lab.cu and sort_lab.cu for the sort terms):
+//   probe path   : a directory probe costs ~17 ps while the directories stay L2-resident and ~58 ps
+//                  once they live in HBM; a candidate is an uncoalesced 8-byte read, ~3 ps;
+//   join path    : 16-byte window records.  The sort costs ~20 ps per (window, combination) record
+//                  when the radix scatter applies (keys of 4..8 nt), else ~28 ps with <= 2^16 slots
+//                  per combination and ~6 ps more per doubling beyond that; verify ~0.25 ps per
+//                  candidate plus ~3 ps per record in well-filled slots or ~20 ps per record otherwise;
+//   compact join : 8-byte window records (L <= 20 or so), two shared-memory radix passes for keys up
+//                  to 11 nt: ~5.3 ps (count) + ~4 ps (pass A) + ~8 ps (pass B) per record, verify as above;
+//   all          : the library index costs ~32 ps per (entry, combination); directories are cleared,
+//                  scanned and copied at ~5 ps per slot; fixed launch floor ~100 us.
+static double scheme_cost(const bc_ctx* ctx, const Scheme& s, uint32_t path) {
+    const uint64_t E = 2ull * ctx->n;
+    const double windows = (double)(ctx->G ? ctx->G : 1);
+    const double dir_bytes = 4.0 * (double)s.dir_slots;
+    const double records = windows * s.n_combos;
+    const double entries = (double)E * s.n_combos;
+    const double cands = windows * s.cand_per_window;
+    const double common = 32.0 * entries + 5.0 * (double)s.dir_slots;
+    double slots_per_combo = (double)s.dir_slots / s.n_combos;
+    const double c_rec = windows / slots_per_combo >= 64.0 ? 3.0 : 20.0;  // windows per slot: dense or sparse verify
+    if (path == 1) {
+        const double c_probe = dir_bytes < 100e6 ? 17.0 : 58.0;
+        return c_probe * records + 3.0 * cands + common;
+    }
+    if (path == 2) {
+        bool radix = true;
+        for (uint32_t c = 0; c < s.n_combos; c++) radix = radix && s.combo[c].key_nt >= 4 && s.combo[c].key_nt <= 8;
+        double c_sort = radix ? 20.0 : 28.0;
+        while (!radix && slots_per_combo > 65536.0) { c_sort += 6.0; slots_per_combo *= 0.5; }
+        return (c_sort + c_rec) * records + 0.25 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
+    }
+    // compact join; small genomes do not fill the chunks of the radix passes
+    const double c_sort = s.key_nt_max <= 5 ? 10.0 : 17.5;
+    return (c_sort + c_rec) * records + 0.25 * cands + common + 5.0 * (double)s.dir_slots + 1.2e8;
 }
 
 static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_out) {
     const uint64_t E = 2ull * ctx->n;
     uint32_t cap = 4;
     while (cap < BC_KEY_MAX_NT && (1ull << (2 * cap)) < 16 * (E ? E : 1)) cap++;
-    const double windows = (double)(ctx->G ? ctx->G : 1);
     double best_cost = 0;
     bool found = false;
     uint32_t best_path = 1;
-    for (uint32_t b = k + 1; b <= k + 4 && b <= BC_MAX_BLOCKS; b++) {
-        if (ctx->par_blocks && (uint32_t)ctx->par_blocks != b) continue;
-        Scheme s;
-        if (!make_scheme(ctx->L, k, b, cap, E, &s)) continue;
-        // Cost model in picoseconds of B200 time per unit, fitted to measurements on cfg 3/4/5
-        // (bench_kernels/scatter_lab.cu for the scatter terms):
-        //   probe path: a directory probe costs ~17 ps while the directories stay L2-resident and
-        //               ~58 ps once they live in HBM; a candidate is an uncoalesced 8-byte read, ~3 ps;
-        //   join path : the window sort costs ~20 ps per (window, combination) record when the radix
-        //               scatter applies (keys of 4..8 nt), else ~28 ps with <= 2^16 slots per
-        //               combination and ~6 ps more per doubling beyond that (open write fronts
-        //               outgrow L2); verify costs ~0.25 ps per candidate plus ~3 ps per record in
-        //               well-filled slots (dense kernel) or ~20 ps per record otherwise;
-        //   both      : the library index costs ~32 ps per (entry, combination); directories are
-        //               cleared, scanned and copied at ~5 ps per slot; fixed launch floor ~100 us.
-        const double dir_bytes = 4.0 * (double)s.dir_slots;
-        const double records = windows * s.n_combos;
-        const double entries = (double)E * s.n_combos;
-        const double cands = windows * s.cand_per_window;
-        const double common = 32.0 * entries + 5.0 * (double)s.dir_slots;
-        const double c_probe = dir_bytes < 100e6 ? 17.0 : 58.0;
-        bool radix = true;
-        for (uint32_t c = 0; c < s.n_combos; c++) radix = radix && s.combo[c].key_nt >= 4 && s.combo[c].key_nt <= 8;
-        double slots_per_combo = (double)s.dir_slots / s.n_combos, c_sort = radix ? 20.0 : 28.0;
-        const double c_rec = windows / slots_per_combo >= 256.0 ? 3.0 : 20.0;  // windows per slot: dense or sparse verify
-        while (!radix && slots_per_combo > 65536.0) { c_sort += 6.0; slots_per_combo *= 0.5; }
-        double probe_cost = c_probe * records + 3.0 * cands + common;
-        double join_cost = (c_sort + c_rec) * records + 0.25 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
-        for (uint32_t path = 1; path <= 2; path++) {
+    auto consider = [&](const Scheme& s) {
+        for (uint32_t path = 1; path <= 3; path++) {
             if (ctx->par_path && (uint32_t)ctx->par_path != path) continue;
-            if (path == 2 && s.n_combos == 0) continue;
-            double cost = path == 1 ? probe_cost : join_cost;
+            if (path == 3 && !s.compact_ok) continue;
+            const double cost = scheme_cost(ctx, s, path);
             if (!found || cost < best_cost) {
                 found = true;
                 best_cost = cost;
@@ -441,8 +523,23 @@ static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_o
                 best_path = path;
             }
         }
+    };
+    Scheme s;
+    if (!ctx->par_key_nt) {
+        for (uint32_t b = k + 1; b <= k + 4 && b <= BC_MAX_BLOCKS; b++) {
+            if (ctx->par_blocks && (uint32_t)ctx->par_blocks != b) continue;
+            if (make_block_scheme(ctx->L, k, b, cap, E, &s)) consider(s);
+        }
     }
-    if (!found) return fail(ctx, BC_EINVAL, "no feasible seed scheme for this (L, k, blocks, path)");
+    if (!ctx->par_blocks) {
+        for (size_t r = 0; r < sizeof bc_design_rows / sizeof bc_design_rows[0]; r++) {
+            const BcDesignRow& row = bc_design_rows[r];
+            if (row.L != ctx->L || row.k != k) continue;
+            if (ctx->par_key_nt ? (uint32_t)ctx->par_key_nt != row.key_nt : row.key_nt > cap) continue;
+            if (make_design_scheme(ctx->L, row, E, &s)) consider(s);
+        }
+    }
+    if (!found) return fail(ctx, BC_EINVAL, "no feasible seed scheme for this (L, k, blocks / key length, path)");
     *path_out = best_path;
     return BC_OK;
 }
@@ -472,9 +569,11 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     memcpy(ctx->block_mask, s.block_mask, sizeof s.block_mask);
     memcpy(ctx->combo, s.combo, sizeof s.combo);
     ctx->dir_slots = s.dir_slots;
+    ctx->n_bins = s.n_bins;
     ctx->stats.blocks = s.b;
     ctx->stats.combos = s.n_combos;
     ctx->stats.path = path;
+    ctx->stats.key_nt = s.key_nt_max;
 
     const uint64_t E = 2ull * ctx->n;
     const uint64_t ent_needed = E * s.n_combos;
@@ -506,6 +605,7 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     ip.n_entries = (uint32_t)E;
     ip.L = ctx->L;
     ip.lib_has_n = ctx->lib_has_n;
+    ip.compact = path == 3 ? 1u : 0u;  // compact join: the index stores the non-key (rem) planes of every entry
     memcpy(ip.combo, ctx->combo, sizeof ip.combo);
     const uint32_t launches0 = bc_launch_counter;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -526,6 +626,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->H = ctx->d_H; p->Lo = ctx->d_L; p->B = ctx->d_B;
     p->start_dev = ctx->d_start_dev;
     p->n_pos = ctx->n_pos;
+    p->n_words = ctx->n_words;
     p->pos_begin = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)ctx->par_scan_rank / (uint64_t)ctx->par_scan_world);
     p->pos_end = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)(ctx->par_scan_rank + 1) / (uint64_t)ctx->par_scan_world);
     p->n_contigs = ctx->n_contigs;
@@ -592,6 +693,9 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         if (ctx->stats.path == 2) {
             CK(bc_join_search(ctx->join, p, ctx->dir_slots, ctx->sm_count, ctx->stream, &launches,
                               (ctx->sink.host || ctx->sink.fn) ? &ctx->sink : nullptr));
+        } else if (ctx->stats.path == 3) {
+            CK(bc_cjoin_search(ctx->join, p, ctx->dir_slots, ctx->n_bins, ctx->sm_count, ctx->stream, &launches,
+                               (ctx->sink.host || ctx->sink.fn) ? &ctx->sink : nullptr));
         } else {
             CK(cudaEventRecord(ctx->ev2, ctx->stream));
             CK(bc_launch_scan_probe(p, ctx->dir_slots * 4ull, ctx->sm_count, ctx->stream));
@@ -602,10 +706,10 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         unsigned long long counts[4] = {0, 0, 0, 0};
         CK(cudaMemcpyAsync(counts, ctx->d_count, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->stats.path != 2) bc_probe_release_l2();
+        if (ctx->stats.path == 1) bc_probe_release_l2();
         float a = 0, b2 = 0;
         CK(cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1));
-        if (ctx->stats.path == 2) { b2 = ctx->join.ms_join_kernels; ms_bucket += ctx->join.ms_bucket_kernels; }
+        if (ctx->stats.path >= 2) { b2 = ctx->join.ms_join_kernels; ms_bucket += ctx->join.ms_bucket_kernels; }
         else CK(cudaEventElapsedTime(&b2, ctx->ev2, ctx->ev3));
         ms_total += a;
         ms_scan += b2;

@@ -1,0 +1,756 @@
+// bc_cjoin.cu - K3-cjoin: the bucket join of bc_join.cu with 8-byte window records, for spacers
+// short enough that a record {dev position, x} holds everything the join needs (L <= ~20: CRISPR
+// guides).  Replaces bowtie align (BowtieRunner.py:104-141) for dense libraries (cfg 3/4).
+//
+// Why a second form: at cfg 4 the step is the sort of ~10^9 (window, combination) records plus the
+// all-pairs verification inside every slot.  Longer keys cut the pairs geometrically (9 nt: 3.6x
+// fewer than 8 nt, 10 nt: 11x) but only pay if the sort stays cheap, and the sort is HBM traffic:
+//   * a record carries only what is NOT implied by its place: the low key bits (until pass B has
+//     used them) and the non-key ("rem") bit planes of the window, Rh | Rl << rem_nt - the key
+//     bits are the slot.  8 bytes instead of 16 through every pass and into the verify kernel;
+//   * the library index stores the same rem planes per entry, so verification is still
+//     2 LOP3 + 1 POPC per pair and never reassembles the window;
+//   * two shared-memory radix passes handle keys up to 11 nt (22 bits = up to 10 top bits in pass
+//     A, up to 12 low bits in pass B), with 8192-record chunks so runs stay >= 64 bytes
+//     (bench_kernels/sort_lab.cu: direct 8-byte scatters cost 25 ps per record, staged runs 3-5 ps).
+//
+//   k_ccount      RED histogram of (window, combination) per directory slot         -> gdir (scan)
+//   k_cbin        pass A: windows -> records grouped by bin (top key bits), runs     -> tmp
+//   k_cplace      pass B: bin regions -> final slots (low key bits)                  -> gwin
+//   k_cverify<K>  slot-aligned warp-tiles of <= 128 windows against the slot's library bucket
+#include "bc_join.h"
+
+#include <string.h>
+
+#include "bc_kernels.h"
+
+struct CBucketParams {
+    const uint32_t* H;
+    const uint32_t* Lo;
+    const uint32_t* B;
+    const uint32_t* lib_dir;      // library directory (to skip windows whose bucket is empty)
+    uint32_t pos_begin, pos_end;  // dev positions handled by this pass over the genome
+    uint32_t n_words;             // words per plane
+    uint32_t L, n_combos, prune, gate_first;
+    uint32_t P, pam_dir, pam_sets[8];
+    ComboDesc combo[BC_MAX_COMBOS];
+};
+
+#define CJ_THREADS 512
+#define CJ_ITEMS 16
+#define CJ_CHUNK (CJ_THREADS * CJ_ITEMS)  // 8192 records per shared-memory sort
+#define CJ_MAX_BINS 1024                  // pass-A bins per combination (top_bits <= 10)
+#define CJ_MAX_SUB 4096                   // pass-B sub-slots per bin (low key bits <= 12)
+
+// ------------------------------------------------------------------------------------- count
+// One RED per (window, combination).  Grid (x = genome chunks, y = combination): the CTAs of one
+// combination run together, so its directory stays in L2.
+__global__ void __launch_bounds__(256) k_ccount(const __grid_constant__ CBucketParams gp, uint32_t* __restrict__ gdir) {
+    const uint32_t lm = bc_lmask(gp.L);
+    const ComboDesc& cd = gp.combo[blockIdx.y];
+    PamGate gate;
+    bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
+    for (uint32_t pos = gp.pos_begin + blockIdx.x * blockDim.x + threadIdx.x; pos < gp.pos_end;
+         pos += gridDim.x * blockDim.x) {
+        if (bc_window(gp.B, pos) & lm) continue;
+        if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
+        const uint32_t wh = bc_window(gp.H, pos) & lm, wl = bc_window(gp.Lo, pos) & lm;
+        const uint32_t slot = cd.dir_off + bc_combo_key(cd, wh, wl);
+        if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
+        atomicAdd(&gdir[slot], 1u);
+    }
+}
+
+// bin_start[g] = first record of bin g (g over all combinations, + end sentinel); bin_cursor = copy;
+// bin_combo[g] = its combination
+__global__ void k_cbin_init(const __grid_constant__ CBucketParams gp, const uint32_t* __restrict__ gdir,
+                            uint32_t n_bins, uint32_t n_slots, uint32_t* __restrict__ bin_start,
+                            uint32_t* __restrict__ bin_cursor, uint8_t* __restrict__ bin_combo) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_bins) return;
+    if (g == n_bins) {
+        bin_start[g] = gdir[n_slots];
+        return;
+    }
+    uint32_t c = 0;
+    while (c + 1 < gp.n_combos && gp.combo[c + 1].bin_off <= g) c++;
+    const ComboDesc& cd = gp.combo[c];
+    const uint32_t low = 2u * cd.key_nt - cd.top_bits;
+    const uint32_t v = gdir[cd.dir_off + ((g - cd.bin_off) << low)];
+    bin_start[g] = v;
+    bin_cursor[g] = v;
+    bin_combo[g] = (uint8_t)c;
+}
+
+// exclusive scan of CJ_THREADS values, one per thread; s_warp: CJ_THREADS / 32 words
+__device__ __forceinline__ uint32_t cj_block_scan(uint32_t v, uint32_t* s_warp) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < CJ_THREADS / 32; w++) before += (uint32_t)w < warp ? s_warp[w] : 0u;
+    __syncthreads();
+    return before + incl - v;
+}
+
+// ------------------------------------------------------------------------------------- pass A
+// Position-major: a chunk of CJ_CHUNK window positions is validated once (ambiguity, PAM gate), its
+// plane words are staged in shared memory, and then every combination in turn bins the chunk's
+// windows: shared-memory histogram over the combination's bins, ONE global atomic per (chunk, bin),
+// records grouped by bin in shared memory and written out as runs.
+__global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ CBucketParams gp,
+                                                        uint32_t* __restrict__ bin_cursor, uint2* __restrict__ tmp) {
+    extern __shared__ __align__(16) uint32_t cj_smem[];
+    uint32_t* s_hist = cj_smem;                      // [CJ_MAX_BINS]
+    uint32_t* s_lstart = s_hist + CJ_MAX_BINS;       // [CJ_MAX_BINS]
+    uint32_t* s_delta = s_lstart + CJ_MAX_BINS;      // [CJ_MAX_BINS] global base - local start
+    uint32_t* s_H = s_delta + CJ_MAX_BINS;           // [CJ_CHUNK / 32 + 2]
+    uint32_t* s_L = s_H + (CJ_CHUNK / 32 + 2);
+    uint32_t* s_warp = s_L + (CJ_CHUNK / 32 + 2);    // [CJ_THREADS / 32]
+    uint2* s_rec = reinterpret_cast<uint2*>(s_warp + CJ_THREADS / 32);  // [CJ_CHUNK]
+    uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_rec + CJ_CHUNK);    // [CJ_CHUNK]
+    const uint32_t lm = bc_lmask(gp.L);
+    PamGate gate;
+    bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t c0 = (uint64_t)gp.pos_begin + (uint64_t)blockIdx.x * CJ_CHUNK; c0 < gp.pos_end;
+         c0 += (uint64_t)gridDim.x * CJ_CHUNK) {
+        // plane words of the chunk (+ the word after it: a window spans two words).  The chunk
+        // need not start on a word boundary: word 0 of the stage is word c0 >> 5 of the plane.
+        const uint32_t w0 = (uint32_t)(c0 >> 5), sh0 = (uint32_t)(c0 & 31u);
+        __syncthreads();
+        for (uint32_t i = tid; i < CJ_CHUNK / 32 + 2; i += CJ_THREADS) {
+            const uint32_t w = min(w0 + i, gp.n_words - 1u);  // the planes are padded by less than a chunk
+            s_H[i] = gp.H[w];
+            s_L[i] = gp.Lo[w];
+        }
+        uint32_t ok = 0;
+#pragma unroll
+        for (int i = 0; i < CJ_ITEMS; i++) {
+            const uint64_t pos64 = c0 + tid + (uint32_t)i * CJ_THREADS;
+            if (pos64 >= gp.pos_end) continue;
+            const uint32_t pos = (uint32_t)pos64;
+            if (bc_window(gp.B, pos) & lm) continue;
+            if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
+            ok |= 1u << i;
+        }
+        __syncthreads();
+        for (uint32_t c = 0; c < gp.n_combos; c++) {
+            const ComboDesc& cd = gp.combo[c];
+            const uint32_t low = 2u * cd.key_nt - cd.top_bits, rem_nt = cd.rem_nt;
+            const uint32_t n_bins = 1u << cd.top_bits;
+            for (uint32_t j = tid; j < n_bins; j += CJ_THREADS) s_hist[j] = 0;
+            __syncthreads();
+            uint32_t x[CJ_ITEMS], rb[CJ_ITEMS];
+#pragma unroll
+            for (int i = 0; i < CJ_ITEMS; i++) {
+                rb[i] = 0xffffffffu;
+                if (!((ok >> i) & 1u)) continue;
+                const uint32_t t = sh0 + tid + (uint32_t)i * CJ_THREADS;  // bit offset inside the staged words
+                const uint32_t wh = __funnelshift_r(s_H[t >> 5], s_H[(t >> 5) + 1], t & 31u) & lm;
+                const uint32_t wl = __funnelshift_r(s_L[t >> 5], s_L[(t >> 5) + 1], t & 31u) & lm;
+                const uint32_t key = bc_combo_key(cd, wh, wl);
+                if (gp.prune && gp.lib_dir[cd.dir_off + key] == gp.lib_dir[cd.dir_off + key + 1]) continue;
+                const uint32_t bin = key >> low;
+                x[i] = ((key & ((1u << low) - 1u)) << (2u * rem_nt)) | (bc_combo_rem(cd, wl) << rem_nt) | bc_combo_rem(cd, wh);
+                rb[i] = atomicAdd(&s_hist[bin], 1u) | (bin << 16);
+            }
+            __syncthreads();
+            {   // two consecutive counters per thread (CJ_MAX_BINS == 2 * CJ_THREADS)
+                const uint32_t j0 = 2u * tid, j1 = j0 + 1;
+                const uint32_t c0n = j0 < n_bins ? s_hist[j0] : 0u, c1n = j1 < n_bins ? s_hist[j1] : 0u;
+                const uint32_t before = cj_block_scan(c0n + c1n, s_warp);
+                if (j0 < n_bins) {
+                    s_lstart[j0] = before;
+                    s_delta[j0] = c0n ? atomicAdd(&bin_cursor[cd.bin_off + j0], c0n) - before : 0u;
+                }
+                if (j1 < n_bins) {
+                    s_lstart[j1] = before + c0n;
+                    s_delta[j1] = c1n ? atomicAdd(&bin_cursor[cd.bin_off + j1], c1n) - (before + c0n) : 0u;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < CJ_ITEMS; i++) {
+                if (rb[i] == 0xffffffffu) continue;
+                const uint32_t bin = rb[i] >> 16, at = s_lstart[bin] + (rb[i] & 0xffffu);
+                s_rec[at] = make_uint2((uint32_t)(c0 + tid + (uint32_t)i * CJ_THREADS), x[i]);
+                s_bin[at] = (uint16_t)bin;
+            }
+            __syncthreads();
+            const uint32_t total = s_lstart[n_bins - 1] + s_hist[n_bins - 1];
+            for (uint32_t i = tid; i < total; i += CJ_THREADS) tmp[i + s_delta[s_bin[i]]] = s_rec[i];
+            __syncthreads();
+        }
+    }
+}
+static_assert(CJ_MAX_BINS == 2 * CJ_THREADS, "k_cbin scans two bins per thread");
+static_assert(CJ_CHUNK <= 65536, "k_cbin packs the local rank into 16 bits");
+
+// chunk_bin[ch] = bin that holds record ch * CJ_CHUNK of the pass-A output
+__global__ void k_cchunk_bins(const uint32_t* __restrict__ bin_start, uint32_t n_bins, const uint32_t* __restrict__ n_rec_ptr,
+                              uint32_t* __restrict__ chunk_bin) {
+    const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_rec = *n_rec_ptr;
+    if ((uint64_t)ch * CJ_CHUNK >= n_rec) return;
+    const uint32_t r = ch * CJ_CHUNK;
+    uint32_t lo = 0, hi = n_bins;  // bin_start[lo] <= r < bin_start[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (bin_start[mid] <= r) lo = mid; else hi = mid;
+    }
+    chunk_bin[ch] = lo;
+}
+
+// ------------------------------------------------------------------------------------- pass B
+// Chunks of the pass-A output, handed out through an atomic counter; a chunk that straddles bin
+// regions is processed piece by piece.  Per piece: shared-memory histogram over the bin's
+// sub-slots (low key bits), one global atomic per (piece, sub-slot) on the slot cursor, records
+// grouped by sub-slot in shared memory and written to their final slots as runs.
+__global__ void __launch_bounds__(CJ_THREADS, 2) k_cplace(const __grid_constant__ CBucketParams gp,
+                                                          const uint2* __restrict__ tmp,
+                                                          const uint32_t* __restrict__ bin_start,
+                                                          const uint8_t* __restrict__ bin_combo,
+                                                          const uint32_t* __restrict__ chunk_bin, uint32_t n_bins,
+                                                          uint32_t* __restrict__ gcursor, uint2* __restrict__ gwin,
+                                                          const uint32_t* __restrict__ n_rec_ptr,
+                                                          uint32_t* __restrict__ work, uint32_t max_sub) {
+    extern __shared__ __align__(16) uint32_t cj_smem[];
+    uint32_t* s_hist = cj_smem;               // [max_sub]
+    uint32_t* s_lstart = s_hist + max_sub;    // [max_sub]
+    uint32_t* s_delta = s_lstart + max_sub;   // [max_sub]
+    uint32_t* s_warp = s_delta + max_sub;     // [CJ_THREADS / 32]
+    uint2* s_rec = reinterpret_cast<uint2*>(s_warp + CJ_THREADS / 32);  // [CJ_CHUNK]
+    __shared__ uint32_t s_chunk;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_rec = *n_rec_ptr;
+    const uint32_t n_chunks = (uint32_t)(((uint64_t)n_rec + CJ_CHUNK - 1) / CJ_CHUNK);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_chunk = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t ch = s_chunk;
+        if (ch >= n_chunks) break;
+        const uint32_t r0 = ch * CJ_CHUNK, r1 = r0 + min((uint32_t)CJ_CHUNK, n_rec - r0);
+        uint32_t g = __ldg(chunk_bin + ch), seg = r0;
+        while (seg < r1) {
+            while (g + 1 < n_bins && __ldg(bin_start + g + 1) <= seg) g++;  // skip empty bins
+            const uint32_t s1 = min(r1, __ldg(bin_start + g + 1));
+            const ComboDesc& cd = gp.combo[__ldg(bin_combo + g)];
+            const uint32_t low = 2u * cd.key_nt - cd.top_bits, rem2 = 2u * cd.rem_nt;
+            const uint32_t n_sub = 1u << low;
+            const uint32_t slot0 = cd.dir_off + ((g - cd.bin_off) << low);
+            uint2 rec[CJ_ITEMS];
+            uint32_t rank[CJ_ITEMS];
+            if (low == 0) {  // the bin is one slot: a plain copy
+#pragma unroll
+                for (int i = 0; i < CJ_ITEMS; i++) {
+                    const uint32_t idx = seg + tid + (uint32_t)i * CJ_THREADS;
+                    if (idx < s1) gwin[idx] = __ldcs(tmp + idx);
+                }
+                seg = s1;
+                continue;
+            }
+            for (uint32_t j = tid; j < n_sub; j += CJ_THREADS) s_hist[j] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < CJ_ITEMS; i++) {
+                const uint32_t idx = seg + tid + (uint32_t)i * CJ_THREADS;
+                if (idx < s1) {
+                    rec[i] = __ldcs(tmp + idx);
+                    rank[i] = atomicAdd(&s_hist[rec[i].y >> rem2], 1u);
+                }
+            }
+            __syncthreads();
+            {   // n_sub / CJ_THREADS (>= 1 when n_sub >= CJ_THREADS) consecutive counters per thread
+                const uint32_t per = (n_sub + CJ_THREADS - 1) / CJ_THREADS;
+                const uint32_t j0 = tid * per;
+                uint32_t sum = 0;
+                for (uint32_t j = 0; j < per; j++) sum += j0 + j < n_sub ? s_hist[j0 + j] : 0u;
+                uint32_t run = cj_block_scan(sum, s_warp);
+                for (uint32_t j = 0; j < per && j0 + j < n_sub; j++) {
+                    const uint32_t cnt = s_hist[j0 + j];
+                    s_lstart[j0 + j] = run;
+                    s_delta[j0 + j] = cnt ? atomicAdd(&gcursor[slot0 + j0 + j], cnt) - run : 0u;
+                    run += cnt;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < CJ_ITEMS; i++) {
+                const uint32_t idx = seg + tid + (uint32_t)i * CJ_THREADS;
+                if (idx < s1) s_rec[s_lstart[rec[i].y >> rem2] + rank[i]] = rec[i];
+            }
+            __syncthreads();
+            const uint32_t n = s1 - seg;
+            for (uint32_t i = tid; i < n; i += CJ_THREADS) {
+                const uint2 r = s_rec[i];
+                gwin[i + s_delta[r.y >> rem2]] = r;
+            }
+            __syncthreads();
+            seg = s1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- verify
+#define CV_THREADS 256
+#define CV_WARPS (CV_THREADS / 32)
+#define CV_ITEMS 4          // window records per lane per warp-tile (at most)
+#define CV_WQ 128           // per-warp candidate queue (entries)
+#define CV_GQ 96            // per-warp queue of groups awaiting re-examination (31 + 2 * 32)
+#define CV_STAGE 64         // library entries per shared-memory stage (x2 buffers per warp)
+#define CV_GROUP 8          // entries per group (one ballot per group)
+#ifndef CV_CHUNK_TILES
+#define CV_CHUNK_TILES 32   // 128-record units per work chunk
+#endif
+#ifndef CV_MINBLOCKS
+#define CV_MINBLOCKS 4
+#endif
+#define CV_INVALID 0xf0000000u  // rem plane of a missing window: 4 mismatches above the rem bits, never <= k
+
+__device__ __forceinline__ void cv_cp_async8(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+__device__ __forceinline__ uint32_t cv_combo_of_slot(const SearchParams& p, uint32_t slot) {
+    uint32_t c = 0;
+    while (c + 1 < p.n_combos && p.combo[c + 1].dir_off <= slot) c++;
+    return c;
+}
+
+// Resolve up to 32 queued candidates {dev position, rem mismatch mask, index entry, slot} with all
+// lanes: mask back to query positions, ownership, PAM annotation, ONE global atomic for the batch,
+// coalesced store of the surviving records.
+static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint4* q, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint4 rec;
+    bool ok = false;
+    if (lane < n) {
+        const uint4 qe = q[lane];
+        const uint32_t c = cv_combo_of_slot(p, qe.w);
+        ok = bc_make_hit(p, c, qe.x, p.ent_id[qe.z], bc_combo_rem_expand(p.combo[c], qe.y), &rec);
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+    if (ballot == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(p.count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) {
+        const unsigned long long dst = base + __popc(ballot & ((1u << lane) - 1u));
+        if (dst < p.cap) reinterpret_cast<uint4*>(p.hits)[dst] = rec;
+    }
+}
+
+static __device__ __noinline__ void cv_overflow(const SearchParams& p, uint32_t pos, uint32_t mr, uint32_t e, uint32_t slot) {
+    uint4 rec;
+    const uint32_t c = cv_combo_of_slot(p, slot);
+    if (bc_make_hit(p, c, pos, p.ent_id[e], bc_combo_rem_expand(p.combo[c], mr), &rec)) {
+        const unsigned long long g = atomicAdd(p.count, 1ull);
+        if (g < p.cap) reinterpret_cast<uint4*>(p.hits)[g] = rec;
+    }
+}
+
+__device__ __forceinline__ void cv_drain(const SearchParams& p, uint4* q, uint32_t* qn, uint32_t lane) {
+    __syncwarp();
+    uint32_t nq = min(*qn, (uint32_t)CV_WQ);
+    if (nq >= 32) {
+        do {
+            cv_resolve(p, q + (nq - 32), 32);
+            nq -= 32;
+        } while (nq >= 32);
+        __syncwarp();
+        if (lane == 0) *qn = nq;
+    }
+    __syncwarp();
+}
+
+// Second level: a queued GROUP {record of the lane that saw it, first entry, slot, end of the tile}
+// stands for CV_ITEMS x CV_GROUP pairs of which at least one passed the filter.  32 groups are
+// re-examined at once, one per lane, so the per-pair compare + branch runs with full lanes.
+static __device__ __noinline__ void cv_resolve_groups(const SearchParams& p, const uint2* __restrict__ gwin,
+                                                      const uint4* gq, uint32_t n, uint4* q, uint32_t* qn) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const int k = (int)p.k;
+    __syncwarp();
+    if (lane < n) {
+        const uint4 item = gq[lane];  // x record index, y first entry, z slot, w end of the tile (record index)
+        const uint32_t rem_nt = p.combo[cv_combo_of_slot(p, item.z)].rem_nt, rm = (1u << rem_nt) - 1u;
+        const uint32_t n_e = min((uint32_t)CV_GROUP, __ldg(p.dir + item.z + 1) - item.y);
+        uint2 w[CV_ITEMS];
+#pragma unroll
+        for (int it = 0; it < CV_ITEMS; it++) w[it] = __ldg(gwin + min(item.x + it * 32, item.w - 1));
+        for (uint32_t j = 0; j < n_e; j++) {
+            const uint2 qe = __ldg(p.ent_hl + item.y + j);
+#pragma unroll
+            for (int it = 0; it < CV_ITEMS; it++) {
+                const uint32_t m_ = ((w[it].y & rm) ^ qe.x) | (((w[it].y >> rem_nt) & rm) ^ qe.y);
+                if (item.x + it * 32 < item.w && __popc(m_) <= k) {
+                    const uint32_t qs = atomicAdd(qn, 1u);
+                    if (qs < CV_WQ) q[qs] = make_uint4(w[it].x, m_, item.y + j, item.z);
+                    else cv_overflow(p, w[it].x, m_, item.y + j, item.z);
+                }
+            }
+        }
+    }
+    cv_drain(p, q, qn, lane);
+}
+
+// One warp-tile: `items` (1..CV_ITEMS, warp-uniform) resident windows per lane against the bucket
+// [ls, le) of the library index, staged through shared memory (cp.async, CV_STAGE entries per
+// stage, double buffered).  One group = CV_GROUP entries (16-byte broadcast LDS, two entries
+// each) x ITEMS windows, independent LOP3/LOP3/POPC chains folded with min, then ONE ballot; a lane
+// whose minimum passes only QUEUES the group.  1 pair in 8 is tested on the ALU pipe instead of
+// POPC (mismatch mask with its K lowest set bits cleared == 0): POPC alone saturates the XU pipe.
+template <int K, int ITEMS>
+__device__ __forceinline__ uint32_t cv_tile(const SearchParams& p, const uint2* __restrict__ gwin, const uint32_t (&wh)[CV_ITEMS],
+                                            const uint32_t (&wl)[CV_ITEMS], uint32_t ls, uint32_t le, uint32_t first,
+                                            uint32_t tend, uint32_t slot, uint2* sbuf, uint4* gq, uint32_t gn, uint4* q,
+                                            uint32_t* qn) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t n_ent = le - ls;
+    const uint32_t n_stage = (n_ent + CV_STAGE - 1) / CV_STAGE;
+    const uint2* bucket = p.ent_hl + ls;
+#define CV_ISSUE(C)                                                                        \
+    do {                                                                                   \
+        uint2* dst_ = sbuf + ((C) & 1u) * CV_STAGE;                                        \
+        _Pragma("unroll") for (int h = 0; h < CV_STAGE / 32; h++) {                        \
+            const uint32_t i_ = (C) * CV_STAGE + h * 32 + lane;                            \
+            if (i_ < n_ent) cv_cp_async8(dst_ + h * 32 + lane, bucket + i_);               \
+        }                                                                                  \
+        asm volatile("cp.async.commit_group;" ::: "memory");                               \
+    } while (0)
+    CV_ISSUE(0u);
+    for (uint32_t c = 0; c < n_stage; c++) {
+        if (c + 1 < n_stage) {
+            CV_ISSUE(c + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const uint4* sb = reinterpret_cast<const uint4*>(sbuf + (c & 1u) * CV_STAGE);
+        const uint32_t ng = (min((uint32_t)CV_STAGE, n_ent - c * CV_STAGE) + CV_GROUP - 1) / CV_GROUP;
+        const uint32_t ebase = ls + c * CV_STAGE;
+        uint32_t g = 0;
+        for (;;) {
+            for (; g < ng && gn < 32; g++) {
+                int best_ = 33;
+                uint32_t rest_ = 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < CV_GROUP / 2; j++) {
+                    const uint4 e2 = sb[g * (CV_GROUP / 2) + j];
+#pragma unroll
+                    for (int it = 0; it < ITEMS; it++) {
+                        best_ = min(best_, __popc((wh[it] ^ e2.x) | (wl[it] ^ e2.y)));
+                        if (j == CV_GROUP / 2 - 1) {
+                            uint32_t m = (wh[it] ^ e2.z) | (wl[it] ^ e2.w);
+#pragma unroll
+                            for (int cc = 0; cc < K; cc++) m &= m - 1u;
+                            rest_ = min(rest_, m);
+                        } else {
+                            best_ = min(best_, __popc((wh[it] ^ e2.z) | (wl[it] ^ e2.w)));
+                        }
+                    }
+                }
+                const bool pass_ = best_ <= K || rest_ == 0u;
+                const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_);
+                if (hit_) {  // warp-uniform
+                    if (pass_) gq[gn + __popc(hit_ & lt_mask)] = make_uint4(first + lane, ebase + g * CV_GROUP, slot, tend);
+                    gn += __popc(hit_);
+                }
+            }
+            if (gn < 32) break;
+            do {  // warp-uniform; at most 31 + 32 groups are queued here
+                gn -= 32;
+                cv_resolve_groups(p, gwin, gq + gn, 32, q, qn);
+            } while (gn >= 32);
+        }
+        __syncwarp();  // every lane is done with this buffer before stage c+2 lands in it
+    }
+#undef CV_ISSUE
+    return gn;
+}
+
+// Every slot is cut into warp-tiles of up to 128 window records ALIGNED TO THE SLOT START, so all
+// windows of a tile share one library bucket, which is streamed once per tile as broadcast loads
+// against the (up to 4) resident windows of each lane.  The record array is cut into chunks of
+// CV_CHUNK_TILES * 128 records handed out through an atomic counter; a warp owns the tiles that
+// START in its chunk.  Records do not carry their slot: the slot of the chunk's first record comes
+// from a binary search of the record directory, the following slots from walking it.
+template <int K>
+__global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __grid_constant__ SearchParams p,
+                                                                      const uint2* __restrict__ gwin,
+                                                                      const uint32_t* __restrict__ gdir, uint32_t n_slots,
+                                                                      uint32_t* __restrict__ work, uint32_t slice,
+                                                                      uint32_t frac_lo, uint32_t frac_hi) {
+    __shared__ uint4 s_q[CV_WARPS][CV_WQ];
+    __shared__ uint4 s_gq[CV_WARPS][CV_GQ];
+    __shared__ __align__(16) uint2 s_ent[CV_WARPS][2 * CV_STAGE];
+    __shared__ uint32_t s_qn[CV_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint4* gq = s_gq[warp];
+    uint2* sbuf = s_ent[warp];
+    uint32_t gn = 0;  // queued groups of this warp (warp-uniform; survives across tiles)
+    uint4* q = s_q[warp];
+    uint32_t* qn = &s_qn[warp];
+    if (lane == 0) *qn = 0;
+    __syncwarp();
+    const uint32_t n_rec = __ldg(gdir + n_slots);
+    const uint32_t wtile = 32 * CV_ITEMS, chunk = wtile * CV_CHUNK_TILES;
+    const uint32_t n_chunks = (uint32_t)(((uint64_t)n_rec + chunk - 1) / chunk);
+    unsigned long long cand = 0;
+    const uint32_t ch_lo = (uint32_t)(((unsigned long long)n_chunks * frac_lo) >> 16);
+    const uint32_t ch_hi = (uint32_t)(((unsigned long long)n_chunks * frac_hi) >> 16);
+    for (;;) {
+        uint32_t ch = 0;
+        if (lane == 0) ch = ch_lo + atomicAdd(work + slice, 1u);
+        ch = __shfl_sync(0xffffffffu, ch, 0);
+        if (ch >= ch_hi) break;
+        const uint32_t r0 = ch * chunk, r1 = r0 + min(chunk, n_rec - r0);
+        // slot of record r0: the last slot whose first record is <= r0 (warp-uniform loads)
+        uint32_t slot = 0;
+        {
+            uint32_t lo = 0, hi = n_slots;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(gdir + mid) <= r0) lo = mid; else hi = mid;
+            }
+            slot = lo;
+        }
+        uint32_t c = cv_combo_of_slot(p, slot);
+        uint32_t a = __ldg(gdir + slot), b = __ldg(gdir + slot + 1);  // records of this slot
+        uint32_t t = a + (r0 - a + wtile - 1) / wtile * wtile;         // first tile start >= r0
+        for (;;) {
+            if (t >= b) {  // slot finished: the next non-empty slot starts where this one ends
+                if (b >= r1) break;
+                uint32_t s2 = slot + 1;
+                for (;;) {  // 32 directory entries at a time
+                    const uint32_t idx = min(s2 + lane + 1, n_slots);
+                    const uint32_t more = __ballot_sync(0xffffffffu, __ldg(gdir + idx) > b);
+                    if (more) {
+                        s2 += __ffs(more) - 1;
+                        break;
+                    }
+                    s2 += 32;
+                }
+                slot = s2;
+                a = b;
+                b = __ldg(gdir + slot + 1);
+                t = a;
+                while (c + 1 < p.n_combos && p.combo[c + 1].dir_off <= slot) c++;
+                continue;
+            }
+            if (t >= r1) break;
+            const uint32_t first = t, tend = min(t + wtile, b);
+            t += wtile;
+            const uint32_t ls = __ldg(p.dir + slot), le = __ldg(p.dir + slot + 1);
+            if (ls == le) continue;
+            const uint32_t rem_nt = p.combo[c].rem_nt, rm = (1u << rem_nt) - 1u;
+            uint32_t wh[CV_ITEMS], wl[CV_ITEMS];
+#pragma unroll
+            for (int it = 0; it < CV_ITEMS; it++) {
+                const uint32_t idx = first + it * 32 + lane;
+                wh[it] = CV_INVALID;
+                wl[it] = 0;
+                if (idx < tend) {
+                    const uint32_t x = __ldcs(&gwin[idx].y);
+                    wh[it] = x & rm;
+                    wl[it] = (x >> rem_nt) & rm;
+                }
+            }
+            const uint32_t n_win = tend - first;
+            cand += (unsigned long long)(le - ls) * ((n_win + 31u - lane) / 32u);
+            switch ((n_win + 31u) / 32u) {
+                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
+                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
+                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
+                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
+            }
+            cv_drain(p, q, qn, lane);
+        }
+    }
+    while (gn) {  // up to CV_GQ - 1 groups are still queued
+        const uint32_t take = min(gn, 32u);
+        gn -= take;
+        cv_resolve_groups(p, gwin, gq + gn, take, q, qn);
+    }
+    __syncwarp();
+    const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
+    if (nq) cv_resolve(p, q, nq);
+    if (p.count_candidates) atomicAdd(p.count + 1, cand);
+}
+
+// ------------------------------------------------------------------------------------------ host
+#define JCK(call)                           \
+    do {                                    \
+        cudaError_t e__ = (call);           \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, uint32_t n_bins, int sm_count,
+                            cudaStream_t st, uint32_t* launches, HitSink* sink) {
+    const uint32_t launches0 = bc_launch_counter;
+    ws.ms_join_kernels = ws.ms_bucket_kernels = 0;
+    if (!ws.ev_a) JCK(cudaEventCreate(&ws.ev_a));
+    if (!ws.ev_b) JCK(cudaEventCreate(&ws.ev_b));
+    if (!ws.ev_c) JCK(cudaEventCreate(&ws.ev_c));
+    const uint32_t n_slots = (uint32_t)(dir_slots - 1);
+
+    uint32_t max_low = 0;
+    for (uint32_t c = 0; c < p.n_combos; c++) {
+        const uint32_t low = 2u * p.combo[c].key_nt - p.combo[c].top_bits;
+        if (low > max_low) max_low = low;
+    }
+    // genome positions per pass: two 8-byte record arrays within the workspace budget
+    const uint64_t span = (uint64_t)p.pos_end - p.pos_begin;
+    uint64_t chunk = span ? span : 1;
+    if (p.join_chunk && chunk > p.join_chunk) chunk = p.join_chunk;
+    const uint64_t cap8 = ws.gwin_cap * 2;  // the workspace is sized in 16-byte records; two uint2 per slot
+    if (chunk * p.n_combos > cap8) {
+        size_t free_b = 0, total_b = 0;
+        JCK(cudaMemGetInfo(&free_b, &total_b));
+        uint64_t budget = ((uint64_t)free_b + ((ws.d_gwin ? 1 : 0) + (ws.d_gtmp ? 1 : 0)) * ws.gwin_cap * sizeof(uint4)) / 2;
+        if (budget > (96ull << 30)) budget = 96ull << 30;
+        const uint64_t fit = budget / (2 * sizeof(uint2)) / p.n_combos;
+        if (chunk > fit) chunk = fit;
+        if (chunk < 1) chunk = 1;
+    }
+    if (chunk * p.n_combos >= (1ull << 32) - 65536) chunk = ((1ull << 32) - 65536) / p.n_combos;
+    const uint64_t rec16_needed = (chunk * p.n_combos + 1) / 2 + 1;
+    if (rec16_needed > ws.gwin_cap || !ws.d_gtmp) {
+        const uint64_t want = rec16_needed > ws.gwin_cap ? rec16_needed : ws.gwin_cap;
+        if (ws.d_gwin) cudaFree(ws.d_gwin);
+        if (ws.d_gtmp) cudaFree(ws.d_gtmp);
+        ws.d_gwin = ws.d_gtmp = nullptr;
+        ws.gwin_cap = 0;
+        JCK(cudaMalloc(&ws.d_gwin, (want + 1) * sizeof(uint4)));
+        JCK(cudaMalloc(&ws.d_gtmp, (want + 1) * sizeof(uint4)));
+        ws.gwin_cap = want;
+    }
+    // per-bin tables live in the bin cursor allocation: cursor | start (+1) | chunk table | combination bytes
+    const uint64_t max_chunks = (chunk * p.n_combos + CJ_CHUNK - 1) / CJ_CHUNK + 1;
+    const uint64_t bin_words = 2ull * (n_bins + 2) + max_chunks + (n_bins + 8) / 4 + 4;
+    if (bin_words > ws.bin_cap) {
+        if (ws.d_bin_cursor) cudaFree(ws.d_bin_cursor);
+        ws.d_bin_cursor = nullptr;
+        ws.bin_cap = 0;
+        JCK(cudaMalloc(&ws.d_bin_cursor, bin_words * sizeof(uint32_t)));
+        ws.bin_cap = bin_words;
+    }
+    uint32_t* d_bin_cursor = ws.d_bin_cursor;
+    uint32_t* d_bin_start = d_bin_cursor + (n_bins + 2);
+    uint32_t* d_chunk_bin = d_bin_start + (n_bins + 2);
+    uint8_t* d_bin_combo = reinterpret_cast<uint8_t*>(d_chunk_bin + max_chunks);
+    if (dir_slots > ws.gdir_cap) {
+        if (ws.d_gdir) cudaFree(ws.d_gdir);
+        if (ws.d_gcursor) cudaFree(ws.d_gcursor);
+        ws.d_gdir = ws.d_gcursor = nullptr;
+        ws.gdir_cap = 0;
+        JCK(cudaMalloc(&ws.d_gdir, dir_slots * 4));
+        JCK(cudaMalloc(&ws.d_gcursor, dir_slots * 4));
+        ws.gdir_cap = dir_slots;
+    }
+    const uint64_t tmp_words = bc_scan_tmp_words(dir_slots);
+    if (tmp_words > ws.scan_tmp_cap) {
+        if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
+        ws.d_scan_tmp = nullptr;
+        ws.scan_tmp_cap = 0;
+        JCK(cudaMalloc(&ws.d_scan_tmp, tmp_words * 4));
+        ws.scan_tmp_cap = tmp_words;
+    }
+    if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, BC_SINK_SLICES * sizeof(uint32_t)));
+
+    CBucketParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.H = p.H; gp.Lo = p.Lo; gp.B = p.B;
+    gp.lib_dir = p.dir;
+    gp.n_words = p.n_words;
+    gp.L = p.L;
+    gp.n_combos = p.n_combos;
+    memcpy(gp.combo, p.combo, sizeof gp.combo);
+    gp.prune = p.dir_entries < (dir_slots - 1) * 2 ? 1u : 0u;
+    gp.gate_first = p.gate_first;
+    gp.P = p.P; gp.pam_dir = p.pam_dir;
+    for (int i = 0; i < 8; i++) gp.pam_sets[i] = p.pam_sets[i];
+
+    const size_t smem_a = (3 * CJ_MAX_BINS + 2 * (CJ_CHUNK / 32 + 2) + CJ_THREADS / 32) * 4 + (size_t)CJ_CHUNK * 8 +
+                          (size_t)CJ_CHUNK * 2;
+    const uint32_t max_sub = 1u << max_low;
+    const size_t smem_b = (3 * (size_t)max_sub + CJ_THREADS / 32) * 4 + (size_t)CJ_CHUNK * 8;
+    JCK(cudaFuncSetAttribute(k_cbin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    JCK(cudaFuncSetAttribute(k_cplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    uint2* d_tmp = reinterpret_cast<uint2*>(ws.d_gtmp);
+    uint2* d_win = reinterpret_cast<uint2*>(ws.d_gwin);
+    const bool one_pass = max_low == 0;  // every bin is one slot: pass A writes the final array
+
+    for (uint64_t begin = p.pos_begin; begin < p.pos_end; begin += chunk) {
+        gp.pos_begin = (uint32_t)begin;
+        gp.pos_end = (uint32_t)((begin + chunk < p.pos_end) ? begin + chunk : p.pos_end);
+        const uint32_t npos = gp.pos_end - gp.pos_begin;
+        uint32_t gx = (npos + 255) / 256;
+        const uint32_t maxb = (uint32_t)sm_count * 8u;
+        if (gx > maxb) gx = maxb;
+        JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
+        JCK(cudaEventRecord(ws.ev_c, st));
+        k_ccount<<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_gdir);
+        JCK(cudaGetLastError());
+        JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
+        if (!one_pass) JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
+        k_cbin_init<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, ws.d_gdir, n_bins, n_slots, d_bin_start, d_bin_cursor, d_bin_combo);
+        JCK(cudaGetLastError());
+        uint32_t bx = (npos + CJ_CHUNK - 1) / CJ_CHUNK;
+        if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
+        k_cbin<<<bx, CJ_THREADS, smem_a, st>>>(gp, d_bin_cursor, one_pass ? d_win : d_tmp);
+        JCK(cudaGetLastError());
+        bc_launch_counter += 3;
+        if (!one_pass) {
+            k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, ws.d_gdir + n_slots, d_chunk_bin);
+            JCK(cudaGetLastError());
+            JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
+            k_cplace<<<(uint32_t)sm_count * 2u, CJ_THREADS, smem_b, st>>>(gp, d_tmp, d_bin_start, d_bin_combo, d_chunk_bin, n_bins,
+                                                                        ws.d_gcursor, d_win, ws.d_gdir + n_slots, ws.d_work, max_sub);
+            JCK(cudaGetLastError());
+            bc_launch_counter += 2;
+        }
+        JCK(cudaEventRecord(ws.ev_a, st));
+        // Streamed delivery: the slices halve (1/2, 1/4, ... and the last one repeated)
+        const uint32_t n_slices = sink ? BC_SINK_SLICES : 1;
+        JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
+        for (uint32_t s = 0; s < n_slices; s++) {
+            const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));
+            const uint32_t dgrid = (uint32_t)sm_count * CV_MINBLOCKS, lo = n_slices == 1 ? 0u : f_lo;
+            switch (p.k) {
+                case 0: k_cverify<0><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                case 1: k_cverify<1><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                case 2: k_cverify<2><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                default: k_cverify<3><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+            }
+            JCK(cudaGetLastError());
+            if (sink) {
+                JCK(cudaMemcpyAsync(sink->h_counts + s, p.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                JCK(cudaEventRecord(sink->ev[s], st));
+            }
+        }
+        JCK(cudaEventRecord(ws.ev_b, st));
+        bc_launch_counter += n_slices;
+        if (sink) JCK(bc_sink_deliver(sink, p, n_slices));
+        JCK(cudaEventSynchronize(ws.ev_b));
+        float ms = 0;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_a, ws.ev_b));
+        ws.ms_join_kernels += ms;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_c, ws.ev_a));
+        ws.ms_bucket_kernels += ms;
+    }
+    *launches = bc_launch_counter - launches0;
+    return cudaSuccess;
+}

@@ -16,20 +16,29 @@
 
 #include "../../include/barcoder_b200.h"
 
-#define BC_MAX_COMBOS 35
-#define BC_MAX_PIECES 4
+#define BC_MAX_COMBOS 40
+#define BC_MAX_PIECES 6
 #define BC_MAX_BLOCKS 8
 #define BC_KEY_MAX_NT 12
 
+// One seed combination = one set of query positions (the key) under which the library is indexed
+// and the genome windows are probed / sorted.  The key positions are at most BC_MAX_PIECES runs;
+// the remaining ("rem") positions are at most BC_MAX_PIECES + 1 runs.
 struct ComboDesc {
-    uint32_t blocks_mask;            // which of the b blocks form this seed combination
+    uint32_t blocks_mask;            // block schemes: which of the b blocks form this combination (0 for designs)
     uint32_t key_mask;               // query-position bits covered by the key pieces
     uint32_t dir_off;                // first directory slot of this combination
     uint8_t n_pieces;
+    uint8_t key_nt;                  // total bases in the key
     uint8_t start[BC_MAX_PIECES];    // first base of each key piece
     uint8_t len[BC_MAX_PIECES];      // bases in each key piece
-    uint8_t key_nt;                  // total bases in the key
-    uint8_t pad[2];
+    uint8_t n_rem;                   // runs of non-key positions (compact join path)
+    uint8_t rem_nt;                  // L - key_nt
+    uint8_t rstart[BC_MAX_PIECES + 1];
+    uint8_t rlen[BC_MAX_PIECES + 1];
+    uint8_t top_bits;                // compact join path: key bits that select the pass-A bin
+    uint8_t pad;
+    uint32_t bin_off;                // compact join path: first pass-A bin of this combination
 };
 
 struct SearchParams {
@@ -39,6 +48,7 @@ struct SearchParams {
     const uint32_t* B;
     const uint32_t* start_dev;  // [n_contigs+1] dev position of each contig start; last = n_pos
     uint32_t n_pos;             // dev positions (bases + separators)
+    uint32_t n_words;           // words per plane (whole tiles + padding, bc_api.cu)
     uint32_t pos_begin, pos_end;  // window start positions this context scans (genome-range sharding)
     uint32_t n_contigs;
     // library
@@ -81,6 +91,28 @@ __device__ __forceinline__ uint32_t bc_combo_key(const ComboDesc& cd, uint32_t h
         key = (key << (2 * len)) | (((h >> st) & m) << len) | ((l >> st) & m);
     }
     return key;
+}
+
+// The non-key bits of a plane word, packed to the low rem_nt bits (ascending position order).
+__device__ __forceinline__ uint32_t bc_combo_rem(const ComboDesc& cd, uint32_t v) {
+    uint32_t out = 0, acc = 0;
+    for (uint32_t i = 0; i < cd.n_rem; i++) {
+        const uint32_t len = cd.rlen[i];
+        out |= ((v >> cd.rstart[i]) & ((1u << len) - 1u)) << acc;
+        acc += len;
+    }
+    return out;
+}
+
+// Inverse of bc_combo_rem for a mismatch mask: packed rem bits back to their query positions.
+__device__ __forceinline__ uint32_t bc_combo_rem_expand(const ComboDesc& cd, uint32_t r) {
+    uint32_t out = 0, acc = 0;
+    for (uint32_t i = 0; i < cd.n_rem; i++) {
+        const uint32_t len = cd.rlen[i];
+        out |= ((r >> acc) & ((1u << len) - 1u)) << cd.rstart[i];
+        acc += len;
+    }
+    return out;
 }
 
 __device__ __forceinline__ uint32_t bc_rev_bits(uint32_t m, uint32_t L) { return __brev(m) >> (32 - L); }
@@ -136,14 +168,15 @@ __device__ __forceinline__ bool bc_gate_window(const PamGate& g, const uint32_t*
                             : bc_gate_side(g, H, Lo, B, right, true);
 }
 
-// Ownership: a hit with <= k mismatches has >= b-k exact blocks; it is reported by the seed
-// combination made of its LOWEST b-k exact blocks and by no other, so every alignment is emitted
-// exactly once although several combinations find it.  m = mismatch mask in QUERY orientation.
+// Ownership: several combinations may find the same alignment (every combination whose key
+// positions are mismatch-free does).  It is reported by the FIRST such combination in index order
+// and by no other, so every alignment is emitted exactly once and no dedup pass is needed.
+// m = mismatch mask in QUERY orientation; the caller found the pair through combination c, so
+// c's own key is mismatch-free by construction.
 __device__ __forceinline__ bool bc_owns(const SearchParams& p, uint32_t c, uint32_t m) {
-    uint32_t need = p.b - p.k, own = 0;
-    for (uint32_t j = 0; j < p.b && need; j++)
-        if (!(m & p.block_mask[j])) { own |= 1u << j; need--; }
-    return own == p.combo[c].blocks_mask;
+    for (uint32_t j = 0; j < c; j++)
+        if (!(m & p.combo[j].key_mask)) return false;
+    return true;
 }
 
 // Rare path: a (window, entry) pair passed the popcount filter in seed combination `c`.

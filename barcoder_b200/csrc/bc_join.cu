@@ -641,6 +641,29 @@ void bc_join_free(JoinWorkspace& ws) {
         if (e__ != cudaSuccess) return e__; \
     } while (0)
 
+// Streamed delivery after the verify slices of one pass have been launched: hits are appended
+// through one atomic cursor, so everything below the counter value read after slice s is final
+// once that slice has finished.
+cudaError_t bc_sink_deliver(HitSink* sink, const SearchParams& p, uint32_t n_slices) {
+    for (uint32_t s = 0; s < n_slices; s++) {
+        JCK(cudaEventSynchronize(sink->ev[s]));
+        uint64_t done = sink->h_counts[s];
+        if (done > p.cap) done = p.cap;
+        if (sink->fn && done >= sink->reported) {  // also called for an empty part: callers count calls
+            sink->fn(sink->fn_user, p.hits, sink->reported, done);
+            sink->reported = done;
+        }
+        if (!sink->host) continue;
+        if (done > sink->cap) done = sink->cap;
+        if (done > sink->copied) {
+            JCK(cudaMemcpyAsync(sink->host + sink->copied, p.hits + sink->copied,
+                                (done - sink->copied) * sizeof(bc_hit), cudaMemcpyDefault, sink->stream));
+            sink->copied = done;
+        }
+    }
+    return cudaSuccess;
+}
+
 cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, int sm_count,
                            cudaStream_t st, uint32_t* launches, HitSink* sink) {
     const uint32_t launches0 = bc_launch_counter;
@@ -779,26 +802,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         }
         JCK(cudaEventRecord(ws.ev_b, st));
         bc_launch_counter += n_slices - 1;
-        if (sink) {
-            // hits are appended through one atomic cursor, so everything below the counter value
-            // read after slice s is final once that slice has finished
-            for (uint32_t s = 0; s < n_slices; s++) {
-                JCK(cudaEventSynchronize(sink->ev[s]));
-                uint64_t done = sink->h_counts[s];
-                if (done > p.cap) done = p.cap;
-                if (sink->fn && done >= sink->reported) {  // also called for an empty part: callers count calls
-                    sink->fn(sink->fn_user, p.hits, sink->reported, done);
-                    sink->reported = done;
-                }
-                if (!sink->host) continue;
-                if (done > sink->cap) done = sink->cap;
-                if (done > sink->copied) {
-                    JCK(cudaMemcpyAsync(sink->host + sink->copied, p.hits + sink->copied,
-                                        (done - sink->copied) * sizeof(bc_hit), cudaMemcpyDefault, sink->stream));
-                    sink->copied = done;
-                }
-            }
-        }
+        if (sink) JCK(bc_sink_deliver(sink, p, n_slices));
         bc_launch_counter += 4;
         // events are reused per chunk, so read them before the next record
         JCK(cudaEventSynchronize(ws.ev_b));

@@ -36,4 +36,8 @@ struct HitSink {
 
 cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, int sm_count,
                            cudaStream_t st, uint32_t* launches, HitSink* sink);
+cudaError_t bc_sink_deliver(HitSink* sink, const SearchParams& p, uint32_t n_slices);
+// compact form (8-byte window records; bc_cjoin.cu): same workspace, the record arrays are viewed as uint2
+cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, uint32_t n_bins, int sm_count,
+                            cudaStream_t st, uint32_t* launches, HitSink* sink);
 void bc_join_free(JoinWorkspace& ws);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_index_scatter(IndexParams ip, const __g
         const uint32_t h = ip.qh[e], l = ip.ql[e];
         const uint32_t slot = cd.dir_off + bc_combo_key(cd, h, l);
         const uint32_t dst = atomicAdd(&coarse_cursor[bc_coarse_of(pl, c, slot)], 1u);
-        tmp[dst] = make_uint4(h, l, e, slot);
+        tmp[dst] = ip.compact ? make_uint4(bc_combo_rem(cd, h), bc_combo_rem(cd, l), e, slot) : make_uint4(h, l, e, slot);
     }
 }
 

@@ -207,8 +207,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only)")
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 probe, 2 join")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 probe, 2 join, 3 compact join")
     ap.add_argument("--blocks", type=int, default=0)
+    ap.add_argument("--key-nt", type=int, default=0, help="force a seed covering design with keys of this length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default=None, choices=["library", "genome"],
                     help="multi-GPU partitioning: library shards (weak scaling, default) or genome ranges "
@@ -262,6 +263,8 @@ def main():
         s.set_param(_native.BC_PARAM_PATH, args.path)
     if args.blocks:
         s.set_param(_native.BC_PARAM_BLOCKS, args.blocks)
+    if args.key_nt:
+        s.set_param(_native.BC_PARAM_KEY_NT, args.key_nt)
     s.set_genome_device(d_genome.data_ptr(), off)
     s.set_library_device(d_lib.data_ptr(), n, L)
 
@@ -388,7 +391,7 @@ def main():
              "index_build": acc["ms_build_index"]}
     dominant = max(parts, key=parts.get)
     ipk = int_peak(local_rank)
-    if st["path"] == 2:
+    if st["path"] >= 2:
         # window sort: the three planes are read once per pass and combination (count, scatter),
         # one 16 B record written; verify: that record read once, the index entries (12 B) once,
         # 16 B written per hit
@@ -417,7 +420,7 @@ def main():
                 "note": "HBM view of the stage with the largest share of the step; the verify stage is "
                         "integer-pipe bound and is rated in roofline_int"}
     roofline_int = None
-    if ipk and st["path"] == 2 and acc["ms_scan_kernel"] > 0:
+    if ipk and st["path"] >= 2 and acc["ms_scan_kernel"] > 0:
         # candidates verified per second against the measured POPC issue rate and the measured
         # verify-atom rate (2 LOP3 + POPC + compare fed from a shared-memory broadcast)
         s.set_param(_native.BC_PARAM_COUNT_CANDIDATES, 1)
@@ -461,7 +464,7 @@ def main():
         "config": {"workload": cfg["name"], "k": k, "pam": cfg["pam"], "spacers_per_gpu": n, "genome_bp": G,
                    "L": L, "pam_gate": bool(args.gate), "parallelism": (f"library-shard x{world}, genome replicated" if shard == "library" else
                                            f"genome-range x{world}, library replicated"),
-                   "seed_scheme": f"b={st['blocks']} blocks, {combos} combinations, path={st['path']}",
+                   "seed_scheme": f"b={st['blocks']} blocks, {combos} combinations, key<={st['key_nt']} nt, path={st['path']}",
                    "l2": "working set (window records + index) is far larger than the 126 MB L2; no flush needed",
                    "hits_per_step": int(total_hits)},
         "e2e": {"value": e2e_value, "unit": "guides*Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

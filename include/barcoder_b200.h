@@ -63,8 +63,9 @@ typedef struct {
                            which the host resolves).  Off = bowtie's full hit set.      */
 
 /* bc_set_param keys */
-#define BC_PARAM_BLOCKS 1     /* pigeonhole blocks b (k+1 <= b <= k+4); 0 = choose        */
-#define BC_PARAM_PATH 2       /* 0 auto, 1 probe kernel, 2 bucket-join kernel             */
+#define BC_PARAM_BLOCKS 1     /* force a block scheme: pigeonhole blocks b (k+1 <= b <= k+4); 0 = choose */
+#define BC_PARAM_PATH 2       /* 0 auto, 1 probe kernel, 2 bucket-join kernel (16-byte window records),
+                                 3 compact bucket-join kernel (8-byte window records, short spacers) */
 #define BC_PARAM_COUNT_CANDIDATES 3 /* 1 = count verified candidates into bc_stats        */
 #define BC_PARAM_HIT_CAPACITY 4     /* initial hit-buffer capacity (records)              */
 #define BC_PARAM_SPACER_ID_BASE 5   /* added to every spacer_id (global ids of a library shard) */
@@ -72,6 +73,8 @@ typedef struct {
                                        context scans only its 1/world slice of window starts  */
 #define BC_PARAM_WINDOW_SORT 7       /* bucket-join path, genome-side sort: 0 auto, 1 direct scatter,
                                         2 two-pass shared-memory radix scatter                    */
+#define BC_PARAM_KEY_NT 9            /* force a seed covering design with keys of this many bases (a row of
+                                        the compiled-in design table for this L and k); 0 = choose      */
 #define BC_PARAM_JOIN_CHUNK 8        /* bucket-join path: upper bound on the window positions sorted per
                                         pass over the genome (0 = as many as the workspace holds); the
                                         passes append to one hit buffer                              */
@@ -81,9 +84,9 @@ typedef struct {
     uint64_t library_spacers; /* n                                                   */
     uint32_t spacer_len;      /* L                                                   */
     uint32_t k;
-    uint32_t blocks;          /* b actually used                                     */
-    uint32_t combos;          /* C(b, k) seed combinations                           */
-    uint32_t path;            /* 1 probe, 2 join                                     */
+    uint32_t blocks;          /* b of the block scheme in use, 0 for a covering design */
+    uint32_t combos;          /* seed combinations (C(b, k) for a block scheme)      */
+    uint32_t path;            /* 1 probe, 2 join, 3 compact join                     */
     uint32_t scan_launches;   /* kernels launched by the last bc_search              */
     uint64_t hits;            /* records produced by the last bc_search              */
     uint64_t candidates;      /* verified (window, entry) pairs, if counting enabled */
@@ -95,7 +98,8 @@ typedef struct {
     float ms_scan_kernel;     /* device time of the verify kernel(s) only            */
     float ms_genome_bucket;   /* join path: device time of the genome bucketing kernels */
     uint32_t index_launches;  /* kernels launched by the last bc_build_index          */
-    uint32_t reserved[6];
+    uint32_t key_nt;          /* longest seed key of the scheme in use (bases)        */
+    uint32_t reserved[5];
 } bc_stats;
 
 int bc_abi_version(void);

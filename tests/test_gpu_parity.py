@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gpu(genome, off, lib, k, pam="", direction="downstream", iupac=False, gate=False, blocks=0, path=0,
-            hit_cap=0, window_sort=0):
+            hit_cap=0, window_sort=0, key_nt=0, join_chunk=0):
     with _native.Searcher(0) as s:
         s.set_genome_array(genome, off)
         s.set_library(lib)
@@ -25,6 +25,10 @@ def run_gpu(genome, off, lib, k, pam="", direction="downstream", iupac=False, ga
             s.set_param(_native.BC_PARAM_HIT_CAPACITY, hit_cap)
         if window_sort:
             s.set_param(_native.BC_PARAM_WINDOW_SORT, window_sort)
+        if key_nt:
+            s.set_param(_native.BC_PARAM_KEY_NT, key_nt)
+        if join_chunk:
+            s.set_param(_native.BC_PARAM_JOIN_CHUNK, join_chunk)
         n = s.search(k)
         hits = s.hits()
         assert len(hits) == n
@@ -290,3 +294,75 @@ def test_join_radix_window_sort_short_keys_and_dense_slots():
     gpu, st = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=2, window_sort=2)
     assert len(ref) > 100000
     assert_same(gpu, ref)
+
+
+# ------------------------------------------------ compact bucket join (8-byte window records, path 3)
+@pytest.mark.parametrize("k,blocks", [(0, 1), (0, 3), (1, 2), (1, 4), (2, 3), (2, 5), (3, 4), (3, 5), (3, 6), (3, 7)])
+@pytest.mark.parametrize("L", [12, 17, 20])
+def test_cjoin_every_block_scheme(k, blocks, L):
+    genome, off, lib = small_case(L, k, seed=17 * blocks + k + L, n=400, G=90000)
+    ref = run_oracle(genome, off, lib, k, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, k, pam="NGG", blocks=blocks, path=3)
+    assert st["blocks"] == blocks and st["path"] == 3
+    assert_same(gpu, ref)
+
+
+@pytest.mark.parametrize("path", [1, 2, 3])
+@pytest.mark.parametrize("key_nt", [9, 10])
+def test_covering_designs_every_path(path, key_nt):
+    """Seed covering designs (bc_designs.inc) instead of block schemes: L=20, k=3, keys of 9 / 10 nt.
+    Same records from the probe kernel, the 16-byte join and the compact join."""
+    genome, off, lib = small_case(20, 3, seed=900 + key_nt, n=3000, G=400000, n_contigs=5, nfrac=0.004)
+    ref = run_oracle(genome, off, lib, 3, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, 3, pam="NGG", key_nt=key_nt, path=path)
+    assert st["blocks"] == 0 and st["key_nt"] == key_nt and st["path"] == path
+    assert st["combos"] == {9: 12, 10: 15}[key_nt]
+    assert_same(gpu, ref)
+
+
+@pytest.mark.parametrize("gate", [False, True])
+@pytest.mark.parametrize("key_nt,blocks", [(0, 5), (9, 0), (10, 0), (0, 6)])
+def test_cjoin_medium_multi_chunk_bins(gate, key_nt, blocks):
+    """Several 8192-record chunks per bin, chunks straddling bins, ragged tiles, N runs, PAM gate,
+    two forced passes over the genome."""
+    genome, off = synth.random_genome(3_000_000, seed=151, n_contigs=9, n_fraction=0.003)
+    lib = synth.random_library(200000, 20, seed=152)
+    synth.plant(lib, genome, 0.2, 3, seed=153)
+    ref = run_oracle(genome, off, lib, 3, pam="NGG", gate=gate)
+    gpu, st = run_gpu(genome, off, lib, 3, pam="NGG", gate=gate, blocks=blocks, key_nt=key_nt, path=3)
+    assert st["path"] == 3
+    assert_same(gpu, ref)
+    gpu2, _ = run_gpu(genome, off, lib, 3, pam="NGG", gate=gate, blocks=blocks, key_nt=key_nt, path=3,
+                      join_chunk=1_700_001)
+    assert_same(gpu2, ref)
+
+
+def test_cjoin_dense_slots_duplicates_and_big_buckets():
+    """Huge slots and buckets (4-nt keys), duplicate spacers, short spacers."""
+    genome, off = synth.random_genome(300000, seed=161, n_contigs=3, n_fraction=0.01, n_run=5)
+    lib = synth.random_library(3000, 8, seed=162, distinct=False)
+    ref = run_oracle(genome, off, lib, 1, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=3)
+    assert len(ref) > 100000 and st["path"] == 3
+    assert_same(gpu, ref)
+    lib = synth.random_library(300_000, 12, seed=172)
+    synth.plant(lib, genome, 0.05, 1, seed=173)
+    ref = run_oracle(genome, off, lib, 1, pam="NGG")
+    gpu, st = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=3)
+    assert_same(gpu, ref)
+
+
+def test_cjoin_hit_sink_and_overflow():
+    genome, off, lib = small_case(20, 2, seed=177, n=2000, G=200000)
+    ref = run_oracle(genome, off, lib, 2, pam="NGG")
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        s.set_param(_native.BC_PARAM_PATH, 3)
+        s.set_param(_native.BC_PARAM_HIT_CAPACITY, 16)
+        sink = np.zeros(len(ref), dtype=_native.HIT_DTYPE)
+        s.set_hit_sink(sink.ctypes.data, len(sink))
+        assert s.search(2) == len(ref)
+        assert_same(_native.canonical_sort(sink.copy()), ref)
+        assert s.stats()["path"] == 3
