@@ -224,7 +224,11 @@ class BowtieRunner(Logger):
             pam_str, targeting = self._pam_columns(ci, start, L[sid] if len(hits) else L[:0])
             df["PAM"] = pam_str
             df["Targeting"] = targeting
-            df.attrs["pam_key"] = (self._pam_used[0].upper(), "class-api")
+            # "class-api" = the 3' slice PAMFinder.get_pam_seq uses for BOTH directions
+            # (PAMProcessor.py:69-87); an explicit set_pam(pam, "upstream") follows the script rule
+            # (5' side, targets.py:266-307) instead, and CRISPRiLibrary then re-annotates with its finder
+            df.attrs["pam_key"] = (self._pam_used[0].upper(),
+                                   "class-api" if self._pam_used[1] == "downstream" else "upstream")
         aligned = np.zeros(len(reads), dtype=bool)
         aligned[sid] = True
         missing = np.nonzero(~aligned)[0]
@@ -270,10 +274,17 @@ class BowtieRunner(Logger):
         if slow.any():
             pattern = re.compile(pam.replace("N", "[ATCG]"))
             minus = (meta & 1) != 0
+            upstream = self._pam_used[1] == "upstream"
             for j in np.nonzero(slow)[0]:
                 seq = self._contigs[ci[j]]
                 s0, e0 = int(start[j]), int(start[j] + lens[j])
-                s = reverse_complement(seq[s0 - P:s0]) if minus[j] else seq[e0:e0 + P]
+                if upstream:  # 5' side of the protospacer; a PAM that leaves the contig is no PAM (targets.py:266-307)
+                    if minus[j]:
+                        s = reverse_complement(seq[e0:e0 + P]) if e0 + P <= len(seq) else ""
+                    else:
+                        s = seq[s0 - P:s0] if s0 - P >= 0 else ""
+                else:
+                    s = reverse_complement(seq[s0 - P:s0]) if minus[j] else seq[e0:e0 + P]
                 pam_str[j] = s
                 targeting[j] = bool(pattern.search(s))
         return pam_str, targeting

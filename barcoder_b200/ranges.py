@@ -69,8 +69,11 @@ class PyRanges:
 
 def overlap_pairs(a, b):
     """All (i, j) with a.Chromosome[i] == b.Chromosome[j] and the half-open intervals overlapping.
-    Sweep per chromosome: b sorted by Start; candidates are b rows with Start < a.End, filtered
-    by End > a.Start through a running maximum of b's interval lengths."""
+    Sweep per chromosome and per LENGTH CLASS of b (powers of 4): within a class the b rows are
+    sorted by Start and the candidates of an a row are those with Start in
+    (a.Start - class max length, a.End), so a few very long intervals (the whole-contig `source`
+    feature GenBankParser.ranges always emits) cannot widen the window of the thousands of short
+    ones: the expansion stays proportional to the number of real pairs."""
     if len(a) == 0 or len(b) == 0:
         return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
     li, ri = [], []
@@ -80,25 +83,29 @@ def overlap_pairs(a, b):
     b_s, b_e = b["Start"].to_numpy(dtype=np.int64), b["End"].to_numpy(dtype=np.int64)
     for chrom in pd.unique(a_chr):
         ia = np.nonzero(a_chr == chrom)[0]
-        ib = np.nonzero(b_chr == chrom)[0]
-        if len(ib) == 0:
+        ib_all = np.nonzero(b_chr == chrom)[0]
+        if len(ib_all) == 0:
             continue
-        order = np.argsort(b_s[ib], kind="stable")
-        ib = ib[order]
-        bs, be = b_s[ib], b_e[ib]
-        max_len = int((be - bs).max()) if len(ib) else 0
-        # b rows that can overlap a row: Start in (a.Start - max_len, a.End)
-        lo = np.searchsorted(bs, a_s[ia] - max_len, side="right")
-        hi = np.searchsorted(bs, a_e[ia], side="left")
-        counts = np.maximum(hi - lo, 0)
-        if counts.sum() == 0:
-            continue
-        rep_a = np.repeat(np.arange(len(ia)), counts)
-        offs = np.arange(counts.sum()) - np.repeat(np.cumsum(counts) - counts, counts)
-        cand_b = np.repeat(lo, counts) + offs
-        ok = (be[cand_b] > a_s[ia][rep_a]) & (bs[cand_b] < a_e[ia][rep_a])
-        li.append(ia[rep_a[ok]])
-        ri.append(ib[cand_b[ok]])
+        blen = np.maximum(b_e[ib_all] - b_s[ib_all], 1)
+        cls = (np.log2(blen) // 2).astype(np.int64)
+        for c in np.unique(cls):
+            ib = ib_all[cls == c]
+            ib = ib[np.argsort(b_s[ib], kind="stable")]
+            bs, be = b_s[ib], b_e[ib]
+            max_len = int((be - bs).max())
+            # b rows that can overlap a row: Start in (a.Start - max_len, a.End)
+            lo = np.searchsorted(bs, a_s[ia] - max_len, side="right")
+            hi = np.searchsorted(bs, a_e[ia], side="left")
+            counts = np.maximum(hi - lo, 0)
+            total = int(counts.sum())
+            if total == 0:
+                continue
+            rep_a = np.repeat(np.arange(len(ia)), counts)
+            offs = np.arange(total) - np.repeat(np.cumsum(counts) - counts, counts)
+            cand_b = np.repeat(lo, counts) + offs
+            ok = (be[cand_b] > a_s[ia][rep_a]) & (bs[cand_b] < a_e[ia][rep_a])
+            li.append(ia[rep_a[ok]])
+            ri.append(ib[cand_b[ok]])
     if not li:
         return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
     li, ri = np.concatenate(li), np.concatenate(ri)

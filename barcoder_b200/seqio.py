@@ -318,7 +318,15 @@ def _read_genbank(handle):
             if line.startswith("ORIGIN"):
                 section = "origin"
                 continue
-            if line.startswith("CONTIG") or (line and not line.startswith(" ")):
+            if line.startswith("CONTIG"):
+                # CONTIG join(...) may wrap over several indented lines: everything up to ORIGIN / //
+                # belongs to it (Biopython keeps it as an annotation and does not parse it as features)
+                if cur:
+                    feats.append(_finish_feature(*cur))
+                    cur = None
+                section = "contig"
+                continue
+            if line and not line.startswith(" "):
                 continue
             key = line[5:21].strip()
             body = line[21:].strip()
@@ -331,6 +339,10 @@ def _read_genbank(handle):
                     cur[1] += body  # location continuation
                 else:
                     cur[2].append(body)
+            continue
+        if section == "contig":
+            if line.startswith("ORIGIN"):
+                section = "origin"
             continue
         if section == "origin":
             seq_chunks.append("".join(line.split()[1:]))

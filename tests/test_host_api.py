@@ -209,3 +209,50 @@ def test_bowtie_runner_call_order_errors(plasmids):
                 b.create_index()  # no CPU fallback
             assert ei.value.message == "Failed to index"
     assert not os.path.exists(b.fasta_path)  # temp dir removed on exit
+
+
+def test_overlap_join_with_whole_contig_source_feature_stays_linear():
+    """GenBankParser.ranges always emits a whole-contig `source` interval; it must not widen the
+    candidate window of the thousands of short gene intervals (quadratic blow-up)."""
+    import time
+    rng = np.random.default_rng(1)
+    n_genes, n_hits, G = 4500, 60_000, 4_600_000
+    gs = np.sort(rng.integers(0, G - 3000, n_genes))
+    b = pd.DataFrame({"Chromosome": "c1", "Start": np.concatenate([[0], gs]),
+                      "End": np.concatenate([[G], gs + rng.integers(200, 3000, n_genes)]),
+                      "Strand": "+", "Type": ["source"] + ["gene"] * n_genes})
+    hs = rng.integers(0, G - 20, n_hits)
+    a = pd.DataFrame({"Chromosome": "c1", "Start": hs, "End": hs + 20, "Strand": "+"})
+    t0 = time.time()
+    li, ri = overlap_pairs(a, b)
+    assert time.time() - t0 < 5.0
+    assert (ri == 0).sum() == n_hits                      # every hit joins the source feature
+    assert len(li) < 3 * n_hits                           # and only the genes it really overlaps
+    sub = np.arange(0, n_hits, 97)
+    bs, be = b["Start"].to_numpy(), b["End"].to_numpy()
+    want = {(int(i), int(j)) for i in sub for j in np.nonzero((bs < hs[i] + 20) & (be > hs[i]))[0]}
+    got = {(int(i), int(j)) for i, j in zip(li, ri) if i % 97 == 0}
+    assert got == want
+
+
+def test_genbank_wrapped_contig_line(tmp_path):
+    """A CONTIG join(...) that wraps over indented lines is not feature text."""
+    text = (
+        "LOCUS       TEST1                     24 bp    DNA     linear   BCT 01-JAN-2000\n"
+        "DEFINITION  test record.\n"
+        "VERSION     TEST1.1\n"
+        "FEATURES             Location/Qualifiers\n"
+        "     source          1..24\n"
+        "                     /organism=\"x\"\n"
+        "     gene            3..10\n"
+        "                     /locus_tag=\"T_1\"\n"
+        "CONTIG      join(AAAA01000001.1:1..1000,gap(100),AAAA01000002.1:1..2000,\n"
+        "            gap(50),AAAA01000003.1:1..500)\n"
+        "ORIGIN\n"
+        "        1 acgtacgtac gtacgtacgt acgt\n"
+        "//\n")
+    path = tmp_path / "wrapped.gb"
+    path.write_text(text)
+    recs = list(seqio.read_genbank(str(path)))
+    assert len(recs) == 1 and recs[0].id == "TEST1.1" and str(recs[0].seq) == "ACGT" * 6
+    assert [f.type for f in recs[0].features] == ["source", "gene"]
