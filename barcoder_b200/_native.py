@@ -27,6 +27,7 @@ BC_PARAM_SCAN_PART = 6
 BC_PARAM_WINDOW_SORT = 7
 BC_PARAM_JOIN_CHUNK = 8
 BC_PARAM_KEY_NT = 9
+BC_PARAM_SLOT_PART = 10
 PATH_AUTO, PATH_PROBE, PATH_JOIN, PATH_CJOIN = 0, 1, 2, 3
 
 META_PAM_OK = 1 << 3

@@ -45,11 +45,12 @@ struct bc_ctx {
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
     int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0, par_join_chunk = 0, par_key_nt = 0;
+    int64_t par_slot_rank = 0, par_slot_world = 1;
 
     // index
     bool have_index = false;
     int index_k = -1;
-    uint32_t b = 0, n_combos = 0, n_bins = 0;
+    uint32_t b = 0, n_combos = 0, n_bins = 0, slot_lo = 0, slot_hi = 0;
     uint32_t block_mask[BC_MAX_BLOCKS] = {0};
     ComboDesc combo[BC_MAX_COMBOS];
     uint64_t dir_slots = 0;
@@ -328,6 +329,11 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
         case BC_PARAM_WINDOW_SORT:
             if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "window sort must be 0, 1 or 2");
             ctx->par_window_sort = value; return BC_OK;
+        case BC_PARAM_SLOT_PART: {
+            const int64_t rank = value & 0xffff, world = (value >> 16) & 0xffff;
+            if (world < 1 || rank >= world) return fail(ctx, BC_EINVAL, "slot part must be rank | world << 16 with rank < world");
+            ctx->par_slot_rank = rank; ctx->par_slot_world = world; ctx->have_index = false; return BC_OK;
+        }
         case BC_PARAM_KEY_NT:
             if (value < 0 || value > BC_KEY_MAX_NT) return fail(ctx, BC_EINVAL, "key length must be 0..12");
             ctx->par_key_nt = value; ctx->have_index = false; return BC_OK;
@@ -605,6 +611,9 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     ip.n_entries = (uint32_t)E;
     ip.L = ctx->L;
     ip.lib_has_n = ctx->lib_has_n;
+    ip.slot_lo = (uint32_t)((s.dir_slots - 1) * (uint64_t)ctx->par_slot_rank / (uint64_t)ctx->par_slot_world);
+    ip.slot_hi = (uint32_t)((s.dir_slots - 1) * (uint64_t)(ctx->par_slot_rank + 1) / (uint64_t)ctx->par_slot_world);
+    ctx->slot_lo = ip.slot_lo; ctx->slot_hi = ip.slot_hi;
     ip.compact = path == 3 ? 1u : 0u;  // compact join: the index stores the non-key (rem) planes of every entry
     memcpy(ip.combo, ctx->combo, sizeof ip.combo);
     const uint32_t launches0 = bc_launch_counter;
@@ -630,6 +639,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->pos_begin = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)ctx->par_scan_rank / (uint64_t)ctx->par_scan_world);
     p->pos_end = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)(ctx->par_scan_rank + 1) / (uint64_t)ctx->par_scan_world);
     p->n_contigs = ctx->n_contigs;
+    p->slot_lo = ctx->slot_lo; p->slot_hi = ctx->slot_hi;
     p->sn = ctx->d_sn;
     p->lib_has_n = ctx->lib_has_n;
     p->L = ctx->L;

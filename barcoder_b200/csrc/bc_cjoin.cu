@@ -32,6 +32,7 @@ struct CBucketParams {
     uint32_t pos_begin, pos_end;  // dev positions handled by this pass over the genome
     uint32_t n_words;             // words per plane
     uint32_t L, n_combos, prune, gate_first;
+    uint32_t slot_lo, slot_hi;    // slot-range sharding
     uint32_t P, pam_dir, pam_sets[8];
     ComboDesc combo[BC_MAX_COMBOS];
 };
@@ -42,20 +43,49 @@ struct CBucketParams {
 #define CJ_MAX_BINS 1024                  // pass-A bins per combination (top_bits <= 10)
 #define CJ_MAX_SUB 4096                   // pass-B sub-slots per bin (low key bits <= 12)
 
+// --------------------------------------------------------------------------------- permutation
+// Key and rem planes of a window are bit gathers of its H / Lo planes.  Done run by run they cost
+// ~300 instructions per (window, combination) and made pass A issue-bound (ncu: 11.5e9 warp
+// instructions for 1.2e9 records); done through a byte-wise lookup table they cost ~10 per plane.
+// lut[c][b][v] = contribution of byte b (value v) of a plane word to the PERMUTED word of
+// combination c: key positions packed above the rem positions, both in ascending order.
+#define CJ_LUT_WORDS 1024
+__global__ void k_clut_build(const __grid_constant__ CBucketParams gp, uint32_t* __restrict__ lut) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= gp.n_combos * CJ_LUT_WORDS) return;
+    const ComboDesc& cd = gp.combo[g >> 10];
+    const uint32_t word = (g & 255u) << (8u * ((g >> 8) & 3u));
+    lut[g] = (bc_combo_gather_key(cd, word) << cd.rem_nt) | bc_combo_rem(cd, word);
+}
+
+__device__ __forceinline__ uint32_t cj_perm(const uint32_t* s_lut, uint32_t v, bool wide) {
+    uint32_t out = s_lut[v & 255u] | s_lut[256u + ((v >> 8) & 255u)] | s_lut[512u + ((v >> 16) & 255u)];
+    if (wide) out |= s_lut[768u + (v >> 24)];  // spacers longer than 24 nt
+    return out;
+}
+
 // ------------------------------------------------------------------------------------- count
 // One RED per (window, combination).  Grid (x = genome chunks, y = combination): the CTAs of one
 // combination run together, so its directory stays in L2.
-__global__ void __launch_bounds__(256) k_ccount(const __grid_constant__ CBucketParams gp, uint32_t* __restrict__ gdir) {
+__global__ void __launch_bounds__(256) k_ccount(const __grid_constant__ CBucketParams gp, const uint32_t* __restrict__ lut,
+                                                uint32_t* __restrict__ gdir) {
+    __shared__ uint32_t s_lut[CJ_LUT_WORDS];
     const uint32_t lm = bc_lmask(gp.L);
     const ComboDesc& cd = gp.combo[blockIdx.y];
+    if (!bc_combo_in_range(cd, gp.slot_lo, gp.slot_hi)) return;
+    for (uint32_t i = threadIdx.x; i < CJ_LUT_WORDS; i += blockDim.x) s_lut[i] = lut[blockIdx.y * CJ_LUT_WORDS + i];
+    __syncthreads();
+    const uint32_t rem_nt = cd.rem_nt, key_nt = cd.key_nt;
+    const bool wide = gp.L > 24;
     PamGate gate;
     bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
     for (uint32_t pos = gp.pos_begin + blockIdx.x * blockDim.x + threadIdx.x; pos < gp.pos_end;
          pos += gridDim.x * blockDim.x) {
         if (bc_window(gp.B, pos) & lm) continue;
         if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
-        const uint32_t wh = bc_window(gp.H, pos) & lm, wl = bc_window(gp.Lo, pos) & lm;
-        const uint32_t slot = cd.dir_off + bc_combo_key(cd, wh, wl);
+        const uint32_t ph = cj_perm(s_lut, bc_window(gp.H, pos) & lm, wide), pl = cj_perm(s_lut, bc_window(gp.Lo, pos) & lm, wide);
+        const uint32_t slot = cd.dir_off + (((ph >> rem_nt) << key_nt) | (pl >> rem_nt));
+        if (slot < gp.slot_lo || slot >= gp.slot_hi) continue;
         if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
         atomicAdd(&gdir[slot], 1u);
     }
@@ -106,6 +136,7 @@ __device__ __forceinline__ uint32_t cj_block_scan(uint32_t v, uint32_t* s_warp) 
 // windows: shared-memory histogram over the combination's bins, ONE global atomic per (chunk, bin),
 // records grouped by bin in shared memory and written out as runs.
 __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ CBucketParams gp,
+                                                        const uint32_t* __restrict__ lut,
                                                         uint32_t* __restrict__ bin_cursor, uint2* __restrict__ tmp) {
     extern __shared__ __align__(16) uint32_t cj_smem[];
     uint32_t* s_hist = cj_smem;                      // [CJ_MAX_BINS]
@@ -114,9 +145,11 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
     uint32_t* s_H = s_delta + CJ_MAX_BINS;           // [CJ_CHUNK / 32 + 2]
     uint32_t* s_L = s_H + (CJ_CHUNK / 32 + 2);
     uint32_t* s_warp = s_L + (CJ_CHUNK / 32 + 2);    // [CJ_THREADS / 32]
-    uint2* s_rec = reinterpret_cast<uint2*>(s_warp + CJ_THREADS / 32);  // [CJ_CHUNK]
+    uint32_t* s_lut = s_warp + CJ_THREADS / 32;      // [CJ_LUT_WORDS] permutation table of the current combination
+    uint2* s_rec = reinterpret_cast<uint2*>(s_lut + CJ_LUT_WORDS);  // [CJ_CHUNK]
     uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_rec + CJ_CHUNK);    // [CJ_CHUNK]
     const uint32_t lm = bc_lmask(gp.L);
+    const bool wide = gp.L > 24;
     PamGate gate;
     bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
     const uint32_t tid = threadIdx.x;
@@ -144,9 +177,12 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
         __syncthreads();
         for (uint32_t c = 0; c < gp.n_combos; c++) {
             const ComboDesc& cd = gp.combo[c];
+            if (!bc_combo_in_range(cd, gp.slot_lo, gp.slot_hi)) continue;  // block-uniform
             const uint32_t low = 2u * cd.key_nt - cd.top_bits, rem_nt = cd.rem_nt;
-            const uint32_t n_bins = 1u << cd.top_bits;
+            const uint32_t n_bins = 1u << cd.top_bits, key_nt = cd.key_nt;
+            const uint32_t rm = (1u << rem_nt) - 1u, low_mask = (1u << low) - 1u;
             for (uint32_t j = tid; j < n_bins; j += CJ_THREADS) s_hist[j] = 0;
+            for (uint32_t j = tid; j < CJ_LUT_WORDS; j += CJ_THREADS) s_lut[j] = lut[c * CJ_LUT_WORDS + j];
             __syncthreads();
             uint32_t x[CJ_ITEMS], rb[CJ_ITEMS];
 #pragma unroll
@@ -156,10 +192,12 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
                 const uint32_t t = sh0 + tid + (uint32_t)i * CJ_THREADS;  // bit offset inside the staged words
                 const uint32_t wh = __funnelshift_r(s_H[t >> 5], s_H[(t >> 5) + 1], t & 31u) & lm;
                 const uint32_t wl = __funnelshift_r(s_L[t >> 5], s_L[(t >> 5) + 1], t & 31u) & lm;
-                const uint32_t key = bc_combo_key(cd, wh, wl);
+                const uint32_t ph = cj_perm(s_lut, wh, wide), pl = cj_perm(s_lut, wl, wide);
+                const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
+                if (cd.dir_off + key < gp.slot_lo || cd.dir_off + key >= gp.slot_hi) continue;
                 if (gp.prune && gp.lib_dir[cd.dir_off + key] == gp.lib_dir[cd.dir_off + key + 1]) continue;
                 const uint32_t bin = key >> low;
-                x[i] = ((key & ((1u << low) - 1u)) << (2u * rem_nt)) | (bc_combo_rem(cd, wl) << rem_nt) | bc_combo_rem(cd, wh);
+                x[i] = ((key & low_mask) << (2u * rem_nt)) | ((pl & rm) << rem_nt) | (ph & rm);
                 rb[i] = atomicAdd(&s_hist[bin], 1u) | (bin << 16);
             }
             __syncthreads();
@@ -680,10 +718,15 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     memcpy(gp.combo, p.combo, sizeof gp.combo);
     gp.prune = p.dir_entries < (dir_slots - 1) * 2 ? 1u : 0u;
     gp.gate_first = p.gate_first;
+    gp.slot_lo = p.slot_lo; gp.slot_hi = p.slot_hi;
     gp.P = p.P; gp.pam_dir = p.pam_dir;
     for (int i = 0; i < 8; i++) gp.pam_sets[i] = p.pam_sets[i];
 
-    const size_t smem_a = (3 * CJ_MAX_BINS + 2 * (CJ_CHUNK / 32 + 2) + CJ_THREADS / 32) * 4 + (size_t)CJ_CHUNK * 8 +
+    if (!ws.d_lut) JCK(cudaMalloc(&ws.d_lut, (size_t)BC_MAX_COMBOS * CJ_LUT_WORDS * sizeof(uint32_t)));
+    k_clut_build<<<(p.n_combos * CJ_LUT_WORDS + 255) / 256, 256, 0, st>>>(gp, ws.d_lut);
+    JCK(cudaGetLastError());
+    bc_launch_counter += 1;
+    const size_t smem_a = (3 * CJ_MAX_BINS + 2 * (CJ_CHUNK / 32 + 2) + CJ_THREADS / 32 + CJ_LUT_WORDS) * 4 + (size_t)CJ_CHUNK * 8 +
                           (size_t)CJ_CHUNK * 2;
     const uint32_t max_sub = 1u << max_low;
     const size_t smem_b = (3 * (size_t)max_sub + CJ_THREADS / 32) * 4 + (size_t)CJ_CHUNK * 8;
@@ -702,7 +745,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         if (gx > maxb) gx = maxb;
         JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
         JCK(cudaEventRecord(ws.ev_c, st));
-        k_ccount<<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_gdir);
+        k_ccount<<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_lut, ws.d_gdir);
         JCK(cudaGetLastError());
         JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
         if (!one_pass) JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
@@ -710,7 +753,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         JCK(cudaGetLastError());
         uint32_t bx = (npos + CJ_CHUNK - 1) / CJ_CHUNK;
         if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
-        k_cbin<<<bx, CJ_THREADS, smem_a, st>>>(gp, d_bin_cursor, one_pass ? d_win : d_tmp);
+        k_cbin<<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, one_pass ? d_win : d_tmp);
         JCK(cudaGetLastError());
         bc_launch_counter += 3;
         if (!one_pass) {

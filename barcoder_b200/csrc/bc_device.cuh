@@ -50,6 +50,7 @@ struct SearchParams {
     uint32_t n_pos;             // dev positions (bases + separators)
     uint32_t n_words;           // words per plane (whole tiles + padding, bc_api.cu)
     uint32_t pos_begin, pos_end;  // window start positions this context scans (genome-range sharding)
+    uint32_t slot_lo, slot_hi;    // directory slots this context owns (slot-range sharding; everything = [0, all slots))
     uint32_t n_contigs;
     // library
     const uint32_t* sn;         // [n] spacer-orientation mask of non-ACGT spacer characters
@@ -76,6 +77,11 @@ struct SearchParams {
     uint32_t spacer_id_base;
 };
 
+// slot-range sharding: does a combination own any slot of [lo, hi)?
+__device__ __forceinline__ bool bc_combo_in_range(const ComboDesc& cd, uint32_t lo, uint32_t hi) {
+    return cd.dir_off < hi && cd.dir_off + (1u << (2u * cd.key_nt)) > lo;
+}
+
 __device__ __forceinline__ uint32_t bc_lmask(uint32_t n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
 // L-bit window of a plane starting at dev position pos (needs words pos>>5 and (pos>>5)+1).
@@ -84,13 +90,21 @@ __device__ __forceinline__ uint32_t bc_window(const uint32_t* __restrict__ plane
     return __funnelshift_r(plane[w], plane[w + 1], pos & 31u);
 }
 
-__device__ __forceinline__ uint32_t bc_combo_key(const ComboDesc& cd, uint32_t h, uint32_t l) {
-    uint32_t key = 0;
+// The key bits of a plane word, packed to the low key_nt bits (ascending position order).
+__device__ __forceinline__ uint32_t bc_combo_gather_key(const ComboDesc& cd, uint32_t v) {
+    uint32_t out = 0, acc = 0;
     for (uint32_t i = 0; i < cd.n_pieces; i++) {
-        uint32_t len = cd.len[i], st = cd.start[i], m = (1u << len) - 1u;
-        key = (key << (2 * len)) | (((h >> st) & m) << len) | ((l >> st) & m);
+        const uint32_t len = cd.len[i];
+        out |= ((v >> cd.start[i]) & ((1u << len) - 1u)) << acc;
+        acc += len;
     }
-    return key;
+    return out;
+}
+
+// Seed key of a window / query under a combination: the key positions of the hi plane above those
+// of the lo plane.  Any bijection works as long as the library index and the genome side agree.
+__device__ __forceinline__ uint32_t bc_combo_key(const ComboDesc& cd, uint32_t h, uint32_t l) {
+    return (bc_combo_gather_key(cd, h) << cd.key_nt) | bc_combo_gather_key(cd, l);
 }
 
 // The non-key bits of a plane word, packed to the low rem_nt bits (ascending position order).

@@ -30,6 +30,7 @@ struct BucketParams {
     const uint32_t* lib_dir;      // library directory (to skip windows whose bucket is empty)
     uint32_t pos_begin, pos_end;  // dev positions handled by this chunk of the genome
     uint32_t L, n_combos, prune, gate_first;
+    uint32_t slot_lo, slot_hi;    // slot-range sharding
     uint32_t P, pam_dir, pam_sets[8];
     ComboDesc combo[BC_MAX_COMBOS];
 };
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
     const uint32_t lm = bc_lmask(gp.L);
     const uint32_t c = blockIdx.y;
     const ComboDesc& cd = gp.combo[c];
+    if (!bc_combo_in_range(cd, gp.slot_lo, gp.slot_hi)) return;
     PamGate gate;
     bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
     for (uint32_t pos = gp.pos_begin + blockIdx.x * blockDim.x + threadIdx.x; pos < gp.pos_end;
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(256) k_bucket(const __grid_constant__ BucketPa
         if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
         const uint32_t wh = bc_window(gp.H, pos) & lm, wl = bc_window(gp.Lo, pos) & lm;
         const uint32_t slot = cd.dir_off + bc_combo_key(cd, wh, wl);
+        if (slot < gp.slot_lo || slot >= gp.slot_hi) continue;
         if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
         if (PASS == 0) {
             atomicAdd(&gdir_or_cursor[slot], 1u);
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS) k_window_bin(const _
         }
         for (uint32_t c = 0; c < gp.n_combos; c++) {
             const ComboDesc& cd = gp.combo[c];
+            if (!bc_combo_in_range(cd, gp.slot_lo, gp.slot_hi)) continue;  // block-uniform
             const uint32_t bin0 = cd.dir_off >> 8;
             s_hist[tid] = 0;
             __syncthreads();
@@ -148,6 +152,7 @@ __global__ void __launch_bounds__(RB_THREADS, RB_MINBLOCKS) k_window_bin(const _
                 slot[i] = 0xffffffffu;
                 if (!((ok >> i) & 1u)) continue;
                 const uint32_t sl = cd.dir_off + bc_combo_key(cd, wh[i], wl[i]);
+                if (sl < gp.slot_lo || sl >= gp.slot_hi) continue;
                 if (gp.prune && gp.lib_dir[sl] == gp.lib_dir[sl + 1]) continue;
                 slot[i] = sl;
                 rank[i] = atomicAdd(&s_hist[(sl >> 8) - bin0], 1u);
@@ -629,6 +634,7 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_work) cudaFree(ws.d_work);
     if (ws.d_bin_cursor) cudaFree(ws.d_bin_cursor);
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
+    if (ws.d_lut) cudaFree(ws.d_lut);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
     if (ws.ev_c) cudaEventDestroy(ws.ev_c);
@@ -741,6 +747,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
     // Skipping windows whose library bucket is empty only pays when most buckets are empty.
     gp.prune = p.dir_entries < (dir_slots - 1) * 2 ? 1u : 0u;
     gp.gate_first = p.gate_first;
+    gp.slot_lo = p.slot_lo; gp.slot_hi = p.slot_hi;
     gp.P = p.P; gp.pam_dir = p.pam_dir;
     for (int i = 0; i < 8; i++) gp.pam_sets[i] = p.pam_sets[i];
 

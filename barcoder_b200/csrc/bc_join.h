@@ -12,6 +12,7 @@ struct JoinWorkspace {
     uint64_t bin_cap = 0;
     uint32_t* d_work = nullptr;      // per-slice chunk counters of the dense verify kernel (dynamic work distribution)
     uint32_t* d_scan_tmp = nullptr;
+    uint32_t* d_lut = nullptr;       // compact join: byte-wise bit-permutation tables, one per combination
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     uint64_t gdir_cap = 0, gwin_cap = 0, scan_tmp_cap = 0;
     float ms_join_kernels = 0;      // device time of the verify kernels of the last search

@@ -91,13 +91,16 @@ __global__ void __launch_bounds__(256) k_pack_library(const uint8_t* __restrict_
 // then scatter of the entries into key order.
 __global__ void __launch_bounds__(256) k_index_count(IndexParams ip, uint32_t* __restrict__ counts) {
     const ComboDesc cd = ip.combo[blockIdx.y];
+    if (!bc_combo_in_range(cd, ip.slot_lo, ip.slot_hi)) return;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ip.n_entries; e += gridDim.x * blockDim.x) {
         if (ip.lib_has_n) {
             uint32_t nm = ip.sn[e >> 1];
             if (e & 1u) nm = bc_rev_bits(nm, ip.L);
             if (nm & cd.key_mask) continue;  // a seed containing a non-ACGT base is never exact
         }
-        atomicAdd(&counts[cd.dir_off + bc_combo_key(cd, ip.qh[e], ip.ql[e])], 1u);
+        const uint32_t slot = cd.dir_off + bc_combo_key(cd, ip.qh[e], ip.ql[e]);
+        if (slot < ip.slot_lo || slot >= ip.slot_hi) continue;
+        atomicAdd(&counts[slot], 1u);
     }
 }
 
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(256) k_index_scatter(IndexParams ip, const __g
                                                        uint4* __restrict__ tmp) {
     const uint32_t c = blockIdx.y;
     const ComboDesc cd = ip.combo[c];
+    if (!bc_combo_in_range(cd, ip.slot_lo, ip.slot_hi)) return;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < ip.n_entries; e += gridDim.x * blockDim.x) {
         if (ip.lib_has_n) {
             uint32_t nm = ip.sn[e >> 1];
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(256) k_index_scatter(IndexParams ip, const __g
         }
         const uint32_t h = ip.qh[e], l = ip.ql[e];
         const uint32_t slot = cd.dir_off + bc_combo_key(cd, h, l);
+        if (slot < ip.slot_lo || slot >= ip.slot_hi) continue;
         const uint32_t dst = atomicAdd(&coarse_cursor[bc_coarse_of(pl, c, slot)], 1u);
         tmp[dst] = ip.compact ? make_uint4(bc_combo_rem(cd, h), bc_combo_rem(cd, l), e, slot) : make_uint4(h, l, e, slot);
     }
@@ -384,8 +389,10 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
                         eb[j] = ee[j] = 0;
                         if (have && c0 + j < p.n_combos) {
                             const uint32_t slot = p.combo[c0 + j].dir_off + bc_combo_key(p.combo[c0 + j], wh, wl);
-                            eb[j] = __ldg(p.dir + slot);
-                            ee[j] = __ldg(p.dir + slot + 1);
+                            if (slot >= p.slot_lo && slot < p.slot_hi) {  // slot-range sharding
+                                eb[j] = __ldg(p.dir + slot);
+                                ee[j] = __ldg(p.dir + slot + 1);
+                            }
                         }
                     }
                     if (have) probes += min((uint32_t)PROBE_BATCH, p.n_combos - c0);

@@ -75,6 +75,11 @@ typedef struct {
                                         2 two-pass shared-memory radix scatter                    */
 #define BC_PARAM_KEY_NT 9            /* force a seed covering design with keys of this many bases (a row of
                                         the compiled-in design table for this L and k); 0 = choose      */
+#define BC_PARAM_SLOT_PART 10         /* slot-range sharding (strong scaling of ONE library over several
+                                        GPUs): value = rank | world << 16.  Every context holds the whole
+                                        genome and library but indexes, sorts and verifies only its 1/world
+                                        range of the seed directory; the contexts' hit sets are disjoint and
+                                        their union is the whole result                                  */
 #define BC_PARAM_JOIN_CHUNK 8        /* bucket-join path: upper bound on the window positions sorted per
                                         pass over the genome (0 = as many as the workspace holds); the
                                         passes append to one hit buffer                              */

@@ -285,3 +285,30 @@ def test_join_dense_path_many_stages_and_tiles():
     # 4^6 slots per combination: ~146 entries (3 stages of 64) and ~732 windows (6 tiles of 128) per slot
     assert 2 * len(lib) / 4096 > 128 and len(genome) / 4096 > 384
     assert gpu.tobytes() == ref.tobytes()
+
+
+@pytest.mark.parametrize("path,key_nt", [(1, 0), (2, 0), (3, 0), (3, 9), (1, 10)])
+def test_slot_range_parts_equal_whole(path, key_nt):
+    """Slot-range sharding (BC_PARAM_SLOT_PART, the strong-scaling split of ONE library): every
+    context indexes / sorts / verifies only its range of the seed directory; the parts are disjoint
+    and their union is the whole hit set."""
+    genome, off = synth.random_genome(1_500_000, seed=81, n_contigs=5, n_fraction=0.002)
+    lib = synth.random_library(30_000, 20, seed=82)
+    synth.plant(lib, genome, 0.3, 3, seed=83)
+    lib[11, 4] = ord("N")
+    ref = oracle_search(genome, off, lib, 3, "NGG")
+    parts = []
+    for r in range(3):
+        with _native.Searcher(0) as s:
+            s.set_genome_array(genome, off)
+            s.set_library(lib)
+            s.set_pam("NGG")
+            s.set_param(_native.BC_PARAM_PATH, path)
+            if key_nt:
+                s.set_param(_native.BC_PARAM_KEY_NT, key_nt)
+            s.set_param(_native.BC_PARAM_SLOT_PART, r | (3 << 16))
+            s.search(3)
+            parts.append(s.hits())
+    assert sum(len(p) for p in parts) == len(ref)
+    assert _native.canonical_sort(np.concatenate(parts)).tobytes() == ref.tobytes()
+    assert all(len(p) > 0 for p in parts)
