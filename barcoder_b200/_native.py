@@ -28,6 +28,7 @@ BC_PARAM_WINDOW_SORT = 7
 BC_PARAM_JOIN_CHUNK = 8
 BC_PARAM_KEY_NT = 9
 BC_PARAM_SLOT_PART = 10
+BC_PARAM_INDEX_SORT = 11
 PATH_AUTO, PATH_PROBE, PATH_JOIN, PATH_CJOIN = 0, 1, 2, 3
 
 META_PAM_OK = 1 << 3

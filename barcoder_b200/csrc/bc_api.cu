@@ -45,7 +45,7 @@ struct bc_ctx {
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
     int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0, par_join_chunk = 0, par_key_nt = 0;
-    int64_t par_slot_rank = 0, par_slot_world = 1;
+    int64_t par_slot_rank = 0, par_slot_world = 1, par_index_sort = 0;
 
     // index
     bool have_index = false;
@@ -122,7 +122,7 @@ extern "C" int bc_create(bc_ctx** out, int device) {
         cudaStreamCreate(&ctx->stream) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
         cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev2) != cudaSuccess ||
         cudaEventCreate(&ctx->ev3) != cudaSuccess ||
-        cudaMalloc(&ctx->d_count, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_count, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_any_n, sizeof(uint32_t)) != cudaSuccess) {
         g_create_err = std::string("CUDA context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx;
@@ -334,6 +334,9 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
             if (world < 1 || rank >= world) return fail(ctx, BC_EINVAL, "slot part must be rank | world << 16 with rank < world");
             ctx->par_slot_rank = rank; ctx->par_slot_world = world; ctx->have_index = false; return BC_OK;
         }
+        case BC_PARAM_INDEX_SORT:
+            if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "index sort must be 0, 1 or 2");
+            ctx->par_index_sort = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_KEY_NT:
             if (value < 0 || value > BC_KEY_MAX_NT) return fail(ctx, BC_EINVAL, "key length must be 0..12");
             ctx->par_key_nt = value; ctx->have_index = false; return BC_OK;
@@ -619,8 +622,12 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     const uint32_t launches0 = bc_launch_counter;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (!ctx->d_coarse_cursor) CK(cudaMalloc(&ctx->d_coarse_cursor, ((size_t)BC_MAX_COMBOS << BC_COARSE_BITS) * 4 + 4));
-    CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_tmp,
-                             ctx->d_coarse_cursor, ctx->d_ent_hl, ctx->d_ent_id, ctx->sm_count, ctx->stream));
+    if (ip.compact && ctx->par_index_sort != 1)  // the two radix passes of the compact window sort, applied to the entries
+        CK(bc_cindex_build(ctx->join, ip, s.n_combos, s.n_bins, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp,
+                           reinterpret_cast<uint2*>(ctx->d_ent_tmp), ctx->d_ent_hl, ctx->d_ent_id, ctx->sm_count, ctx->stream));
+    else
+        CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_tmp,
+                                 ctx->d_coarse_cursor, ctx->d_ent_hl, ctx->d_ent_id, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev0, ctx->ev1));
@@ -696,7 +703,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
     for (int attempt = 0; attempt < 3; attempt++) {
         SearchParams p;
         fill_params(ctx, &p);
-        CK(cudaMemsetAsync(ctx->d_count, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_count, 0, 8 * sizeof(unsigned long long), ctx->stream));
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         uint32_t launches = 0;
         ctx->sink.copied = ctx->sink.reported = 0;

@@ -34,6 +34,11 @@ struct CBucketParams {
     uint32_t L, n_combos, prune, gate_first;
     uint32_t slot_lo, slot_hi;    // slot-range sharding
     uint32_t P, pam_dir, pam_sets[8];
+    // library-side sort (index build): entries instead of genome windows
+    const uint32_t* qh;
+    const uint32_t* ql;
+    const uint32_t* sn;
+    uint32_t n_entries, lib_has_n;
     ComboDesc combo[BC_MAX_COMBOS];
 };
 
@@ -67,6 +72,7 @@ __device__ __forceinline__ uint32_t cj_perm(const uint32_t* s_lut, uint32_t v, b
 // ------------------------------------------------------------------------------------- count
 // One RED per (window, combination).  Grid (x = genome chunks, y = combination): the CTAs of one
 // combination run together, so its directory stays in L2.
+template <bool LIB>
 __global__ void __launch_bounds__(256) k_ccount(const __grid_constant__ CBucketParams gp, const uint32_t* __restrict__ lut,
                                                 uint32_t* __restrict__ gdir) {
     __shared__ uint32_t s_lut[CJ_LUT_WORDS];
@@ -77,6 +83,20 @@ __global__ void __launch_bounds__(256) k_ccount(const __grid_constant__ CBucketP
     __syncthreads();
     const uint32_t rem_nt = cd.rem_nt, key_nt = cd.key_nt;
     const bool wide = gp.L > 24;
+    if (LIB) {  // library entries (index build)
+        for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < gp.n_entries; e += gridDim.x * blockDim.x) {
+            if (gp.lib_has_n) {
+                uint32_t nm = gp.sn[e >> 1];
+                if (e & 1u) nm = bc_rev_bits(nm, gp.L);
+                if (nm & cd.key_mask) continue;  // a seed containing a non-ACGT base is never exact
+            }
+            const uint32_t ph = cj_perm(s_lut, gp.qh[e], wide), pl = cj_perm(s_lut, gp.ql[e], wide);
+            const uint32_t slot = cd.dir_off + (((ph >> rem_nt) << key_nt) | (pl >> rem_nt));
+            if (slot < gp.slot_lo || slot >= gp.slot_hi) continue;
+            atomicAdd(&gdir[slot], 1u);
+        }
+        return;
+    }
     PamGate gate;
     bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
     for (uint32_t pos = gp.pos_begin + blockIdx.x * blockDim.x + threadIdx.x; pos < gp.pos_end;
@@ -135,6 +155,9 @@ __device__ __forceinline__ uint32_t cj_block_scan(uint32_t v, uint32_t* s_warp) 
 // plane words are staged in shared memory, and then every combination in turn bins the chunk's
 // windows: shared-memory histogram over the combination's bins, ONE global atomic per (chunk, bin),
 // records grouped by bin in shared memory and written out as runs.
+// LIB = true sorts the library entries instead (index build): "position" = entry number, the planes
+// are the query planes qh / ql, and an entry whose key touches a non-ACGT spacer character is skipped.
+template <bool LIB>
 __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ CBucketParams gp,
                                                         const uint32_t* __restrict__ lut,
                                                         uint32_t* __restrict__ bin_cursor, uint2* __restrict__ tmp) {
@@ -153,26 +176,32 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
     PamGate gate;
     bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
     const uint32_t tid = threadIdx.x;
-    for (uint64_t c0 = (uint64_t)gp.pos_begin + (uint64_t)blockIdx.x * CJ_CHUNK; c0 < gp.pos_end;
-         c0 += (uint64_t)gridDim.x * CJ_CHUNK) {
+    const uint64_t src_begin = LIB ? 0ull : (uint64_t)gp.pos_begin, src_end = LIB ? (uint64_t)gp.n_entries : (uint64_t)gp.pos_end;
+    for (uint64_t c0 = src_begin + (uint64_t)blockIdx.x * CJ_CHUNK; c0 < src_end; c0 += (uint64_t)gridDim.x * CJ_CHUNK) {
         // plane words of the chunk (+ the word after it: a window spans two words).  The chunk
         // need not start on a word boundary: word 0 of the stage is word c0 >> 5 of the plane.
         const uint32_t w0 = (uint32_t)(c0 >> 5), sh0 = (uint32_t)(c0 & 31u);
         __syncthreads();
-        for (uint32_t i = tid; i < CJ_CHUNK / 32 + 2; i += CJ_THREADS) {
-            const uint32_t w = min(w0 + i, gp.n_words - 1u);  // the planes are padded by less than a chunk
-            s_H[i] = gp.H[w];
-            s_L[i] = gp.Lo[w];
-        }
         uint32_t ok = 0;
+        if (!LIB) {
+            for (uint32_t i = tid; i < CJ_CHUNK / 32 + 2; i += CJ_THREADS) {
+                const uint32_t w = min(w0 + i, gp.n_words - 1u);  // the planes are padded by less than a chunk
+                s_H[i] = gp.H[w];
+                s_L[i] = gp.Lo[w];
+            }
 #pragma unroll
-        for (int i = 0; i < CJ_ITEMS; i++) {
-            const uint64_t pos64 = c0 + tid + (uint32_t)i * CJ_THREADS;
-            if (pos64 >= gp.pos_end) continue;
-            const uint32_t pos = (uint32_t)pos64;
-            if (bc_window(gp.B, pos) & lm) continue;
-            if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
-            ok |= 1u << i;
+            for (int i = 0; i < CJ_ITEMS; i++) {
+                const uint64_t pos64 = c0 + tid + (uint32_t)i * CJ_THREADS;
+                if (pos64 >= gp.pos_end) continue;
+                const uint32_t pos = (uint32_t)pos64;
+                if (bc_window(gp.B, pos) & lm) continue;
+                if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
+                ok |= 1u << i;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CJ_ITEMS; i++)
+                if (c0 + tid + (uint32_t)i * CJ_THREADS < src_end) ok |= 1u << i;
         }
         __syncthreads();
         for (uint32_t c = 0; c < gp.n_combos; c++) {
@@ -189,13 +218,25 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
             for (int i = 0; i < CJ_ITEMS; i++) {
                 rb[i] = 0xffffffffu;
                 if (!((ok >> i) & 1u)) continue;
-                const uint32_t t = sh0 + tid + (uint32_t)i * CJ_THREADS;  // bit offset inside the staged words
-                const uint32_t wh = __funnelshift_r(s_H[t >> 5], s_H[(t >> 5) + 1], t & 31u) & lm;
-                const uint32_t wl = __funnelshift_r(s_L[t >> 5], s_L[(t >> 5) + 1], t & 31u) & lm;
+                uint32_t wh, wl;
+                if (!LIB) {
+                    const uint32_t t = sh0 + tid + (uint32_t)i * CJ_THREADS;  // bit offset inside the staged words
+                    wh = __funnelshift_r(s_H[t >> 5], s_H[(t >> 5) + 1], t & 31u) & lm;
+                    wl = __funnelshift_r(s_L[t >> 5], s_L[(t >> 5) + 1], t & 31u) & lm;
+                } else {
+                    const uint32_t e = (uint32_t)c0 + tid + (uint32_t)i * CJ_THREADS;
+                    if (gp.lib_has_n) {  // a seed containing a non-ACGT spacer character is never exact
+                        uint32_t nm = gp.sn[e >> 1];
+                        if (e & 1u) nm = bc_rev_bits(nm, gp.L);
+                        if (nm & cd.key_mask) continue;
+                    }
+                    wh = gp.qh[e];
+                    wl = gp.ql[e];
+                }
                 const uint32_t ph = cj_perm(s_lut, wh, wide), pl = cj_perm(s_lut, wl, wide);
                 const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
                 if (cd.dir_off + key < gp.slot_lo || cd.dir_off + key >= gp.slot_hi) continue;
-                if (gp.prune && gp.lib_dir[cd.dir_off + key] == gp.lib_dir[cd.dir_off + key + 1]) continue;
+                if (!LIB && gp.prune && gp.lib_dir[cd.dir_off + key] == gp.lib_dir[cd.dir_off + key + 1]) continue;
                 const uint32_t bin = key >> low;
                 x[i] = ((key & low_mask) << (2u * rem_nt)) | ((pl & rm) << rem_nt) | (ph & rm);
                 rb[i] = atomicAdd(&s_hist[bin], 1u) | (bin << 16);
@@ -252,12 +293,15 @@ __global__ void k_cchunk_bins(const uint32_t* __restrict__ bin_start, uint32_t n
 // regions is processed piece by piece.  Per piece: shared-memory histogram over the bin's
 // sub-slots (low key bits), one global atomic per (piece, sub-slot) on the slot cursor, records
 // grouped by sub-slot in shared memory and written to their final slots as runs.
+// LIB = true writes the library index instead of window records: ent_hl[dst] = {Rh, Rl}, ent_id[dst] = entry.
+template <bool LIB>
 __global__ void __launch_bounds__(CJ_THREADS, 2) k_cplace(const __grid_constant__ CBucketParams gp,
                                                           const uint2* __restrict__ tmp,
                                                           const uint32_t* __restrict__ bin_start,
                                                           const uint8_t* __restrict__ bin_combo,
                                                           const uint32_t* __restrict__ chunk_bin, uint32_t n_bins,
                                                           uint32_t* __restrict__ gcursor, uint2* __restrict__ gwin,
+                                                          uint32_t* __restrict__ out_id,
                                                           const uint32_t* __restrict__ n_rec_ptr,
                                                           uint32_t* __restrict__ work, uint32_t max_sub) {
     extern __shared__ __align__(16) uint32_t cj_smem[];
@@ -287,11 +331,20 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cplace(const __grid_constant_
             const uint32_t slot0 = cd.dir_off + ((g - cd.bin_off) << low);
             uint2 rec[CJ_ITEMS];
             uint32_t rank[CJ_ITEMS];
+            const uint32_t rem_nt = cd.rem_nt, rm = (1u << rem_nt) - 1u;
             if (low == 0) {  // the bin is one slot: a plain copy
 #pragma unroll
                 for (int i = 0; i < CJ_ITEMS; i++) {
                     const uint32_t idx = seg + tid + (uint32_t)i * CJ_THREADS;
-                    if (idx < s1) gwin[idx] = __ldcs(tmp + idx);
+                    if (idx < s1) {
+                        const uint2 r = __ldcs(tmp + idx);
+                        if (LIB) {
+                            gwin[idx] = make_uint2(r.y & rm, (r.y >> rem_nt) & rm);
+                            out_id[idx] = r.x;
+                        } else {
+                            gwin[idx] = r;
+                        }
+                    }
                 }
                 seg = s1;
                 continue;
@@ -330,11 +383,173 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cplace(const __grid_constant_
             const uint32_t n = s1 - seg;
             for (uint32_t i = tid; i < n; i += CJ_THREADS) {
                 const uint2 r = s_rec[i];
-                gwin[i + s_delta[r.y >> rem2]] = r;
+                const uint32_t dst = i + s_delta[r.y >> rem2];
+                if (LIB) {
+                    gwin[dst] = make_uint2(r.y & rm, (r.y >> rem_nt) & rm);
+                    out_id[dst] = r.x;
+                } else {
+                    gwin[dst] = r;
+                }
             }
             __syncthreads();
             seg = s1;
         }
+    }
+}
+
+// ------------------------------------------------------------------- pass B, bulk-async form
+// Same pass with the chunk loads taken off the critical path: a chunk of the pass-A output is one
+// contiguous run of bytes, so ONE elected thread fetches it with a 1-D bulk asynchronous copy
+// (cp.async.bulk.shared::cluster.global, completion on an mbarrier) into one half of a double
+// buffer while the CTA sorts the other half.  The chunk is sorted IN PLACE in its buffer (every
+// thread holds its records in registers between the two barriers), so the second buffer costs no
+// extra shared memory over the staged form above.  ncu on the staged form: 2.35 TB/s, long
+// scoreboard 15 warps per issue - load, sort and store of a chunk were serialised per CTA.
+__device__ __forceinline__ void pl_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void pl_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses to the buffer are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(gmem_src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void pl_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+
+template <bool LIB, int ITEMS>
+__global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(const __grid_constant__ CBucketParams gp,
+                                                                             const uint2* __restrict__ tmp,
+                                                                             const uint32_t* __restrict__ bin_start,
+                                                                             const uint8_t* __restrict__ bin_combo,
+                                                                             uint32_t n_bins, uint32_t* __restrict__ gcursor,
+                                                                             uint2* __restrict__ gwin, uint32_t* __restrict__ out_id,
+                                                                             const uint32_t* __restrict__ n_rec_ptr,
+                                                                             uint32_t* __restrict__ work, uint32_t max_sub) {
+    constexpr uint32_t CH = CJ_THREADS * ITEMS;
+    extern __shared__ __align__(128) uint32_t cj_smem[];
+    uint2* s_buf = reinterpret_cast<uint2*>(cj_smem);            // [2][CH] chunk double buffer (sorted in place)
+    uint32_t* s_hist = cj_smem + 4 * CH;                         // [max_sub]
+    uint32_t* s_lstart = s_hist + max_sub;                       // [max_sub]
+    uint32_t* s_delta = s_lstart + max_sub;                      // [max_sub]
+    uint32_t* s_warp = s_delta + max_sub;                        // [CJ_THREADS / 32]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_chunk[2];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_rec = *n_rec_ptr;
+    const uint32_t n_chunks = (uint32_t)(((uint64_t)n_rec + CH - 1) / CH);
+    if (tid == 0) {
+        pl_mbar_init(&s_bar[0], 1);
+        pl_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t ch = atomicAdd(work, 1u);
+        s_chunk[0] = ch;
+        if (ch < n_chunks) {
+            const uint32_t r0 = ch * CH, cnt = min(CH, n_rec - r0);
+            pl_bulk_load(s_buf, tmp + r0, (cnt * 8u + 15u) & ~15u, &s_bar[0]);
+        }
+    }
+    uint32_t cur = 0, parity0 = 0, parity1 = 0;
+    for (;;) {
+        __syncthreads();  // s_chunk[cur] is visible; everybody is done with buffer cur ^ 1
+        const uint32_t ch = s_chunk[cur];
+        if (ch >= n_chunks) break;
+        if (tid == 0) {   // fetch the next chunk into the other buffer while this one is sorted
+            const uint32_t nx = atomicAdd(work, 1u);
+            s_chunk[cur ^ 1u] = nx;
+            if (nx < n_chunks) {
+                const uint32_t r0n = nx * CH, cntn = min(CH, n_rec - r0n);
+                pl_bulk_load(s_buf + (cur ^ 1u) * CH, tmp + r0n, (cntn * 8u + 15u) & ~15u, &s_bar[cur ^ 1u]);
+            }
+        }
+        pl_mbar_wait(&s_bar[cur], cur ? parity1 : parity0);
+        if (cur) parity1 ^= 1u; else parity0 ^= 1u;
+        uint2* buf = s_buf + cur * CH;
+        const uint32_t r0 = ch * CH, r1 = r0 + min(CH, n_rec - r0);
+        // bin of the chunk's first record (one thread searches; chunks mostly lie inside one bin)
+        uint32_t g;
+        {
+            uint32_t lo = 0, hi = n_bins;  // bin_start[lo] <= r0 < bin_start[hi]
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(bin_start + mid) <= r0) lo = mid; else hi = mid;
+            }
+            g = lo;
+        }
+        uint32_t seg = r0;
+        while (seg < r1) {
+            while (g + 1 < n_bins && __ldg(bin_start + g + 1) <= seg) g++;  // skip empty bins
+            const uint32_t s1 = min(r1, __ldg(bin_start + g + 1));
+            const ComboDesc& cd = gp.combo[__ldg(bin_combo + g)];
+            const uint32_t low = 2u * cd.key_nt - cd.top_bits, rem2 = 2u * cd.rem_nt;
+            const uint32_t n_sub = 1u << low;
+            const uint32_t slot0 = cd.dir_off + ((g - cd.bin_off) << low);
+            const uint32_t rem_nt = cd.rem_nt, rm = (1u << rem_nt) - 1u;
+            uint2* sb = buf + (seg - r0);
+            const uint32_t n = s1 - seg;
+            if (low != 0) {
+                uint2 rec[ITEMS];
+                uint32_t rank[ITEMS];
+                for (uint32_t j = tid; j < n_sub; j += CJ_THREADS) s_hist[j] = 0;
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < ITEMS; i++) {
+                    const uint32_t idx = tid + (uint32_t)i * CJ_THREADS;
+                    if (idx < n) {
+                        rec[i] = sb[idx];
+                        rank[i] = atomicAdd(&s_hist[rec[i].y >> rem2], 1u);
+                    }
+                }
+                __syncthreads();  // every record of the piece is in registers: the buffer may be overwritten
+                {
+                    const uint32_t per = (n_sub + CJ_THREADS - 1) / CJ_THREADS;
+                    const uint32_t j0 = tid * per;
+                    uint32_t sum = 0;
+                    for (uint32_t j = 0; j < per; j++) sum += j0 + j < n_sub ? s_hist[j0 + j] : 0u;
+                    uint32_t run = cj_block_scan(sum, s_warp);
+                    for (uint32_t j = 0; j < per && j0 + j < n_sub; j++) {
+                        const uint32_t cnt = s_hist[j0 + j];
+                        s_lstart[j0 + j] = run;
+                        s_delta[j0 + j] = cnt ? atomicAdd(&gcursor[slot0 + j0 + j], cnt) - run : 0u;
+                        run += cnt;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < ITEMS; i++) {
+                    const uint32_t idx = tid + (uint32_t)i * CJ_THREADS;
+                    if (idx < n) sb[s_lstart[rec[i].y >> rem2] + rank[i]] = rec[i];
+                }
+                __syncthreads();
+            }
+            for (uint32_t i = tid; i < n; i += CJ_THREADS) {
+                const uint2 r = sb[i];
+                const uint32_t dst = low != 0 ? i + s_delta[r.y >> rem2] : seg + i;
+                if (LIB) {
+                    gwin[dst] = make_uint2(r.y & rm, (r.y >> rem_nt) & rm);
+                    out_id[dst] = r.x;
+                } else {
+                    gwin[dst] = r;
+                }
+            }
+            __syncthreads();
+            seg = s1;
+        }
+        cur ^= 1u;
     }
 }
 
@@ -343,7 +558,7 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cplace(const __grid_constant_
 #define CV_WARPS (CV_THREADS / 32)
 #define CV_ITEMS 4          // window records per lane per warp-tile (at most)
 #define CV_WQ 128           // per-warp candidate queue (entries)
-#define CV_GQ 96            // per-warp queue of groups awaiting re-examination (31 + 2 * 32)
+#define CV_GQ 160           // per-warp queue of {window, group} items awaiting re-examination (31 + 4 * 32 + 1)
 #define CV_STAGE 64         // library entries per shared-memory stage (x2 buffers per warp)
 #define CV_GROUP 8          // entries per group (one ballot per group)
 #ifndef CV_CHUNK_TILES
@@ -369,6 +584,9 @@ __device__ __forceinline__ uint32_t cv_combo_of_slot(const SearchParams& p, uint
 // lanes: mask back to query positions, ownership, PAM annotation, ONE global atomic for the batch,
 // coalesced store of the surviving records.
 static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint4* q, uint32_t n) {
+#ifdef CV_DEBUG_NO_RESOLVE  // timing experiment only: candidates are found but not turned into records
+    if (p.cap != 1) return;
+#endif
     const uint32_t lane = threadIdx.x & 31u;
     uint4 rec;
     bool ok = false;
@@ -411,48 +629,75 @@ __device__ __forceinline__ void cv_drain(const SearchParams& p, uint4* q, uint32
     __syncwarp();
 }
 
-// Second level: a queued GROUP {record of the lane that saw it, first entry, slot, end of the tile}
-// stands for CV_ITEMS x CV_GROUP pairs of which at least one passed the filter.  32 groups are
-// re-examined at once, one per lane, so the per-pair compare + branch runs with full lanes.
+// Second level.  A queue item {window planes (wh | wl << 16), record index, first entry of the group,
+// slot} stands for ONE window x CV_GROUP entries of which at least one pair passed the filter.
+// 32 items are re-examined at once, one per lane, so the per-pair compare + branch runs with full
+// lanes; the window comes from the queue (no record re-read), only passing pairs fetch their
+// position.  (The first version queued whole 4-window groups: at 9-10 nt keys 70-90 % of the groups
+// contain a passing pair somewhere in the warp, and re-reading their records cost 13 GB of random
+// sectors - ncu: 31.7 GB read for 11.5 GB algorithmic.)
 static __device__ __noinline__ void cv_resolve_groups(const SearchParams& p, const uint2* __restrict__ gwin,
                                                       const uint4* gq, uint32_t n, uint4* q, uint32_t* qn) {
     const uint32_t lane = threadIdx.x & 31u;
     const int k = (int)p.k;
     __syncwarp();
-    if (lane < n) {
-        const uint4 item = gq[lane];  // x record index, y first entry, z slot, w end of the tile (record index)
-        const uint32_t rem_nt = p.combo[cv_combo_of_slot(p, item.z)].rem_nt, rm = (1u << rem_nt) - 1u;
-        const uint32_t n_e = min((uint32_t)CV_GROUP, __ldg(p.dir + item.z + 1) - item.y);
-        uint2 w[CV_ITEMS];
-#pragma unroll
-        for (int it = 0; it < CV_ITEMS; it++) w[it] = __ldg(gwin + min(item.x + it * 32, item.w - 1));
+    const uint4 item = lane < n ? gq[lane] : make_uint4(0u, 0u, 0u, 0xffffffffu);  // x planes, y record index, z first entry, w slot
+    if (item.w != 0xffffffffu) {
+        const uint32_t wh = item.x & 0xffffu, wl = item.x >> 16;
+        const uint32_t n_e = min((uint32_t)CV_GROUP, __ldg(p.dir + item.w + 1) - item.z);
         for (uint32_t j = 0; j < n_e; j++) {
-            const uint2 qe = __ldg(p.ent_hl + item.y + j);
-#pragma unroll
-            for (int it = 0; it < CV_ITEMS; it++) {
-                const uint32_t m_ = ((w[it].y & rm) ^ qe.x) | (((w[it].y >> rem_nt) & rm) ^ qe.y);
-                if (item.x + it * 32 < item.w && __popc(m_) <= k) {
-                    const uint32_t qs = atomicAdd(qn, 1u);
-                    if (qs < CV_WQ) q[qs] = make_uint4(w[it].x, m_, item.y + j, item.z);
-                    else cv_overflow(p, w[it].x, m_, item.y + j, item.z);
-                }
+            const uint2 qe = __ldg(p.ent_hl + item.z + j);
+            const uint32_t m_ = (wh ^ qe.x) | (wl ^ qe.y);
+            if (__popc(m_) <= k) {
+                const uint32_t pos = __ldg(&gwin[item.y].x);
+                const uint32_t qs = atomicAdd(qn, 1u);
+                if (qs < CV_WQ) q[qs] = make_uint4(pos, m_, item.z + j, item.w);
+                else cv_overflow(p, pos, m_, item.z + j, item.w);
             }
         }
     }
     cv_drain(p, q, qn, lane);
 }
 
-// One warp-tile: `items` (1..CV_ITEMS, warp-uniform) resident windows per lane against the bucket
+// Hand n <= 32 queue items over to k_cfinish through the global item queue (one atomic, one coalesced
+// 16-byte store per lane).  Re-examining them inside the verify kernel cost it 45 % of its time
+// (timing experiment, cfg 4 at 9-nt keys: first level alone 22.6 ms, + second level 32.9 ms,
+// + hit resolution 39.1 ms): the dependent loads of the slow path stall warps that should be
+// feeding the POPC pipe.  If the queue is full the items are resolved here, as before.
+__device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* gq,
+                                               uint32_t n, uint4* q, uint32_t* qn) {
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long base = 0;
+    __syncwarp();
+    // always a whole batch of 32 (missing lanes carry a null item), so the accepted batches tile the
+    // queue without holes and k_cfinish can trust every item below min(counter, capacity)
+    if (lane == 0) base = atomicAdd(p.count + 4, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + 32ull <= p.item_cap) {
+        p.items[base + lane] = lane < n ? gq[lane] : make_uint4(0u, 0u, 0u, 0xffffffffu);
+        __syncwarp();
+    } else {
+        cv_resolve_groups(p, gwin, gq, n, q, qn);
+    }
+}
+
+// One warp-tile: `ITEMS` (1..CV_ITEMS, warp-uniform) resident windows per lane against the bucket
 // [ls, le) of the library index, staged through shared memory (cp.async, CV_STAGE entries per
 // stage, double buffered).  One group = CV_GROUP entries (16-byte broadcast LDS, two entries
-// each) x ITEMS windows, independent LOP3/LOP3/POPC chains folded with min, then ONE ballot; a lane
-// whose minimum passes only QUEUES the group.  1 pair in 8 is tested on the ALU pipe instead of
-// POPC (mismatch mask with its K lowest set bits cleared == 0): POPC alone saturates the XU pipe.
+// each) x ITEMS windows: independent LOP3/LOP3/POPC chains folded with min PER WINDOW, then one
+// ballot per window; a lane whose minimum passes only QUEUES {window, group}.  With CV_ALU_PAIRS,
+// 1 pair in 8 is tested on the ALU pipe instead of POPC (mismatch mask with its K lowest set bits
+// cleared == 0): POPC alone saturates the XU pipe.
+#ifndef CV_FINISH_KERNEL
+#define CV_FINISH_KERNEL 1   // second level + hit resolution in k_cfinish (global item queue) instead of inside k_cverify
+#endif
+#ifndef CV_ALU_PAIRS
+#define CV_ALU_PAIRS 1
+#endif
 template <int K, int ITEMS>
 __device__ __forceinline__ uint32_t cv_tile(const SearchParams& p, const uint2* __restrict__ gwin, const uint32_t (&wh)[CV_ITEMS],
                                             const uint32_t (&wl)[CV_ITEMS], uint32_t ls, uint32_t le, uint32_t first,
-                                            uint32_t tend, uint32_t slot, uint2* sbuf, uint4* gq, uint32_t gn, uint4* q,
-                                            uint32_t* qn) {
+                                            uint32_t slot, uint2* sbuf, uint4* gq, uint32_t gn, uint4* q, uint32_t* qn) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n_ent = le - ls;
@@ -482,35 +727,46 @@ __device__ __forceinline__ uint32_t cv_tile(const SearchParams& p, const uint2* 
         uint32_t g = 0;
         for (;;) {
             for (; g < ng && gn < 32; g++) {
-                int best_ = 33;
-                uint32_t rest_ = 0xffffffffu;
+                int best_[ITEMS];
+                uint32_t rest_[ITEMS];
+#pragma unroll
+                for (int it = 0; it < ITEMS; it++) { best_[it] = 33; rest_[it] = 1u; }
 #pragma unroll
                 for (int j = 0; j < CV_GROUP / 2; j++) {
                     const uint4 e2 = sb[g * (CV_GROUP / 2) + j];
 #pragma unroll
                     for (int it = 0; it < ITEMS; it++) {
-                        best_ = min(best_, __popc((wh[it] ^ e2.x) | (wl[it] ^ e2.y)));
-                        if (j == CV_GROUP / 2 - 1) {
+                        best_[it] = min(best_[it], __popc((wh[it] ^ e2.x) | (wl[it] ^ e2.y)));
+                        if (CV_ALU_PAIRS && j == CV_GROUP / 2 - 1) {
                             uint32_t m = (wh[it] ^ e2.z) | (wl[it] ^ e2.w);
 #pragma unroll
                             for (int cc = 0; cc < K; cc++) m &= m - 1u;
-                            rest_ = min(rest_, m);
+                            rest_[it] = m;
                         } else {
-                            best_ = min(best_, __popc((wh[it] ^ e2.z) | (wl[it] ^ e2.w)));
+                            best_[it] = min(best_[it], __popc((wh[it] ^ e2.z) | (wl[it] ^ e2.w)));
                         }
                     }
                 }
-                const bool pass_ = best_ <= K || rest_ == 0u;
-                const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_);
-                if (hit_) {  // warp-uniform
-                    if (pass_) gq[gn + __popc(hit_ & lt_mask)] = make_uint4(first + lane, ebase + g * CV_GROUP, slot, tend);
-                    gn += __popc(hit_);
+#pragma unroll
+                for (int it = 0; it < ITEMS; it++) {
+                    const bool pass_ = best_[it] <= K || rest_[it] == 0u;
+#ifdef CV_DEBUG_NO_SECOND  // timing experiment only: first level alone (no hits are produced)
+                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_) & (first == 0xffffffffu ? 1u : 0u);
+#else
+                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_);
+#endif
+                    if (hit_) {  // warp-uniform
+                        if (pass_)
+                            gq[gn + __popc(hit_ & lt_mask)] =
+                                make_uint4(wh[it] | (wl[it] << 16), first + it * 32 + lane, ebase + g * CV_GROUP, slot);
+                        gn += __popc(hit_);
+                    }
                 }
             }
             if (gn < 32) break;
-            do {  // warp-uniform; at most 31 + 32 groups are queued here
+            do {  // warp-uniform; at most 31 + 32 * ITEMS items are queued here
                 gn -= 32;
-                cv_resolve_groups(p, gwin, gq + gn, 32, q, qn);
+                cv_flush_items(p, gwin, gq + gn, 32, q, qn);
             } while (gn >= 32);
         }
         __syncwarp();  // every lane is done with this buffer before stage c+2 lands in it
@@ -609,23 +865,47 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
             const uint32_t n_win = tend - first;
             cand += (unsigned long long)(le - ls) * ((n_win + 31u - lane) / 32u);
             switch ((n_win + 31u) / 32u) {
-                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
-                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
-                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
-                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, ls, le, first, tend, slot, sbuf, gq, gn, q, qn); break;
+                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
+                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
+                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
+                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
             }
             cv_drain(p, q, qn, lane);
         }
     }
-    while (gn) {  // up to CV_GQ - 1 groups are still queued
+    while (gn) {  // up to CV_GQ - 1 items are still queued
         const uint32_t take = min(gn, 32u);
         gn -= take;
-        cv_resolve_groups(p, gwin, gq + gn, take, q, qn);
+        cv_flush_items(p, gwin, gq + gn, take, q, qn);
     }
     __syncwarp();
     const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
     if (nq) cv_resolve(p, q, nq);
     if (p.count_candidates) atomicAdd(p.count + 1, cand);
+}
+
+// Second level + hit resolution as a kernel of their own: every warp takes batches of 32 items of
+// the global queue, one per lane (8 entries each, tested against the item's window), queues the
+// passing pairs and resolves them 32 at a time (ownership, PAM, one atomic per batch).  All of it
+// is dependent random loads; here they overlap across ~10^8 items instead of stalling the POPC loop.
+__global__ void __launch_bounds__(CV_THREADS, 6) k_cfinish(const __grid_constant__ SearchParams p, const uint2* __restrict__ gwin) {
+    __shared__ uint4 s_q[CV_WARPS][CV_WQ];
+    __shared__ uint32_t s_qn[CV_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint4* q = s_q[warp];
+    uint32_t* qn = &s_qn[warp];
+    if (lane == 0) *qn = 0;
+    __syncwarp();
+    const unsigned long long queued = p.count[4];
+    const unsigned long long n_items = queued < p.item_cap ? queued : p.item_cap;  // whole batches of 32; item_cap is a multiple of 32
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * CV_WARPS;
+    for (unsigned long long b0 = ((unsigned long long)blockIdx.x * CV_WARPS + warp) * 32ull; b0 < n_items; b0 += n_warps * 32ull) {
+        const uint32_t n = (uint32_t)min(32ull, n_items - b0);
+        cv_resolve_groups(p, gwin, p.items + b0, n, q, qn);
+    }
+    __syncwarp();
+    const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
+    if (nq) cv_resolve(p, q, nq);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -634,6 +914,107 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
         cudaError_t e__ = (call);           \
         if (e__ != cudaSuccess) return e__; \
     } while (0)
+
+static cudaError_t cj_ensure_bins(JoinWorkspace& ws, uint32_t n_bins, uint64_t max_chunks) {
+    const uint64_t bin_words = 2ull * (n_bins + 2) + max_chunks + (n_bins + 8) / 4 + 4;
+    if (bin_words > ws.bin_cap) {
+        if (ws.d_bin_cursor) cudaFree(ws.d_bin_cursor);
+        ws.d_bin_cursor = nullptr;
+        ws.bin_cap = 0;
+        JCK(cudaMalloc(&ws.d_bin_cursor, bin_words * sizeof(uint32_t)));
+        ws.bin_cap = bin_words;
+    }
+    return cudaSuccess;
+}
+
+#ifndef CJ_PLACE_FORM
+#define CJ_PLACE_FORM 2   // pass B: 0 staged (LDG), 1 bulk-async with 4096-record chunks, 2 bulk-async with 8192-record chunks
+#endif
+template <bool LIB>
+static cudaError_t cj_launch_place(const CBucketParams& gp, const uint2* tmp, const uint32_t* bin_start, const uint8_t* bin_combo,
+                                   const uint32_t* chunk_bin, uint32_t n_bins, uint32_t* gcursor, uint2* out, uint32_t* out_id,
+                                   const uint32_t* n_rec_ptr, uint32_t* work, uint32_t max_sub, size_t smem_b, int sm_count,
+                                   cudaStream_t st) {
+    if (CJ_PLACE_FORM == 0) {
+        JCK(cudaFuncSetAttribute(k_cplace<LIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        k_cplace<LIB><<<(uint32_t)sm_count * 2u, CJ_THREADS, smem_b, st>>>(gp, tmp, bin_start, bin_combo, chunk_bin, n_bins, gcursor, out,
+                                                                        out_id, n_rec_ptr, work, max_sub);
+    } else if (CJ_PLACE_FORM == 1) {
+        const size_t smem = 2 * (size_t)CJ_THREADS * 8 * 8 + (3 * (size_t)max_sub + CJ_THREADS / 32) * 4;
+        JCK(cudaFuncSetAttribute(k_cplace_bulk<LIB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_cplace_bulk<LIB, 8><<<(uint32_t)sm_count * 2u, CJ_THREADS, smem, st>>>(gp, tmp, bin_start, bin_combo, n_bins, gcursor, out, out_id,
+                                                                              n_rec_ptr, work, max_sub);
+    } else {
+        const size_t smem = 2 * (size_t)CJ_THREADS * 16 * 8 + (3 * (size_t)max_sub + CJ_THREADS / 32) * 4;
+        JCK(cudaFuncSetAttribute(k_cplace_bulk<LIB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_cplace_bulk<LIB, 16><<<(uint32_t)sm_count, CJ_THREADS, smem, st>>>(gp, tmp, bin_start, bin_combo, n_bins, gcursor, out, out_id,
+                                                                           n_rec_ptr, work, max_sub);
+    }
+    return cudaGetLastError();
+}
+
+static size_t cj_smem_a() {
+    return (3 * CJ_MAX_BINS + 2 * (CJ_CHUNK / 32 + 2) + CJ_THREADS / 32 + CJ_LUT_WORDS) * 4 + (size_t)CJ_CHUNK * 8 +
+           (size_t)CJ_CHUNK * 2;
+}
+
+// Library index of the compact join path, built with the same two radix passes as the window sort:
+// count (RED) -> scan -> pass A (entries grouped by bin) -> pass B (final key order, written as
+// ent_hl = rem planes {Rh, Rl} and ent_id = entry).  `tmp` must hold one uint2 per (entry, combination).
+cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n_combos, uint32_t n_bins, uint32_t* d_dir,
+                            uint64_t dir_slots, uint32_t* d_cursor, uint32_t* d_scan_tmp, uint2* tmp, uint2* ent_hl,
+                            uint32_t* ent_id, int sm_count, cudaStream_t st) {
+    const uint32_t n_slots = (uint32_t)(dir_slots - 1);
+    JCK(cudaMemsetAsync(d_dir, 0, dir_slots * sizeof(uint32_t), st));
+    if (ip.n_entries == 0) return cudaSuccess;
+    CBucketParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.qh = ip.qh; gp.ql = ip.ql; gp.sn = ip.sn;
+    gp.n_entries = ip.n_entries;
+    gp.lib_has_n = ip.lib_has_n;
+    gp.L = ip.L;
+    gp.n_combos = n_combos;
+    gp.slot_lo = ip.slot_lo; gp.slot_hi = ip.slot_hi;
+    memcpy(gp.combo, ip.combo, sizeof gp.combo);
+    uint32_t max_low = 0;
+    for (uint32_t c = 0; c < n_combos; c++) {
+        const uint32_t low = 2u * gp.combo[c].key_nt - gp.combo[c].top_bits;
+        if (low > max_low) max_low = low;
+    }
+    const uint64_t max_chunks = ((uint64_t)ip.n_entries * n_combos + CJ_CHUNK - 1) / CJ_CHUNK + 1;
+    JCK(cj_ensure_bins(ws, n_bins, max_chunks));
+    uint32_t* d_bin_cursor = ws.d_bin_cursor;
+    uint32_t* d_bin_start = d_bin_cursor + (n_bins + 2);
+    uint32_t* d_chunk_bin = d_bin_start + (n_bins + 2);
+    uint8_t* d_bin_combo = reinterpret_cast<uint8_t*>(d_chunk_bin + max_chunks);
+    if (!ws.d_lut) JCK(cudaMalloc(&ws.d_lut, (size_t)BC_MAX_COMBOS * CJ_LUT_WORDS * sizeof(uint32_t)));
+    if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, BC_SINK_SLICES * sizeof(uint32_t)));
+    k_clut_build<<<(n_combos * CJ_LUT_WORDS + 255) / 256, 256, 0, st>>>(gp, ws.d_lut);
+    JCK(cudaGetLastError());
+    uint32_t gx = (ip.n_entries + 255) / 256;
+    if (gx > (uint32_t)sm_count * 8u) gx = (uint32_t)sm_count * 8u;
+    k_ccount<true><<<dim3(gx, n_combos), 256, 0, st>>>(gp, ws.d_lut, d_dir);
+    JCK(cudaGetLastError());
+    JCK(bc_exclusive_scan(d_dir, dir_slots, d_scan_tmp, st));
+    JCK(cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    k_cbin_init<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, d_dir, n_bins, n_slots, d_bin_start, d_bin_cursor, d_bin_combo);
+    JCK(cudaGetLastError());
+    const size_t smem_a = cj_smem_a();
+    const uint32_t max_sub = 1u << max_low;
+    const size_t smem_b = (3 * (size_t)max_sub + CJ_THREADS / 32) * 4 + (size_t)CJ_CHUNK * 8;
+    JCK(cudaFuncSetAttribute(k_cbin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    uint32_t bx = (ip.n_entries + CJ_CHUNK - 1) / CJ_CHUNK;
+    if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
+    k_cbin<true><<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, tmp);
+    JCK(cudaGetLastError());
+    k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, d_dir + n_slots, d_chunk_bin);
+    JCK(cudaGetLastError());
+    JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
+    JCK(cj_launch_place<true>(gp, tmp, d_bin_start, d_bin_combo, d_chunk_bin, n_bins, d_cursor, ent_hl, ent_id, d_dir + n_slots,
+                              ws.d_work, max_sub, smem_b, sm_count, st));
+    bc_launch_counter += 7;
+    return cudaSuccess;
+}
 
 cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, uint32_t n_bins, int sm_count,
                             cudaStream_t st, uint32_t* launches, HitSink* sink) {
@@ -677,14 +1058,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     }
     // per-bin tables live in the bin cursor allocation: cursor | start (+1) | chunk table | combination bytes
     const uint64_t max_chunks = (chunk * p.n_combos + CJ_CHUNK - 1) / CJ_CHUNK + 1;
-    const uint64_t bin_words = 2ull * (n_bins + 2) + max_chunks + (n_bins + 8) / 4 + 4;
-    if (bin_words > ws.bin_cap) {
-        if (ws.d_bin_cursor) cudaFree(ws.d_bin_cursor);
-        ws.d_bin_cursor = nullptr;
-        ws.bin_cap = 0;
-        JCK(cudaMalloc(&ws.d_bin_cursor, bin_words * sizeof(uint32_t)));
-        ws.bin_cap = bin_words;
-    }
+    JCK(cj_ensure_bins(ws, n_bins, max_chunks));
     uint32_t* d_bin_cursor = ws.d_bin_cursor;
     uint32_t* d_bin_start = d_bin_cursor + (n_bins + 2);
     uint32_t* d_chunk_bin = d_bin_start + (n_bins + 2);
@@ -707,6 +1081,23 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         ws.scan_tmp_cap = tmp_words;
     }
     if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, BC_SINK_SLICES * sizeof(uint32_t)));
+    // global item queue between k_cverify and k_cfinish: about one item per candidate pair; sized from the
+    // hit buffer (a full queue only means the verify kernel resolves the overflow itself)
+    {
+        uint64_t want = 2 * p.cap + (1ull << 16);
+        if (want > (1ull << 29)) want = 1ull << 29;
+        want &= ~31ull;
+        if (want > ws.item_cap) {
+            if (ws.d_items) cudaFree(ws.d_items);
+            ws.d_items = nullptr;
+            ws.item_cap = 0;
+            if (cudaMalloc(&ws.d_items, want * sizeof(uint4)) == cudaSuccess) ws.item_cap = want;
+            else (void)cudaGetLastError();  // no queue: everything is resolved inside the verify kernel
+        }
+    }
+    SearchParams pv = p;
+    pv.items = ws.d_items;
+    pv.item_cap = CV_FINISH_KERNEL ? ws.item_cap : 0;
 
     CBucketParams gp;
     memset(&gp, 0, sizeof gp);
@@ -726,12 +1117,10 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     k_clut_build<<<(p.n_combos * CJ_LUT_WORDS + 255) / 256, 256, 0, st>>>(gp, ws.d_lut);
     JCK(cudaGetLastError());
     bc_launch_counter += 1;
-    const size_t smem_a = (3 * CJ_MAX_BINS + 2 * (CJ_CHUNK / 32 + 2) + CJ_THREADS / 32 + CJ_LUT_WORDS) * 4 + (size_t)CJ_CHUNK * 8 +
-                          (size_t)CJ_CHUNK * 2;
+    const size_t smem_a = cj_smem_a();
     const uint32_t max_sub = 1u << max_low;
     const size_t smem_b = (3 * (size_t)max_sub + CJ_THREADS / 32) * 4 + (size_t)CJ_CHUNK * 8;
-    JCK(cudaFuncSetAttribute(k_cbin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    JCK(cudaFuncSetAttribute(k_cplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    JCK(cudaFuncSetAttribute(k_cbin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
     uint2* d_tmp = reinterpret_cast<uint2*>(ws.d_gtmp);
     uint2* d_win = reinterpret_cast<uint2*>(ws.d_gwin);
     const bool one_pass = max_low == 0;  // every bin is one slot: pass A writes the final array
@@ -745,7 +1134,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         if (gx > maxb) gx = maxb;
         JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
         JCK(cudaEventRecord(ws.ev_c, st));
-        k_ccount<<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_lut, ws.d_gdir);
+        k_ccount<false><<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_lut, ws.d_gdir);
         JCK(cudaGetLastError());
         JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
         if (!one_pass) JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
@@ -753,16 +1142,15 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         JCK(cudaGetLastError());
         uint32_t bx = (npos + CJ_CHUNK - 1) / CJ_CHUNK;
         if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
-        k_cbin<<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, one_pass ? d_win : d_tmp);
+        k_cbin<false><<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, one_pass ? d_win : d_tmp);
         JCK(cudaGetLastError());
         bc_launch_counter += 3;
         if (!one_pass) {
             k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, ws.d_gdir + n_slots, d_chunk_bin);
             JCK(cudaGetLastError());
             JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
-            k_cplace<<<(uint32_t)sm_count * 2u, CJ_THREADS, smem_b, st>>>(gp, d_tmp, d_bin_start, d_bin_combo, d_chunk_bin, n_bins,
-                                                                        ws.d_gcursor, d_win, ws.d_gdir + n_slots, ws.d_work, max_sub);
-            JCK(cudaGetLastError());
+            JCK(cj_launch_place<false>(gp, d_tmp, d_bin_start, d_bin_combo, d_chunk_bin, n_bins, ws.d_gcursor, d_win, nullptr,
+                                       ws.d_gdir + n_slots, ws.d_work, max_sub, smem_b, sm_count, st));
             bc_launch_counter += 2;
         }
         JCK(cudaEventRecord(ws.ev_a, st));
@@ -772,13 +1160,19 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         for (uint32_t s = 0; s < n_slices; s++) {
             const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));
             const uint32_t dgrid = (uint32_t)sm_count * CV_MINBLOCKS, lo = n_slices == 1 ? 0u : f_lo;
+            JCK(cudaMemsetAsync(p.count + 4, 0, sizeof(unsigned long long), st));
             switch (p.k) {
-                case 0: k_cverify<0><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
-                case 1: k_cverify<1><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
-                case 2: k_cverify<2><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
-                default: k_cverify<3><<<dgrid, CV_THREADS, 0, st>>>(p, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                case 0: k_cverify<0><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                case 1: k_cverify<1><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                case 2: k_cverify<2><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                default: k_cverify<3><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
             }
             JCK(cudaGetLastError());
+            if (pv.item_cap) {
+                k_cfinish<<<(uint32_t)sm_count * 6u, CV_THREADS, 0, st>>>(pv, d_win);
+                JCK(cudaGetLastError());
+                bc_launch_counter += 1;
+            }
             if (sink) {
                 JCK(cudaMemcpyAsync(sink->h_counts + s, p.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 JCK(cudaEventRecord(sink->ev[s], st));

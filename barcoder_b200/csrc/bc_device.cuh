@@ -71,7 +71,9 @@ struct SearchParams {
     uint32_t join_chunk;        // bucket-join path: max window positions per pass over the genome, 0 = as many as fit (BC_PARAM_JOIN_CHUNK)
     // output
     bc_hit* hits;
-    unsigned long long* count;  // [0] hits, [1] candidates, [2] probes, [3] next tile of the probe kernel
+    unsigned long long* count;  // [0] hits, [1] candidates, [2] probes, [3] next tile of the probe kernel, [4] queued verify items
+    uint4* items;               // compact join: global queue of {window, entry group} items for k_cfinish
+    unsigned long long item_cap;
     unsigned long long cap;
     uint32_t count_candidates;
     uint32_t spacer_id_base;

@@ -12,6 +12,8 @@ struct JoinWorkspace {
     uint64_t bin_cap = 0;
     uint32_t* d_work = nullptr;      // per-slice chunk counters of the dense verify kernel (dynamic work distribution)
     uint32_t* d_scan_tmp = nullptr;
+    uint4* d_items = nullptr;        // compact join: {window, entry group} items handed from k_cverify to k_cfinish
+    uint64_t item_cap = 0;
     uint32_t* d_lut = nullptr;       // compact join: byte-wise bit-permutation tables, one per combination
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     uint64_t gdir_cap = 0, gwin_cap = 0, scan_tmp_cap = 0;
@@ -41,4 +43,8 @@ cudaError_t bc_sink_deliver(HitSink* sink, const SearchParams& p, uint32_t n_sli
 // compact form (8-byte window records; bc_cjoin.cu): same workspace, the record arrays are viewed as uint2
 cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, uint32_t n_bins, int sm_count,
                             cudaStream_t st, uint32_t* launches, HitSink* sink);
+struct IndexParams;
+cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n_combos, uint32_t n_bins, uint32_t* d_dir,
+                            uint64_t dir_slots, uint32_t* d_cursor, uint32_t* d_scan_tmp, uint2* tmp, uint2* ent_hl,
+                            uint32_t* ent_id, int sm_count, cudaStream_t st);
 void bc_join_free(JoinWorkspace& ws);

@@ -4,12 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # the CPU path timed on host cores
 
-Workload (config.workload): BASELINE.json configs[3] - a 10^7-spacer 20-mer library (1 % planted)
-against a 100 Mbp synthetic genome, <= 3 mismatches, PAM NGG downstream, library sharded over
-the GPUs.  Scaling is WEAK: every GPU searches its own 10^7-spacer shard (the N-GPU job is an
-N x 10^7 library), the genome is replicated, hits are gathered to rank 0 over NCCL.
+Workload (config.workload): BASELINE.json configs[3] - ONE 10^7-spacer 20-mer library (1 % planted)
+against a 100 Mbp synthetic genome, <= 3 mismatches, PAM NGG downstream.  At N > 1 the job is the
+same library (STRONG scaling): every GPU holds the packed genome and library, and the seed
+directory is cut into N slot ranges (BC_PARAM_SLOT_PART) - a GPU indexes, sorts and verifies only
+the (window, entry) pairs whose seed key falls in its range, so index build, window sort and
+verification all shrink with N; the hit records are merged on rank 0 through a peer-memory sink
+(copy engines over NVLink while the search runs).  `--shard library` runs the round-1 weak-scaling
+job instead (10^7 spacers PER GPU), `--shard genome` cuts the genome into ranges (cfg 5).
 
-A step = seed-index build + genome scan (bucketing + verification, PAM fused) + hit gather, with
+A step = seed-index build + genome scan (window sort + verification, PAM fused) + hit merge, with
 the ASCII inputs already resident in HBM (`value`).  `e2e` is the same metric through the host
 C-ABI calls: pinned host ASCII buffers -> H2D -> pack -> index -> scan -> D2H of the hit records
 (streamed into a pinned buffer through bc_set_hit_sink while the scan runs).
@@ -33,7 +37,7 @@ CONFIGS = {
     # name: genome bp, contigs, N fraction, genome seed, spacers per GPU, L, library seed, planted, k, pam, iupac
     "cfg4": dict(G=100_000_000, contigs=1, nfrac=0.0, gseed=4, n=10_000_000, L=20, lseed=40, planted=0.01,
                  k=3, pam="NGG", iupac=False,
-                 name="cfg4: 10M 20-mers/GPU x 100 Mbp synthetic, k<=3, NGG downstream (BASELINE.json configs[3])"),
+                 name="cfg4: 10M 20-mers x 100 Mbp synthetic, k<=3, NGG downstream (BASELINE.json configs[3])"),
     "cfg3": dict(G=4_641_652, contigs=1, nfrac=0.0, gseed=1, n=None, L=20, lseed=0, planted=0.0, k=3, pam="NGG",
                  iupac=False, name="cfg3: all NGG 20-mers of a 4.64 Mbp synthetic genome vs itself, k<=3"),
     "cfg5": dict(G=3_000_000_000, contigs=24, nfrac=0.001, gseed=5, n=1_000_000, L=32, lseed=50, planted=0.01,
@@ -118,6 +122,19 @@ def int_peak(device):
     return {"popc_per_s": popc.value, "verify_atom_per_s": atom.value, "sm_count": sms.value}
 
 
+def source_hash():
+    """Hash of the kernel sources: profiles/traffic.json is only trusted for the code it was captured from."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(glob.glob(os.path.join(ROOT, "barcoder_b200", "csrc", "*.cu*")) +
+                       glob.glob(os.path.join(ROOT, "barcoder_b200", "csrc", "*.inc")) +
+                       glob.glob(os.path.join(ROOT, "barcoder_b200", "csrc", "*.h"))):
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as h:
@@ -128,11 +145,9 @@ def measured_peaks():
 
 def cpu_sample_once(cfg, genome, lib, n_s, G_s, threads):
     from oracle import oracle
-    from barcoder_b200 import synth
     contigs = [bytes(genome[:G_s])]
-    spacers = synth.rows_to_strings(lib[:n_s])
     t0 = time.time()
-    hits = oracle.search(contigs, spacers, cfg["k"], pam=cfg["pam"], direction="downstream",
+    hits = oracle.search(contigs, np.ascontiguousarray(lib[:n_s]), cfg["k"], pam=cfg["pam"], direction="downstream",
                          flags=oracle.PAM_FLAG_IUPAC if cfg["iupac"] else 0, threads=threads)
     dt = time.time() - t0
     return dict(value=n_s * (G_s / 1e6) / dt, seconds=dt, n=n_s, G=G_s, hits=int(len(hits)))
@@ -140,29 +155,76 @@ def cpu_sample_once(cfg, genome, lib, n_s, G_s, threads):
 
 def cpu_calibrate(cfg, genome, lib, budget_s, threads):
     """Pick a bounded sample (first n_s spacers x first G_s bases) that keeps the oracle busy for
-    roughly budget_s seconds on this box."""
-    n_s = min(len(lib), 20_000)
-    G_s = min(len(genome), 4_000_000)
+    roughly budget_s seconds on this box.  The library sample is large (up to 2*10^6 spacers) so
+    that the seed buckets are as dense as in the full job and the oracle's cost model picks the
+    same kind of scheme; the rate includes its index build, like the GPU step does."""
+    n_s = min(len(lib), 2_000_000)
+    G_s = min(len(genome), 1_000_000)
     best = None
-    for _ in range(4):
+    for _ in range(5):
         best = cpu_sample_once(cfg, genome, lib, n_s, G_s, threads)
-        if best["seconds"] >= budget_s / 3 or G_s >= len(genome):
+        if best["seconds"] >= budget_s / 2 or G_s >= len(genome):
             break
-        G_s = min(len(genome), int(G_s * min(8.0, max(2.0, (budget_s / 1.5) / max(best["seconds"], 1e-3)))))
+        G_s = min(len(genome), int(G_s * min(8.0, max(2.0, budget_s / max(best["seconds"], 1e-3)))))
     return best
 
 
-def cpu_result(cfg, best, threads):
+def cpu_result(cfg, best, threads, n_full, G_full):
+    frac = best["n"] * best["G"] / (float(n_full) * G_full)
     return {"value": best["value"], "unit": "guides*Mbp/s", "cores": threads, "kind": "port",
-            "sample": f"first {best['n']} spacers x first {best['G']} bp of the genome, k={cfg['k']}, "
-                      f"{best['seconds']:.1f} s, {best['hits']} hits; oracle/oracle.c pigeonhole search on "
-                      f"{threads} threads (CPU restatement, not bowtie - bowtie 1.3.1 is not installable here)"}
+            "sample_fraction": frac, "extrapolated_full_job_s": n_full * (G_full / 1e6) / best["value"],
+            "bowtie": bowtie_probe(),
+            "sample": f"first {best['n']} spacers x first {best['G']} bp of the genome ({frac:.2e} of the job, "
+                      f"rate extrapolated linearly), k={cfg['k']}, {best['seconds']:.1f} s incl. index build, "
+                      f"{best['hits']} hits; oracle/oracle.c: generalised-pigeonhole seeds chosen by a cost model, "
+                      f"key-sorted 2-bit library, rolling window, popcount-first verification, {threads} threads "
+                      f"(CPU restatement, not bowtie - bowtie 1.3.1 is not installable here)"}
+
+
+def bowtie_probe():
+    """The reference shells out to bowtie / bowtie-build (BowtieRunner.py:87,107).  If the binaries
+    ever appear on PATH the exact reference command line can be timed; here it only records that
+    they are absent."""
+    import shutil
+    found = {name: shutil.which(name) for name in ("bowtie", "bowtie-build")}
+    return {"available": all(found.values()), "paths": found}
+
+
+def bowtie_time(cfg, genome, lib, n_s, G_s, threads):
+    """bowtie-build + `bowtie -S -a --nomaqround --mm --tryhard --quiet --best -p N -v k`
+    (BowtieRunner.py:111-125) on the same bounded sample, if the binaries exist."""
+    import shutil
+    import tempfile
+    if not (shutil.which("bowtie") and shutil.which("bowtie-build")):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        fa, fq, idx, sam = (os.path.join(d, x) for x in ("g.fasta", "r.fastq", "idx", "out.sam"))
+        with open(fa, "w") as h:
+            h.write(">chr\n" + bytes(genome[:G_s]).decode() + "\n")
+        with open(fq, "w") as h:
+            for i, row in enumerate(lib[:n_s]):
+                sp = bytes(row).decode()
+                h.write(f"@r{i}\n{sp}\n+\n{'I' * len(sp)}\n")
+        t0 = time.time()
+        subprocess.run(["bowtie-build", fa, idx], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t1 = time.time()
+        subprocess.run(["bowtie", "-S", "-a", "--nomaqround", "--mm", "--tryhard", "--quiet", "--best", "-p",
+                        str(threads), "-v", str(cfg["k"]), "-x", idx, fq, sam], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t2 = time.time()
+    return {"build_s": t1 - t0, "align_s": t2 - t1, "threads": threads, "n": n_s, "G": G_s,
+            "value": n_s * (G_s / 1e6) / (t2 - t0)}
 
 
 def cpu_baseline_run(cfg, genome, off, lib, budget_s=20.0, threads=None):
     """Time the oracle (CPU restatement, kind 'port') on a bounded sample of the workload."""
     threads = threads or os.cpu_count() or 1
-    return cpu_result(cfg, cpu_calibrate(cfg, genome, lib, budget_s, threads), threads)
+    best = cpu_calibrate(cfg, genome, lib, budget_s, threads)
+    res = cpu_result(cfg, best, threads, len(lib), len(genome))
+    bt = bowtie_time(cfg, genome, lib, min(best["n"], 200_000), best["G"], threads)
+    if bt:
+        res["bowtie_timed"] = bt
+    return res
 
 
 def run_reference(args, cfg):
@@ -182,14 +244,14 @@ def run_reference(args, cfg):
         if i >= args.warmup:
             vals.append(last["value"])
     value = statistics.mean(vals) if vals else cal["value"]
-    n_tot = len(lib) * args.gpus
-    res = cpu_result(cfg, last, threads)
+    n_tot = len(lib)
+    res = cpu_result(cfg, last, threads, len(lib), len(genome))
     line = {
         "impl": "reference", "metric": "guides*Mbp/s at <=k mismatches", "value": value, "unit": "guides*Mbp/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * last["seconds"], "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * last["seconds"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64 2-bit packed (XOR/popcount)", "data": "synthetic",
-        "config": {"workload": cfg["name"], "k": cfg["k"], "pam": cfg["pam"], "spacers_per_gpu": len(lib),
+        "config": {"workload": cfg["name"], "k": cfg["k"], "pam": cfg["pam"], "spacers": len(lib),
                    "genome_bp": len(genome), "note": "each step = the bounded sample in cpu_baseline.sample; "
                    f"full job would take ~{n_tot * (len(genome) / 1e6) / value:.0f} s at this rate"},
         "cpu_baseline": dict(res, value=value),
@@ -211,9 +273,10 @@ def main():
     ap.add_argument("--blocks", type=int, default=0)
     ap.add_argument("--key-nt", type=int, default=0, help="force a seed covering design with keys of this length")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", default=None, choices=["library", "genome"],
-                    help="multi-GPU partitioning: library shards (weak scaling, default) or genome ranges "
-                         "(strong scaling; default for cfg5, which is probe-bound)")
+    ap.add_argument("--shard", default=None, choices=["slots", "library", "genome"],
+                    help="multi-GPU partitioning: slot ranges of the seed directory (strong scaling of one "
+                         "library, default), genome ranges (strong; default for cfg5, which is probe-bound) or "
+                         "library shards (weak scaling: the configured library PER GPU)")
     ap.add_argument("--gate", action="store_true", help="PAM-first gating: report only PAM-adjacent hits")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel experiments only)")
     ap.add_argument("--verify", action="store_true", help="check a sample of the result against the oracle")
@@ -240,7 +303,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    shard = args.shard or ("genome" if args.config == "cfg5" else "library")
+    shard = args.shard or ("genome" if args.config == "cfg5" else "slots")
     genome, off, lib = make_workload(cfg, rank if shard == "library" else 0, args.scale)
     n, L = lib.shape
     G = len(genome)
@@ -255,10 +318,12 @@ def main():
 
     s = _native.Searcher(local_rank)
     s.set_pam(cfg["pam"], "downstream", iupac=cfg["iupac"], gate=args.gate)
-    if shard == "library":
+    if shard == "library":   # weak scaling: a different library on every rank, global spacer ids
         s.set_param(_native.BC_PARAM_SPACER_ID_BASE, rank * n)
-    else:  # every rank holds the whole library and scans its 1/world slice of the genome
+    elif shard == "genome":  # every rank holds the whole library and scans its 1/world slice of the genome
         s.set_param(_native.BC_PARAM_SCAN_PART, rank | (world << 16))
+    else:                    # every rank holds genome + library and owns 1/world of the seed directory
+        s.set_param(_native.BC_PARAM_SLOT_PART, rank | (world << 16))
     if args.path:
         s.set_param(_native.BC_PARAM_PATH, args.path)
     if args.blocks:
@@ -352,7 +417,23 @@ def main():
     for key in acc:
         acc[key] /= args.steps
     st = s.stats()
+    merged_ok = None
     if peer["g"] is not None:
+        # Order-independent checksum of the 16-byte records: every rank hashes what ITS search produced
+        # (its own device buffer), the hashes are summed over the ranks, and rank 0 compares the sum with
+        # the hash of what actually arrived in its peer buffer.  Untimed.
+        def digest(t):
+            if t.shape[0] == 0:
+                return torch.zeros(2, dtype=torch.int64, device=device)
+            v = t.to(torch.int64) & 0xffffffff
+            h = (v[:, 0] * 0x9E3779B1) ^ (v[:, 1] * 0x85EBCA77) ^ (v[:, 2] * 0xC2B2AE3D) ^ (v[:, 3] * 0x27D4EB2F)
+            h = (h ^ (h >> 29)) * 0x165667B19E3779F9
+            return torch.stack([h.sum(), torch.tensor(t.shape[0], dtype=torch.int64, device=device)])
+        mine = digest(multi_gpu.hits_as_tensor(s, device))
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            got = sum((digest(seg) for seg in peer["g"].segments()), torch.zeros(2, dtype=torch.int64, device=device))
+            merged_ok = bool(torch.equal(got, mine)) and int(mine[1].item()) == int(total_hits)
         peer["g"].close()
 
     # ---- end-to-end arm: host buffers in, host records out
@@ -386,39 +467,46 @@ def main():
     # ---- roofline of the dominant kernel group (DESIGN.md sections 4 and 6)
     peaks, peak_src = measured_peaks()
     combos = st["combos"]
-    records = float(G) * combos          # (window, combination) records; windows touching N are dropped
-    parts = {"verify": acc["ms_scan_kernel"], "genome_bucket": acc["ms_genome_bucket"],
+    E = 2.0 * n
+    records = float(G) * combos / (world if shard in ("slots", "genome") else 1)   # (window, combination) records of this rank
+    entries = E * combos / (world if shard == "slots" else 1)
+    parts = {"verify": acc["ms_scan_kernel"], "window_sort": acc["ms_genome_bucket"],
              "index_build": acc["ms_build_index"]}
     dominant = max(parts, key=parts.get)
     ipk = int_peak(local_rank)
+    rec_b = 8.0 if st["path"] == 3 else 16.0
     if st["path"] >= 2:
-        # window sort: the three planes are read once per pass and combination (count, scatter),
-        # one 16 B record written; verify: that record read once, the index entries (12 B) once,
-        # 16 B written per hit
-        alg_bytes = {"genome_bucket": 2 * combos * (3 * G / 8) + 16.0 * records,
-                     "verify": 16.0 * records + 12.0 * 2 * n * combos + 16.0 * st["hits"],
-                     "index_build": (8 + 16 + 16 + 12) * 2.0 * n * combos}
-        names = {"verify": "k_verify_dense+k_verify_sparse", "genome_bucket": "k_bucket<0>+scan+k_bucket<1>",
+        # window sort: the planes are read by the count pass and by pass A, every record is written by
+        # pass A, read and written by pass B; verify: every record read once, the index entries (12 B)
+        # once, 16 B written per hit; index: entries read, written to the coarse array, read, written
+        alg_bytes = {"window_sort": 2 * (3 * G / 8) + 3 * rec_b * records,
+                     "verify": rec_b * records + 12.0 * entries + 16.0 * st["hits"],
+                     "index_build": (8 + 16 + 16 + 12) * entries}
+        names = {"verify": "k_cverify" if st["path"] == 3 else "k_verify_dense+k_verify_sparse",
+                 "window_sort": "k_ccount+scan+k_cbin+k_cplace" if st["path"] == 3 else "k_bucket<0>+scan+k_window_bin+k_window_place",
                  "index_build": "k_index_count+scan+k_index_scatter+k_fine_scatter"}
     else:
-        alg_bytes = {"verify": 3 * G / 8 + 16.0 * st["hits"], "genome_bucket": 0.0,
-                     "index_build": (8 + 16 + 16 + 12) * 2.0 * n * combos}
-        names = {"verify": "k_scan_probe", "genome_bucket": "-", "index_build": "k_index_count+scan+scatter"}
-    traffic = None
+        alg_bytes = {"verify": 3 * G / 8 + 16.0 * st["hits"], "window_sort": 0.0,
+                     "index_build": (8 + 16 + 16 + 12) * entries}
+        names = {"verify": "k_scan_probe", "window_sort": "-", "index_build": "k_index_count+scan+scatter"}
+    traffic, traffic_note = None, None
     try:  # DRAM bytes per launch from the committed ncu --set full capture of this configuration
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as h:
-            traffic = json.load(h).get(f"{args.config}:b{st['blocks']}:path{st['path']}", {}).get(dominant)
-    except OSError:
+            tj = json.load(h)
+        if tj.get("source_hash") == source_hash():
+            traffic = tj.get("entries", {}).get(f"{args.config}:key{st['key_nt']}:c{combos}:path{st['path']}:n{world}", {}).get(dominant)
+        else:
+            traffic_note = "profiles/traffic.json was captured from different kernel sources; not used"
+    except (OSError, ValueError):
         pass
     kernel_ms = parts[dominant]
     achieved = alg_bytes[dominant] / (kernel_ms / 1e3) / 1e9 if kernel_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes[dominant],
-                "share_of_step": kernel_ms / max(ms_per_step, 1e-9),
-                "ms": {k2: round(v, 4) for k2, v in parts.items()},
-                "note": "HBM view of the stage with the largest share of the step; the verify stage is "
-                        "integer-pipe bound and is rated in roofline_int"}
+    roofline_hbm = {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes[dominant],
+                    "share_of_step": kernel_ms / max(ms_per_step, 1e-9)}
+    if traffic_note:
+        roofline_hbm["traffic_note"] = traffic_note
     roofline_int = None
     if ipk and st["path"] >= 2 and acc["ms_scan_kernel"] > 0:
         # candidates verified per second against the measured POPC issue rate and the measured
@@ -428,14 +516,23 @@ def main():
         cand = s.stats()["candidates"]
         s.set_param(_native.BC_PARAM_COUNT_CANDIDATES, 0)
         rate = cand / (acc["ms_scan_kernel"] / 1e3)
+        pairs_k1 = float(G) * E / (world if shard != "library" else 1) * (k + 1) / 4.0 ** (L // (k + 1)) if L >= k + 1 else None
         roofline_int = {"bound": "int_popc", "kernel": names["verify"], "achieved": rate / 1e12,
                         "peak": ipk["popc_per_s"] / 1e12, "unit": "Tpairs/s (1 POPC per pair)",
                         "frac": rate / ipk["popc_per_s"], "frac_of_verify_atom": rate / ipk["verify_atom_per_s"],
                         "verify_atom_peak": ipk["verify_atom_per_s"] / 1e12, "candidates": cand,
+                        "pairs_vs_k_plus_1": (cand / pairs_k1) if pairs_k1 else None,
+                        "traffic": traffic if dominant == "verify" else None,
                         "share_of_step": acc["ms_scan_kernel"] / max(ms_per_step, 1e-9),
                         "peak_source": "bench_kernels/int_peak.cu measured in this run (POPC: 16/clk/SM)",
-                        "note": "peak = one POPC per pair; k_verify_dense tests 1 pair in 8 on the ALU pipe instead "
-                                "(clear-lowest-bit test), so the POPC pipe itself sees 7/8 of `achieved`"}
+                        "note": "peak = one POPC per candidate pair (1 pair in 8 is tested on the ALU pipe instead); "
+                                "pairs_vs_k_plus_1 = candidates / what the classic k+1-seed filter would verify"}
+    # `roofline` = the bound that binds the dominant stage: the POPC pipe for verification, HBM otherwise
+    if dominant == "verify" and roofline_int:
+        roofline = dict(roofline_int, hbm_view=roofline_hbm)
+    else:
+        roofline = dict(roofline_hbm, int_view=roofline_int)
+    roofline["stage_ms"] = {k2: round(v, 4) for k2, v in parts.items()}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -459,20 +556,21 @@ def main():
     line = {
         "metric": "guides*Mbp/s at <=k mismatches", "value": value, "unit": "guides*Mbp/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak" if shard == "library" else "strong", "vs_baseline": None,
+        "scaling": "weak" if shard == "library" else "strong", "vs_baseline": None, "merged_ok": merged_ok,
         "dtype": "u32 bit-planes (XOR/popcount)", "data": "synthetic",
         "config": {"workload": cfg["name"], "k": k, "pam": cfg["pam"], "spacers_per_gpu": n, "genome_bp": G,
-                   "L": L, "pam_gate": bool(args.gate), "parallelism": (f"library-shard x{world}, genome replicated" if shard == "library" else
-                                           f"genome-range x{world}, library replicated"),
+                   "L": L, "pam_gate": bool(args.gate),
+                   "parallelism": {"library": f"library-shard x{world} (a {n}-spacer library per GPU), genome replicated",
+                                   "genome": f"genome-range x{world}, library replicated",
+                                   "slots": f"seed-directory slot-range x{world}: genome and library replicated, index / "
+                                            "window sort / verification sharded by seed key"}[shard],
                    "seed_scheme": f"b={st['blocks']} blocks, {combos} combinations, key<={st['key_nt']} nt, path={st['path']}",
                    "l2": "working set (window records + index) is far larger than the 126 MB L2; no flush needed",
                    "hits_per_step": int(total_hits)},
         "e2e": {"value": e2e_value, "unit": "guides*Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e.item() / e2e_steps, "host_phase_ms": e2e_phase_ms},
         "gpu_launches": int(launches),
-        "clocks": clocks, "roofline": dict(roofline, int_pipe_frac=(roofline_int["frac"] if roofline_int else None)),
-        "roofline_int": roofline_int,
-        "roofline_best": ("roofline_int" if roofline_int and roofline_int["frac"] > roofline["frac"] else "roofline"),
+        "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu,
         "stage_ms": dict({k2: round(v, 4) for k2, v in acc.items()},
                          ms_pack_genome=round(s.stats()["ms_pack_genome"], 4),

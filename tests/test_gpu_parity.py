@@ -366,3 +366,23 @@ def test_cjoin_hit_sink_and_overflow():
         assert s.search(2) == len(ref)
         assert_same(_native.canonical_sort(sink.copy()), ref)
         assert s.stats()["path"] == 3
+
+
+@pytest.mark.parametrize("index_sort", [1, 2])
+def test_cjoin_index_builders_agree(index_sort):
+    """The compact path's library index can be built by the two radix passes (default) or by the
+    two-level atomic scatter of the other paths (BC_PARAM_INDEX_SORT): same records; spacers with
+    non-ACGT characters are skipped per combination in both."""
+    genome, off, lib = small_case(20, 3, seed=333, n=5000, G=500000, n_contigs=4, nfrac=0.004)
+    lib[17, 3] = ord("N")
+    ref = run_oracle(genome, off, lib, 3, pam="NGG")
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        s.set_param(_native.BC_PARAM_PATH, 3)
+        s.set_param(_native.BC_PARAM_KEY_NT, 9)
+        s.set_param(_native.BC_PARAM_INDEX_SORT, index_sort)
+        n = s.search(3)
+        assert n == len(ref)
+        assert_same(_native.canonical_sort(s.hits()), ref)
