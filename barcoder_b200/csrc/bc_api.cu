@@ -508,9 +508,12 @@ static double scheme_cost(const bc_ctx* ctx, const Scheme& s, uint32_t path) {
         while (!radix && slots_per_combo > 65536.0) { c_sort += 6.0; slots_per_combo *= 0.5; }
         return (c_sort + c_rec) * records + 0.25 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
     }
-    // compact join; small genomes do not fill the chunks of the radix passes
+    // compact join (measured at cfg 4, 9- and 10-nt designs): sort 17-18 ps per record, index 20 ps per
+    // (entry, combination) with the radix builder, first-level verify 0.25 ps per candidate plus ~5 ps
+    // per record of tile overhead when the slots are small (< 256 windows)
     const double c_sort = s.key_nt_max <= 5 ? 10.0 : 17.5;
-    return (c_sort + c_rec) * records + 0.25 * cands + common + 5.0 * (double)s.dir_slots + 1.2e8;
+    const double c_tile = windows / slots_per_combo >= 256.0 ? 1.0 : 5.0;
+    return (c_sort + c_tile) * records + 0.25 * cands + 20.0 * entries + 10.0 * (double)s.dir_slots + 1.2e8;
 }
 
 static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_out) {

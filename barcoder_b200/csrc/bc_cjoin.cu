@@ -775,16 +775,54 @@ __device__ __forceinline__ uint32_t cv_tile(const SearchParams& p, const uint2* 
     return gn;
 }
 
-// Every slot is cut into warp-tiles of up to 128 window records ALIGNED TO THE SLOT START, so all
-// windows of a tile share one library bucket, which is streamed once per tile as broadcast loads
-// against the (up to 4) resident windows of each lane.  The record array is cut into chunks of
-// CV_CHUNK_TILES * 128 records handed out through an atomic counter; a warp owns the tiles that
-// START in its chunk.  Records do not carry their slot: the slot of the chunk's first record comes
-// from a binary search of the record directory, the following slots from walking it.
+// ------------------------------------------------------------------------------------ tile list
+// Every slot with windows AND library entries is cut into warp-tiles of up to 128 window records
+// aligned to the slot start, so all windows of a tile share one library bucket.  The tiles are
+// listed up front ({first record, end record, bucket begin, bucket end} + slot): the verify kernel
+// then needs ONE descriptor load per tile instead of walking the two directories with dependent
+// loads, and carries no slot-walk state in registers (the walking version spilled 240 bytes per
+// thread at 64 registers: ncu counted 1.3e9 local-memory load requests, 3x its global loads).
+#define CV_WTILE (32 * CV_ITEMS)
+__global__ void __launch_bounds__(256) k_ctile_count(const uint32_t* __restrict__ gdir, const uint32_t* __restrict__ dir,
+                                                     uint32_t n_slots, uint32_t* __restrict__ tile_start,
+                                                     unsigned long long* __restrict__ cand_out) {
+    unsigned long long cand = 0;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_slots; s += gridDim.x * blockDim.x) {
+        uint32_t tiles = 0;
+        if (s < n_slots) {
+            const uint32_t n_win = gdir[s + 1] - gdir[s], n_ent = dir[s + 1] - dir[s];
+            if (n_win && n_ent) tiles = (n_win + CV_WTILE - 1) / CV_WTILE;
+            cand += (unsigned long long)n_win * n_ent;
+        }
+        tile_start[s] = tiles;  // scanned in place afterwards; [n_slots] becomes the number of tiles
+    }
+    if (cand_out && cand) atomicAdd(cand_out, cand);
+}
+
+__global__ void __launch_bounds__(256) k_ctile_fill(const uint32_t* __restrict__ gdir, const uint32_t* __restrict__ dir,
+                                                    uint32_t n_slots, const uint32_t* __restrict__ tile_start,
+                                                    uint4* __restrict__ tile_desc, uint32_t* __restrict__ tile_slot) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+        const uint32_t t0 = tile_start[s], t1 = tile_start[s + 1];
+        if (t0 == t1) continue;
+        const uint32_t a = gdir[s], b = gdir[s + 1], ls = dir[s], le = dir[s + 1];
+        for (uint32_t t = t0; t < t1; t++) {
+            const uint32_t first = a + (t - t0) * CV_WTILE;
+            tile_desc[t] = make_uint4(first, min(first + CV_WTILE, b), ls, le);
+            tile_slot[t] = s;
+        }
+    }
+}
+
+// Verify, first level: warps take chunks of CV_CHUNK_TILES tiles from an atomic counter; per tile
+// the (up to 4) windows of every lane stay in registers and the slot's bucket is streamed against
+// them (cv_tile).  Passing {window, entry group} items go to the global queue of k_cfinish.
 template <int K>
 __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __grid_constant__ SearchParams p,
                                                                       const uint2* __restrict__ gwin,
-                                                                      const uint32_t* __restrict__ gdir, uint32_t n_slots,
+                                                                      const uint4* __restrict__ tile_desc,
+                                                                      const uint32_t* __restrict__ tile_slot,
+                                                                      const uint32_t* __restrict__ n_tiles_ptr,
                                                                       uint32_t* __restrict__ work, uint32_t slice,
                                                                       uint32_t frac_lo, uint32_t frac_hi) {
     __shared__ uint4 s_q[CV_WARPS][CV_WQ];
@@ -794,15 +832,13 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint4* gq = s_gq[warp];
     uint2* sbuf = s_ent[warp];
-    uint32_t gn = 0;  // queued groups of this warp (warp-uniform; survives across tiles)
+    uint32_t gn = 0;  // queued items of this warp (warp-uniform; survives across tiles)
     uint4* q = s_q[warp];
     uint32_t* qn = &s_qn[warp];
     if (lane == 0) *qn = 0;
     __syncwarp();
-    const uint32_t n_rec = __ldg(gdir + n_slots);
-    const uint32_t wtile = 32 * CV_ITEMS, chunk = wtile * CV_CHUNK_TILES;
-    const uint32_t n_chunks = (uint32_t)(((uint64_t)n_rec + chunk - 1) / chunk);
-    unsigned long long cand = 0;
+    const uint32_t n_tiles = *n_tiles_ptr;
+    const uint32_t n_chunks = (n_tiles + CV_CHUNK_TILES - 1) / CV_CHUNK_TILES;
     const uint32_t ch_lo = (uint32_t)(((unsigned long long)n_chunks * frac_lo) >> 16);
     const uint32_t ch_hi = (uint32_t)(((unsigned long long)n_chunks * frac_hi) >> 16);
     for (;;) {
@@ -810,65 +846,30 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
         if (lane == 0) ch = ch_lo + atomicAdd(work + slice, 1u);
         ch = __shfl_sync(0xffffffffu, ch, 0);
         if (ch >= ch_hi) break;
-        const uint32_t r0 = ch * chunk, r1 = r0 + min(chunk, n_rec - r0);
-        // slot of record r0: the last slot whose first record is <= r0 (warp-uniform loads)
-        uint32_t slot = 0;
-        {
-            uint32_t lo = 0, hi = n_slots;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (__ldg(gdir + mid) <= r0) lo = mid; else hi = mid;
-            }
-            slot = lo;
-        }
-        uint32_t c = cv_combo_of_slot(p, slot);
-        uint32_t a = __ldg(gdir + slot), b = __ldg(gdir + slot + 1);  // records of this slot
-        uint32_t t = a + (r0 - a + wtile - 1) / wtile * wtile;         // first tile start >= r0
-        for (;;) {
-            if (t >= b) {  // slot finished: the next non-empty slot starts where this one ends
-                if (b >= r1) break;
-                uint32_t s2 = slot + 1;
-                for (;;) {  // 32 directory entries at a time
-                    const uint32_t idx = min(s2 + lane + 1, n_slots);
-                    const uint32_t more = __ballot_sync(0xffffffffu, __ldg(gdir + idx) > b);
-                    if (more) {
-                        s2 += __ffs(more) - 1;
-                        break;
-                    }
-                    s2 += 32;
-                }
-                slot = s2;
-                a = b;
-                b = __ldg(gdir + slot + 1);
-                t = a;
-                while (c + 1 < p.n_combos && p.combo[c + 1].dir_off <= slot) c++;
-                continue;
-            }
-            if (t >= r1) break;
-            const uint32_t first = t, tend = min(t + wtile, b);
-            t += wtile;
-            const uint32_t ls = __ldg(p.dir + slot), le = __ldg(p.dir + slot + 1);
-            if (ls == le) continue;
+        const uint32_t t_end = min((ch + 1) * CV_CHUNK_TILES, n_tiles);
+        uint32_t c = 0;  // combination of the current slot; tiles are in slot order
+        for (uint32_t t = ch * CV_CHUNK_TILES; t < t_end; t++) {
+            const uint4 d = __ldg(tile_desc + t);  // x first record, y end record, z bucket begin, w bucket end
+            const uint32_t slot = __ldg(tile_slot + t);
+            while (c + 1 < p.n_combos && p.combo[c + 1].dir_off <= slot) c++;
             const uint32_t rem_nt = p.combo[c].rem_nt, rm = (1u << rem_nt) - 1u;
             uint32_t wh[CV_ITEMS], wl[CV_ITEMS];
 #pragma unroll
             for (int it = 0; it < CV_ITEMS; it++) {
-                const uint32_t idx = first + it * 32 + lane;
+                const uint32_t idx = d.x + it * 32 + lane;
                 wh[it] = CV_INVALID;
                 wl[it] = 0;
-                if (idx < tend) {
+                if (idx < d.y) {
                     const uint32_t x = __ldcs(&gwin[idx].y);
                     wh[it] = x & rm;
                     wl[it] = (x >> rem_nt) & rm;
                 }
             }
-            const uint32_t n_win = tend - first;
-            cand += (unsigned long long)(le - ls) * ((n_win + 31u - lane) / 32u);
-            switch ((n_win + 31u) / 32u) {
-                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
-                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
-                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
-                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, ls, le, first, slot, sbuf, gq, gn, q, qn); break;
+            switch ((d.y - d.x + 31u) / 32u) {
+                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
+                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
+                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
+                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
             }
             cv_drain(p, q, qn, lane);
         }
@@ -881,7 +882,6 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
     __syncwarp();
     const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
     if (nq) cv_resolve(p, q, nq);
-    if (p.count_candidates) atomicAdd(p.count + 1, cand);
 }
 
 // Second level + hit resolution as a kernel of their own: every warp takes batches of 32 items of
@@ -1095,6 +1095,26 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             else (void)cudaGetLastError();  // no queue: everything is resolved inside the verify kernel
         }
     }
+    // tile list: at most one ragged tile per non-empty slot plus the full ones
+    {
+        const uint64_t max_tiles = chunk * p.n_combos / CV_WTILE + n_slots + 2;
+        if (max_tiles > ws.tile_cap) {
+            if (ws.d_tile_desc) cudaFree(ws.d_tile_desc);
+            if (ws.d_tile_slot) cudaFree(ws.d_tile_slot);
+            ws.d_tile_desc = nullptr; ws.d_tile_slot = nullptr;
+            ws.tile_cap = 0;
+            JCK(cudaMalloc(&ws.d_tile_desc, max_tiles * sizeof(uint4)));
+            JCK(cudaMalloc(&ws.d_tile_slot, max_tiles * sizeof(uint32_t)));
+            ws.tile_cap = max_tiles;
+        }
+        if (dir_slots > ws.tile_start_cap) {
+            if (ws.d_tile_start) cudaFree(ws.d_tile_start);
+            ws.d_tile_start = nullptr;
+            ws.tile_start_cap = 0;
+            JCK(cudaMalloc(&ws.d_tile_start, dir_slots * sizeof(uint32_t)));
+            ws.tile_start_cap = dir_slots;
+        }
+    }
     SearchParams pv = p;
     pv.items = ws.d_items;
     pv.item_cap = CV_FINISH_KERNEL ? ws.item_cap : 0;
@@ -1153,6 +1173,15 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
                                        ws.d_gdir + n_slots, ws.d_work, max_sub, smem_b, sm_count, st));
             bc_launch_counter += 2;
         }
+        {   // tile list of this pass
+            const uint32_t tg = (uint32_t)sm_count * 8u;
+            k_ctile_count<<<tg, 256, 0, st>>>(ws.d_gdir, p.dir, n_slots, ws.d_tile_start, p.count_candidates ? p.count + 1 : nullptr);
+            JCK(cudaGetLastError());
+            JCK(bc_exclusive_scan(ws.d_tile_start, dir_slots, ws.d_scan_tmp, st));
+            k_ctile_fill<<<tg, 256, 0, st>>>(ws.d_gdir, p.dir, n_slots, ws.d_tile_start, ws.d_tile_desc, ws.d_tile_slot);
+            JCK(cudaGetLastError());
+            bc_launch_counter += 2;
+        }
         JCK(cudaEventRecord(ws.ev_a, st));
         // Streamed delivery: the slices halve (1/2, 1/4, ... and the last one repeated)
         const uint32_t n_slices = sink ? BC_SINK_SLICES : 1;
@@ -1162,10 +1191,10 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             const uint32_t dgrid = (uint32_t)sm_count * CV_MINBLOCKS, lo = n_slices == 1 ? 0u : f_lo;
             JCK(cudaMemsetAsync(p.count + 4, 0, sizeof(unsigned long long), st));
             switch (p.k) {
-                case 0: k_cverify<0><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
-                case 1: k_cverify<1><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
-                case 2: k_cverify<2><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
-                default: k_cverify<3><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_gdir, n_slots, ws.d_work, s, lo, f_hi); break;
+                case 0: k_cverify<0><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+                case 1: k_cverify<1><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+                case 2: k_cverify<2><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+                default: k_cverify<3><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
             }
             JCK(cudaGetLastError());
             if (pv.item_cap) {

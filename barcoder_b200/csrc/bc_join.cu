@@ -636,6 +636,9 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.d_scan_tmp) cudaFree(ws.d_scan_tmp);
     if (ws.d_lut) cudaFree(ws.d_lut);
     if (ws.d_items) cudaFree(ws.d_items);
+    if (ws.d_tile_desc) cudaFree(ws.d_tile_desc);
+    if (ws.d_tile_slot) cudaFree(ws.d_tile_slot);
+    if (ws.d_tile_start) cudaFree(ws.d_tile_start);
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
     if (ws.ev_c) cudaEventDestroy(ws.ev_c);

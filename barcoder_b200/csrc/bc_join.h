@@ -12,6 +12,10 @@ struct JoinWorkspace {
     uint64_t bin_cap = 0;
     uint32_t* d_work = nullptr;      // per-slice chunk counters of the dense verify kernel (dynamic work distribution)
     uint32_t* d_scan_tmp = nullptr;
+    uint4* d_tile_desc = nullptr;    // compact join: warp-tile list of the verify kernel ({first, end, bucket begin, bucket end})
+    uint32_t* d_tile_slot = nullptr;
+    uint32_t* d_tile_start = nullptr; // first tile of every slot (+ total)
+    uint64_t tile_cap = 0, tile_start_cap = 0;
     uint4* d_items = nullptr;        // compact join: {window, entry group} items handed from k_cverify to k_cfinish
     uint64_t item_cap = 0;
     uint32_t* d_lut = nullptr;       // compact join: byte-wise bit-permutation tables, one per combination
