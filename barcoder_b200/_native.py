@@ -40,7 +40,7 @@ HIT_DTYPE = np.dtype([("spacer_id", "<u4"), ("gpos", "<u4"), ("mm_mask", "<u4"),
 EXPORTS = (
     "bc_abi_version", "bc_create", "bc_destroy", "bc_set_genome", "bc_set_genome_dev", "bc_set_library",
     "bc_set_library_dev", "bc_set_pam", "bc_set_param", "bc_build_index", "bc_search", "bc_copy_hits",
-    "bc_set_hit_sink", "bc_set_slice_callback", "bc_peer_export", "bc_peer_open", "bc_peer_close", "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
+    "bc_set_hit_sink", "bc_sort_hits", "bc_set_slice_callback", "bc_peer_export", "bc_peer_open", "bc_peer_close", "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
 )
 
 
@@ -61,7 +61,8 @@ class BcStats(ctypes.Structure):
         ("ms_pack_genome", ctypes.c_float), ("ms_pack_library", ctypes.c_float),
         ("ms_build_index", ctypes.c_float), ("ms_search", ctypes.c_float),
         ("ms_scan_kernel", ctypes.c_float), ("ms_genome_bucket", ctypes.c_float),
-        ("index_launches", ctypes.c_uint32), ("key_nt", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 5),
+        ("index_launches", ctypes.c_uint32), ("key_nt", ctypes.c_uint32), ("ms_sort_hits", ctypes.c_float),
+        ("reserved", ctypes.c_uint32 * 4),
     ]
 
     def as_dict(self):
@@ -101,6 +102,7 @@ def load():
     L.bc_search.argtypes = [vp, i32, ctypes.POINTER(u64)]
     L.bc_copy_hits.argtypes = [vp, vp, u64]
     L.bc_set_hit_sink.argtypes = [vp, vp, u64]
+    L.bc_sort_hits.argtypes = [vp, i32]
     L.bc_set_slice_callback.argtypes = [vp, SLICE_FN, vp]
     L.bc_peer_export.argtypes = [vp, u64, ctypes.POINTER(vp), ctypes.c_char_p]
     L.bc_peer_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
@@ -219,8 +221,13 @@ class Searcher:
         self._check(self._L.bc_search(self._ctx, int(k), ctypes.byref(n)))
         return n.value
 
+    def sort_hits(self, order="canonical"):
+        """Order the device hit buffer before copying it out: "canonical" = (spacer_id, gpos, strand),
+        "best" = (spacer_id, mismatches, gpos, strand), the order of `bowtie --best`."""
+        self._check(self._L.bc_sort_hits(self._ctx, {"canonical": 0, "best": 1}[order]))
+
     def hits(self):
-        """Copy the result records of the last search to the host (unordered)."""
+        """Copy the result records of the last search to the host (unordered unless sort_hits() was called)."""
         st = self.stats()
         out = np.empty(st["hits"], dtype=HIT_DTYPE)
         if len(out):

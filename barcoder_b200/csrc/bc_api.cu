@@ -69,6 +69,9 @@ struct bc_ctx {
     uint64_t hit_cap = 0, n_hits = 0;
     unsigned long long* d_count = nullptr;
     HitSink sink;                     // optional streamed delivery to host memory (bc_set_hit_sink)
+    bc_hit* d_sort_scratch = nullptr; // bc_sort_hits: ping-pong buffer, histogram, scan scratch
+    uint32_t *d_sort_hist = nullptr, *d_sort_tmp = nullptr, *d_sort_orand = nullptr;
+    uint64_t sort_cap = 0, sort_hist_cap = 0, sort_tmp_cap = 0;
 
     bc_stats stats;
 };
@@ -142,6 +145,7 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     dfree(ctx->d_dir); dfree(ctx->d_cursor); dfree(ctx->d_scan_tmp); dfree(ctx->d_ent_id); dfree(ctx->d_ent_hl);
     dfree(ctx->d_ent_tmp); dfree(ctx->d_coarse_cursor);
     dfree(ctx->d_hits); dfree(ctx->d_count);
+    dfree(ctx->d_sort_scratch); dfree(ctx->d_sort_hist); dfree(ctx->d_sort_tmp); dfree(ctx->d_sort_orand);
     bc_join_free(ctx->join);
     bc_guides_free(ctx->guides);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -849,6 +853,49 @@ extern "C" int bc_copy_hits(bc_ctx* ctx, bc_hit* dst, uint64_t cap) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(dst, ctx->d_hits, ctx->n_hits * sizeof(bc_hit), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return BC_OK;
+}
+
+extern "C" int bc_sort_hits(bc_ctx* ctx, int order) {
+    if (!ctx) return BC_EINVAL;
+    if (order != 0 && order != 1) return fail(ctx, BC_EINVAL, "bc_sort_hits: order must be 0 (canonical) or 1 (best)");
+    if (ctx->n_hits < 2) return BC_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->sort_cap < ctx->hit_cap) {
+        dfree(ctx->d_sort_scratch);
+        ctx->sort_cap = 0;
+        CK(cudaMalloc(&ctx->d_sort_scratch, ctx->hit_cap * sizeof(bc_hit)));
+        ctx->sort_cap = ctx->hit_cap;
+    }
+    const uint64_t hw = bc_sort_hist_words(ctx->n_hits);
+    if (hw > ctx->sort_hist_cap) {
+        dfree(ctx->d_sort_hist);
+        ctx->sort_hist_cap = 0;
+        CK(cudaMalloc(&ctx->d_sort_hist, hw * sizeof(uint32_t)));
+        ctx->sort_hist_cap = hw;
+    }
+    const uint64_t tw = bc_scan_tmp_words(hw);
+    if (tw > ctx->sort_tmp_cap) {
+        dfree(ctx->d_sort_tmp);
+        ctx->sort_tmp_cap = 0;
+        CK(cudaMalloc(&ctx->d_sort_tmp, tw * sizeof(uint32_t)));
+        ctx->sort_tmp_cap = tw;
+    }
+    if (!ctx->d_sort_orand) CK(cudaMalloc(&ctx->d_sort_orand, 8 * sizeof(uint32_t)));
+    uint4* result = nullptr;
+    uint32_t passes = 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(bc_sort_records(reinterpret_cast<uint4*>(ctx->d_hits), reinterpret_cast<uint4*>(ctx->d_sort_scratch), ctx->n_hits, order,
+                       ctx->d_sort_hist, ctx->sort_hist_cap, ctx->d_sort_tmp, ctx->d_sort_orand, ctx->sm_count, ctx->stream,
+                       &result, &passes));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_sort_hits, ctx->ev0, ctx->ev1));
+    if (result != reinterpret_cast<uint4*>(ctx->d_hits)) {  // the sorted records ended up in the scratch buffer: swap roles
+        bc_hit* t = ctx->d_hits;
+        ctx->d_hits = ctx->d_sort_scratch;
+        ctx->d_sort_scratch = t;
+    }
     return BC_OK;
 }
 

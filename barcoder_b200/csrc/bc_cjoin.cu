@@ -583,7 +583,7 @@ __device__ __forceinline__ uint32_t cv_combo_of_slot(const SearchParams& p, uint
 // Resolve up to 32 queued candidates {dev position, rem mismatch mask, index entry, slot} with all
 // lanes: mask back to query positions, ownership, PAM annotation, ONE global atomic for the batch,
 // coalesced store of the surviving records.
-static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint4* q, uint32_t n) {
+static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* q, uint32_t n) {
 #ifdef CV_DEBUG_NO_RESOLVE  // timing experiment only: candidates are found but not turned into records
     if (p.cap != 1) return;
 #endif
@@ -591,9 +591,15 @@ static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint
     uint4 rec;
     bool ok = false;
     if (lane < n) {
-        const uint4 qe = q[lane];
+        const uint4 qe = q[lane];  // x record index, y rem mismatch mask, z index entry, w slot
         const uint32_t c = cv_combo_of_slot(p, qe.w);
-        ok = bc_make_hit(p, c, qe.x, p.ent_id[qe.z], bc_combo_rem_expand(p.combo[c], qe.y), &rec);
+        const uint32_t m = bc_combo_rem_expand(p.combo[c], qe.y);
+        // ownership first: nearly half of the candidates belong to an earlier combination and need
+        // neither their position nor their entry id (two random DRAM sectors)
+        if (p.lib_has_n || bc_owns(p, c, m)) {
+            const uint32_t pos = __ldg(&gwin[qe.x].x), e = __ldg(p.ent_id + qe.z);
+            ok = bc_make_hit(p, c, pos, e, m, &rec);
+        }
     }
     const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
     if (ballot == 0) return;
@@ -606,21 +612,23 @@ static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint
     }
 }
 
-static __device__ __noinline__ void cv_overflow(const SearchParams& p, uint32_t pos, uint32_t mr, uint32_t e, uint32_t slot) {
+static __device__ __noinline__ void cv_overflow(const SearchParams& p, const uint2* __restrict__ gwin, uint32_t rec_idx,
+                                                uint32_t mr, uint32_t e, uint32_t slot) {
     uint4 rec;
     const uint32_t c = cv_combo_of_slot(p, slot);
-    if (bc_make_hit(p, c, pos, p.ent_id[e], bc_combo_rem_expand(p.combo[c], mr), &rec)) {
+    if (bc_make_hit(p, c, __ldg(&gwin[rec_idx].x), p.ent_id[e], bc_combo_rem_expand(p.combo[c], mr), &rec)) {
         const unsigned long long g = atomicAdd(p.count, 1ull);
         if (g < p.cap) reinterpret_cast<uint4*>(p.hits)[g] = rec;
     }
 }
 
-__device__ __forceinline__ void cv_drain(const SearchParams& p, uint4* q, uint32_t* qn, uint32_t lane) {
+__device__ __forceinline__ void cv_drain(const SearchParams& p, const uint2* __restrict__ gwin, uint4* q, uint32_t* qn,
+                                         uint32_t lane) {
     __syncwarp();
     uint32_t nq = min(*qn, (uint32_t)CV_WQ);
     if (nq >= 32) {
         do {
-            cv_resolve(p, q + (nq - 32), 32);
+            cv_resolve(p, gwin, q + (nq - 32), 32);
             nq -= 32;
         } while (nq >= 32);
         __syncwarp();
@@ -644,19 +652,23 @@ static __device__ __noinline__ void cv_resolve_groups(const SearchParams& p, con
     const uint4 item = lane < n ? gq[lane] : make_uint4(0u, 0u, 0u, 0xffffffffu);  // x planes, y record index, z first entry, w slot
     if (item.w != 0xffffffffu) {
         const uint32_t wh = item.x & 0xffffu, wl = item.x >> 16;
-        const uint32_t n_e = min((uint32_t)CV_GROUP, __ldg(p.dir + item.w + 1) - item.z);
-        for (uint32_t j = 0; j < n_e; j++) {
-            const uint2 qe = __ldg(p.ent_hl + item.z + j);
-            const uint32_t m_ = (wh ^ qe.x) | (wl ^ qe.y);
-            if (__popc(m_) <= k) {
-                const uint32_t pos = __ldg(&gwin[item.y].x);
+        const uint32_t le = __ldg(p.dir + item.w + 1);  // end of the bucket: the last group may be ragged
+        // all CV_GROUP entry loads are issued before the first one is used (one at a time, every lane
+        // waited for CV_GROUP dependent DRAM round trips: 22 us per batch of 32 items in k_cfinish)
+        uint2 qe[CV_GROUP];
+#pragma unroll
+        for (int j = 0; j < CV_GROUP; j++) qe[j] = __ldg(p.ent_hl + min(item.z + j, le - 1u));
+#pragma unroll
+        for (int j = 0; j < CV_GROUP; j++) {
+            const uint32_t m_ = (wh ^ qe[j].x) | (wl ^ qe[j].y);
+            if (item.z + j < le && __popc(m_) <= k) {
                 const uint32_t qs = atomicAdd(qn, 1u);
-                if (qs < CV_WQ) q[qs] = make_uint4(pos, m_, item.z + j, item.w);
-                else cv_overflow(p, pos, m_, item.z + j, item.w);
+                if (qs < CV_WQ) q[qs] = make_uint4(item.y, m_, item.z + j, item.w);
+                else cv_overflow(p, gwin, item.y, m_, item.z + j, item.w);
             }
         }
     }
-    cv_drain(p, q, qn, lane);
+    cv_drain(p, gwin, q, qn, lane);
 }
 
 // Hand n <= 32 queue items over to k_cfinish through the global item queue (one atomic, one coalesced
@@ -871,7 +883,7 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
                 case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
                 default: gn = cv_tile<K, 4>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
             }
-            cv_drain(p, q, qn, lane);
+            cv_drain(p, gwin, q, qn, lane);
         }
     }
     while (gn) {  // up to CV_GQ - 1 items are still queued
@@ -881,7 +893,7 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
     }
     __syncwarp();
     const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
-    if (nq) cv_resolve(p, q, nq);
+    if (nq) cv_resolve(p, gwin, q, nq);
 }
 
 // Second level + hit resolution as a kernel of their own: every warp takes batches of 32 items of
@@ -905,7 +917,7 @@ __global__ void __launch_bounds__(CV_THREADS, 6) k_cfinish(const __grid_constant
     }
     __syncwarp();
     const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
-    if (nq) cv_resolve(p, q, nq);
+    if (nq) cv_resolve(p, gwin, q, nq);
 }
 
 // ------------------------------------------------------------------------------------------ host

@@ -62,3 +62,10 @@ cudaError_t bc_launch_index_build(const IndexParams& ip, uint32_t n_combos, uint
 #endif
 cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int sm_count, cudaStream_t st);
 void bc_probe_release_l2();
+
+// bc_sort.cu: stable LSD radix sort of the 16-byte hit records (order 0: spacer_id, gpos, strand;
+// order 1: spacer_id, mismatches, gpos, strand).  *result = rec or scratch, whichever holds the output.
+cudaError_t bc_sort_records(uint4* rec, uint4* scratch, uint64_t n, int order, uint32_t* d_hist, uint64_t hist_words,
+                            uint32_t* d_scan_tmp, uint32_t* d_orand, int sm_count, cudaStream_t st, uint4** result,
+                            uint32_t* passes_out);
+size_t bc_sort_hist_words(uint64_t n);

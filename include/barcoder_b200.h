@@ -106,7 +106,8 @@ typedef struct {
     float ms_genome_bucket;   /* join path: device time of the genome bucketing kernels */
     uint32_t index_launches;  /* kernels launched by the last bc_build_index          */
     uint32_t key_nt;          /* longest seed key of the scheme in use (bases)        */
-    uint32_t reserved[5];
+    float ms_sort_hits;       /* device time of the last bc_sort_hits                 */
+    uint32_t reserved[4];
 } bc_stats;
 
 int bc_abi_version(void);
@@ -186,6 +187,13 @@ int bc_set_slice_callback(bc_ctx* ctx, bc_slice_fn fn, void* user);
 int bc_peer_export(bc_ctx* ctx, uint64_t n_records, bc_hit** d_ptr, unsigned char handle[64]);
 int bc_peer_open(bc_ctx* ctx, const unsigned char handle[64], bc_hit** d_ptr);
 int bc_peer_close(bc_ctx* ctx, bc_hit* d_ptr, int owner);
+
+/* Orders the device hit buffer of the last bc_search in place, before it is copied out: the counterpart
+ * of bowtie writing its alignments read by read, and with --best fewest mismatches first
+ * (BowtieRunner.py:119).  order 0: (spacer_id, gpos, strand) - the canonical order of the parity tests;
+ * order 1: (spacer_id, mismatches, gpos, strand) - `bowtie --best`.  Records streamed earlier through a
+ * hit sink are not re-sent. */
+int bc_sort_hits(bc_ctx* ctx, int order);
 
 /* Device-side view of the result buffer (valid until the next bc_search/bc_destroy),
  * for callers that gather across GPUs without a host round trip. */

@@ -386,3 +386,46 @@ def test_cjoin_index_builders_agree(index_sort):
         n = s.search(3)
         assert n == len(ref)
         assert_same(_native.canonical_sort(s.hits()), ref)
+
+
+@pytest.mark.parametrize("order", ["canonical", "best"])
+def test_device_hit_sort(order):
+    """bc_sort_hits: the device buffer comes back ordered like the host lexsort the parity tests use
+    ("canonical") or like `bowtie --best` (fewest mismatches first within a read)."""
+    genome, off, lib = small_case(20, 3, seed=444, n=4000, G=600000, n_contigs=5, nfrac=0.004)
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        n = s.search(3)
+        raw = s.hits()
+        s.sort_hits(order)
+        got = s.hits()
+        assert s.stats()["ms_sort_hits"] > 0
+    assert n == len(got) > 5000
+    if order == "canonical":
+        want = raw[np.lexsort((raw["meta"] & 1, raw["gpos"], raw["spacer_id"]))]
+    else:
+        want = raw[np.lexsort((raw["meta"] & 1, raw["gpos"], (raw["meta"] >> 1) & 3, raw["spacer_id"]))]
+    assert got.tobytes() == want.tobytes()
+
+
+def test_device_hit_sort_large_and_degenerate():
+    """> 1 tile per digit pass, many equal keys (stability), single-record and empty buffers."""
+    genome, off = synth.random_genome(3000, seed=21, n_contigs=2, n_fraction=0.01, n_run=5)
+    lib = synth.random_library(50000, 6, seed=22, distinct=False)
+    with _native.Searcher(0) as s:
+        s.set_genome_array(genome, off)
+        s.set_library(lib)
+        s.set_pam("NGG", "downstream")
+        n = s.search(1)
+        raw = s.hits()
+        s.sort_hits("best")
+        got = s.hits()
+        assert n == len(got) > 500000
+        want = raw[np.lexsort((raw["meta"] & 1, raw["gpos"], (raw["meta"] >> 1) & 3, raw["spacer_id"]))]
+        assert got.tobytes() == want.tobytes()
+        s.set_library(np.frombuffer(b"ACGTAC", np.uint8).reshape(1, 6))
+        s.search(0)
+        s.sort_hits("canonical")
+        assert len(s.hits()) == s.stats()["hits"]

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../barcoder_b200/csrc"
 name=$1; shift
 objs=""
 mkdir -p /tmp/bcvar_$name
-for f in bc_api bc_kernels bc_join bc_cjoin bc_guides; do
+for f in bc_api bc_kernels bc_join bc_cjoin bc_sort bc_guides; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c $f.cu -o /tmp/bcvar_$name/$f.o &
   objs="$objs /tmp/bcvar_$name/$f.o"
 done
