@@ -20,7 +20,11 @@ The result is kept as a hit table (`.hits`, `.frame`) registered under `sam_path
 PySamParser(bowtie.sam_path).ranges needs no text round trip; a bowtie-style SAM file is also
 written to `sam_path` (always when write_sam=True, by default only up to SAM_AUTO_LIMIT lines).
 
-`num_threads` is accepted for compatibility and ignored (the search runs on one GPU).
+Several GPUs: `BowtieRunner(devices=[0, 1, ...])` (or devices="all") keeps one search context per GPU,
+each driven by its own host thread; every GPU holds the genome and the library and owns one slot
+range of the seed directory (BC_PARAM_SLOT_PART), so index build, window sort and verification all
+split N ways and the per-GPU hit sets are disjoint.  With devices="auto" the reference's
+`num_threads` argument of align() (bowtie -p, BowtieRunner.py:104,120) picks how many GPUs are used.
 There is no CPU fallback: any native error surfaces as BowtieError.
 """
 from __future__ import annotations
@@ -49,10 +53,12 @@ class BowtieError(Exception):
 
 
 class BowtieRunner(Logger):
-    def __init__(self, device=0, write_sam="auto", write_files=True):
+    def __init__(self, device=0, write_sam="auto", write_files=True, devices=None):
         super().__init__()
         self.temp_dir = tempfile.TemporaryDirectory()
         self.device = device
+        self.devices = devices          # None: [device]; list of ordinals; "all"; "auto" (num_threads decides)
+        self._searchers = []
         self.write_sam = write_sam
         self.write_files = write_files
         self._index_path = None
@@ -92,9 +98,10 @@ class BowtieRunner(Logger):
 
     def close(self):
         RESULTS.pop(self.sam_path, None)
-        if self._searcher is not None:
-            self._searcher.close()
-            self._searcher = None
+        for srch in self._searchers:
+            srch.close()
+        self._searchers = []
+        self._searcher = None
         self.temp_dir.cleanup()
 
     # ---- inputs
@@ -128,18 +135,39 @@ class BowtieRunner(Logger):
         self._pam = (pam, direction)
 
     # ---- compute
+    def _device_list(self):
+        if self.devices is None:
+            return [self.device]
+        if isinstance(self.devices, str):
+            n = _native.device_count()
+            if n == 0:
+                raise BowtieError("no usable CUDA device")
+            return list(range(n))           # "all" / "auto": align() may use fewer ("auto" + num_threads)
+        return list(self.devices)
+
     def create_index(self):
         if not self._contigs or sum(len(c) for c in self._contigs) == 0:
             raise BowtieError("BowtieRunner.fasta_path does not exist or is an empty")
-        self.info(f"Creating index on CUDA device {self.device} ...")
+        devs = self._device_list()
+        self.info(f"Creating index on CUDA device(s) {devs} ...")
         try:
-            if self._searcher is None:
-                self._searcher = _native.Searcher(self.device)
-            self._searcher.set_genome(self._contigs)
+            if not self._searchers:
+                self._searchers = [_native.Searcher(d) for d in devs]
+                self._searcher = self._searchers[0]
+            self._on_all(self._searchers, lambda srch, _i: srch.set_genome(self._contigs))
         except (_native.NativeError, _native.NativeLibraryError) as exc:
             raise BowtieError("Failed to index") from exc
         st = self._searcher.stats()
-        self.subproc(f"packed {st['genome_bases']} bases in {st['ms_pack_genome']:.3f} ms")
+        self.subproc(f"packed {st['genome_bases']} bases in {st['ms_pack_genome']:.3f} ms on {len(devs)} GPU(s)")
+
+    @staticmethod
+    def _on_all(searchers, fn):
+        """fn(searcher, index) on every context, one host thread per GPU (the C calls release the GIL)."""
+        if len(searchers) == 1:
+            return [fn(searchers[0], 0)]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(searchers)) as ex:
+            return list(ex.map(lambda a: fn(a[1], a[0]), enumerate(searchers)))
 
     def _pam_setting(self):
         if self._pam is not None:
@@ -154,7 +182,7 @@ class BowtieRunner(Logger):
         if self._searcher is None:
             raise BowtieError("bowtie failed: create_index() has not been called")
         k = int(num_mismatches)
-        self.info(f"Performing alignment on CUDA device {self.device} ...")
+        self.info(f"Performing alignment on {len(self._searchers)} CUDA device(s) ...")
         self.json(["bc_search", "-a", f"-v{k}", f"reads={len(self._reads)}"])
         pam = self._pam_setting()
         reads = self._reads
@@ -163,26 +191,40 @@ class BowtieRunner(Logger):
         for i, r in enumerate(upper):
             by_len.setdefault(len(r), []).append(i)
         parts, self.stats = [], []
+        active = self._searchers
+        if self.devices == "auto" and num_threads:
+            active = active[:max(1, min(len(active), int(num_threads)))]
+        world = len(active)
         try:
-            self._searcher.set_pam(pam[0] if pam else "", pam[1] if pam else "downstream")
             for L, idx in sorted(by_len.items()):
                 if L == 0 or L > 32:
                     if L > 32:
                         raise BowtieError(f"spacers longer than 32 nt are not supported (got {L})")
                     continue
                 idx = np.asarray(idx, dtype=np.int64)
-                self._searcher.set_library([upper[i] for i in idx])
-                self._searcher.search(k)
-                h = self._searcher.hits()
-                h["spacer_id"] = idx[h["spacer_id"]].astype(np.uint32)  # back to read order
-                parts.append(h)
-                self.stats.append(self._searcher.stats())
+                lib = [upper[i] for i in idx]
+
+                def one(srch, rank):
+                    srch.set_pam(pam[0] if pam else "", pam[1] if pam else "downstream")
+                    srch.set_library(lib)
+                    srch.set_param(_native.BC_PARAM_SLOT_PART, rank | (world << 16))
+                    srch.search(k)
+                    srch.sort_hits("best")   # bowtie --best: per read, fewest mismatches first (device radix sort)
+                    return srch.hits(), srch.stats()
+
+                for h, st in self._on_all(active, one):
+                    h["spacer_id"] = idx[h["spacer_id"]].astype(np.uint32)  # back to read order
+                    parts.append(h)
+                    self.stats.append(st)
         except (_native.NativeError, _native.NativeLibraryError) as exc:
             raise BowtieError(f"bc_search failed: {exc}") from exc
         hits = np.concatenate(parts) if parts else np.zeros(0, dtype=_native.HIT_DTYPE)
-        # bowtie --best: per read, fewest mismatches first; then by position for determinism
-        order = np.lexsort((hits["meta"] & 1, hits["gpos"], (hits["meta"] >> 1) & 3, hits["spacer_id"]))
-        self.hits = hits[order]
+        # bowtie --best: per read, fewest mismatches first; then by position for determinism.  One GPU and
+        # one spacer length: the device already sorted the buffer; otherwise the sorted parts are merged
+        if len(parts) > 1:
+            order = np.lexsort((hits["meta"] & 1, hits["gpos"], (hits["meta"] >> 1) & 3, hits["spacer_id"]))
+            hits = hits[order]
+        self.hits = hits
         self._pam_used = pam
         self.frame = self._build_frame()
         RESULTS[self.sam_path] = self

@@ -38,7 +38,7 @@ META_PAM_AMB = 1 << 5
 HIT_DTYPE = np.dtype([("spacer_id", "<u4"), ("gpos", "<u4"), ("mm_mask", "<u4"), ("meta", "<u4")])
 
 EXPORTS = (
-    "bc_abi_version", "bc_create", "bc_destroy", "bc_set_genome", "bc_set_genome_dev", "bc_set_library",
+    "bc_abi_version", "bc_device_count", "bc_create", "bc_destroy", "bc_set_genome", "bc_set_genome_dev", "bc_set_library",
     "bc_set_library_dev", "bc_set_pam", "bc_set_param", "bc_build_index", "bc_search", "bc_copy_hits",
     "bc_set_hit_sink", "bc_sort_hits", "bc_set_slice_callback", "bc_peer_export", "bc_peer_open", "bc_peer_close", "bc_hits_device", "bc_get_stats", "bc_last_error", "bc_enumerate_guides", "bc_copy_guides",
 )
@@ -62,11 +62,12 @@ class BcStats(ctypes.Structure):
         ("ms_build_index", ctypes.c_float), ("ms_search", ctypes.c_float),
         ("ms_scan_kernel", ctypes.c_float), ("ms_genome_bucket", ctypes.c_float),
         ("index_launches", ctypes.c_uint32), ("key_nt", ctypes.c_uint32), ("ms_sort_hits", ctypes.c_float),
-        ("reserved", ctypes.c_uint32 * 4),
+        ("ms_win_count", ctypes.c_float), ("ms_win_bin", ctypes.c_float), ("ms_win_place", ctypes.c_float),
+        ("ms_finish", ctypes.c_float),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 _lib = None
@@ -89,6 +90,7 @@ def load():
     vp, u8p, u32, u64, i32, i64 = (ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64,
                                    ctypes.c_int, ctypes.c_int64)
     L.bc_abi_version.restype = i32
+    L.bc_device_count.restype = i32
     L.bc_create.argtypes = [ctypes.POINTER(vp), i32]
     L.bc_destroy.argtypes = [vp]
     L.bc_destroy.restype = None
@@ -118,6 +120,11 @@ def load():
             getattr(L, name).restype = i32
     _lib = L
     return L
+
+
+def device_count():
+    """Usable CUDA devices."""
+    return int(load().bc_device_count())
 
 
 class NativeError(RuntimeError):

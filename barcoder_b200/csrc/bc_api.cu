@@ -103,6 +103,11 @@ static thread_local std::string g_create_err;
 
 extern "C" int bc_abi_version(void) { return BC_ABI_VERSION; }
 
+extern "C" int bc_device_count(void) {
+    int count = 0;
+    return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
+}
+
 extern "C" int bc_create(bc_ctx** out, int device) {
     if (!out) return BC_EINVAL;
     *out = nullptr;
@@ -760,6 +765,10 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
     ctx->stats.ms_search = ms_total;
     ctx->stats.ms_scan_kernel = ms_scan;
     ctx->stats.ms_genome_bucket = ms_bucket;
+    ctx->stats.ms_win_count = ctx->stats.path == 3 ? ctx->join.ms_kernel[0] : 0;
+    ctx->stats.ms_win_bin = ctx->stats.path == 3 ? ctx->join.ms_kernel[1] : 0;
+    ctx->stats.ms_win_place = ctx->stats.path == 3 ? ctx->join.ms_kernel[2] : 0;
+    ctx->stats.ms_finish = ctx->stats.path == 3 ? ctx->join.ms_kernel[5] : 0;
     if (n_hits_out) *n_hits_out = ctx->n_hits;
     if (ctx->sink.fn && ctx->n_hits > ctx->sink.reported) {  // the rest (all of it on the probe path)
         ctx->sink.fn(ctx->sink.fn_user, ctx->d_hits, ctx->sink.reported, ctx->n_hits);

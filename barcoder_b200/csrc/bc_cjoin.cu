@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
 // the global queue, one per lane (8 entries each, tested against the item's window), queues the
 // passing pairs and resolves them 32 at a time (ownership, PAM, one atomic per batch).  All of it
 // is dependent random loads; here they overlap across ~10^8 items instead of stalling the POPC loop.
-__global__ void __launch_bounds__(CV_THREADS, 6) k_cfinish(const __grid_constant__ SearchParams p, const uint2* __restrict__ gwin) {
+__global__ void __launch_bounds__(CV_THREADS, 4) k_cfinish(const __grid_constant__ SearchParams p, const uint2* __restrict__ gwin) {
     __shared__ uint4 s_q[CV_WARPS][CV_WQ];
     __shared__ uint32_t s_qn[CV_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1035,6 +1035,10 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     if (!ws.ev_a) JCK(cudaEventCreate(&ws.ev_a));
     if (!ws.ev_b) JCK(cudaEventCreate(&ws.ev_b));
     if (!ws.ev_c) JCK(cudaEventCreate(&ws.ev_c));
+    for (int i = 0; i < 6; i++) {
+        if (!ws.ev_k[i]) JCK(cudaEventCreate(&ws.ev_k[i]));
+        ws.ms_kernel[i] = 0;
+    }
     const uint32_t n_slots = (uint32_t)(dir_slots - 1);
 
     uint32_t max_low = 0;
@@ -1168,14 +1172,17 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         JCK(cudaEventRecord(ws.ev_c, st));
         k_ccount<false><<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_lut, ws.d_gdir);
         JCK(cudaGetLastError());
+        JCK(cudaEventRecord(ws.ev_k[0], st));  // end of the count kernel
         JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
         if (!one_pass) JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
         k_cbin_init<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, ws.d_gdir, n_bins, n_slots, d_bin_start, d_bin_cursor, d_bin_combo);
         JCK(cudaGetLastError());
         uint32_t bx = (npos + CJ_CHUNK - 1) / CJ_CHUNK;
         if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
+        JCK(cudaEventRecord(ws.ev_k[1], st));  // start of pass A
         k_cbin<false><<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, one_pass ? d_win : d_tmp);
         JCK(cudaGetLastError());
+        JCK(cudaEventRecord(ws.ev_k[2], st));  // end of pass A
         bc_launch_counter += 3;
         if (!one_pass) {
             k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, ws.d_gdir + n_slots, d_chunk_bin);
@@ -1185,6 +1192,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
                                        ws.d_gdir + n_slots, ws.d_work, max_sub, smem_b, sm_count, st));
             bc_launch_counter += 2;
         }
+        JCK(cudaEventRecord(ws.ev_k[3], st));      // end of pass B
         {   // tile list of this pass
             const uint32_t tg = (uint32_t)sm_count * 8u;
             k_ctile_count<<<tg, 256, 0, st>>>(ws.d_gdir, p.dir, n_slots, ws.d_tile_start, p.count_candidates ? p.count + 1 : nullptr);
@@ -1209,8 +1217,9 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
                 default: k_cverify<3><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
             }
             JCK(cudaGetLastError());
+            if (s + 1 == n_slices) JCK(cudaEventRecord(ws.ev_k[4], st));  // end of the (last) first-level kernel
             if (pv.item_cap) {
-                k_cfinish<<<(uint32_t)sm_count * 6u, CV_THREADS, 0, st>>>(pv, d_win);
+                k_cfinish<<<(uint32_t)sm_count * 4u, CV_THREADS, 0, st>>>(pv, d_win);
                 JCK(cudaGetLastError());
                 bc_launch_counter += 1;
             }
@@ -1228,6 +1237,16 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         ws.ms_join_kernels += ms;
         JCK(cudaEventElapsedTime(&ms, ws.ev_c, ws.ev_a));
         ws.ms_bucket_kernels += ms;
+        // per-kernel split (count, pass A, pass B, tile list, first-level verify, finish); the verify
+        // figures are those of the last slice, i.e. of the whole stage when nothing is streamed
+        JCK(cudaEventElapsedTime(&ms, ws.ev_c, ws.ev_k[0])); ws.ms_kernel[0] += ms;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_k[1], ws.ev_k[2])); ws.ms_kernel[1] += ms;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_k[2], ws.ev_k[3])); ws.ms_kernel[2] += ms;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_k[3], ws.ev_a)); ws.ms_kernel[3] += ms;
+        if (n_slices == 1) {
+            JCK(cudaEventElapsedTime(&ms, ws.ev_a, ws.ev_k[4])); ws.ms_kernel[4] += ms;
+            JCK(cudaEventElapsedTime(&ms, ws.ev_k[4], ws.ev_b)); ws.ms_kernel[5] += ms;
+        }
     }
     *launches = bc_launch_counter - launches0;
     return cudaSuccess;

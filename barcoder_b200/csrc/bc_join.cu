@@ -642,6 +642,8 @@ void bc_join_free(JoinWorkspace& ws) {
     if (ws.ev_a) cudaEventDestroy(ws.ev_a);
     if (ws.ev_b) cudaEventDestroy(ws.ev_b);
     if (ws.ev_c) cudaEventDestroy(ws.ev_c);
+    for (int i = 0; i < 6; i++)
+        if (ws.ev_k[i]) cudaEventDestroy(ws.ev_k[i]);
     ws = JoinWorkspace();
 }
 

@@ -20,6 +20,8 @@ struct JoinWorkspace {
     uint64_t item_cap = 0;
     uint32_t* d_lut = nullptr;       // compact join: byte-wise bit-permutation tables, one per combination
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    cudaEvent_t ev_k[6] = {nullptr};  // compact join: per-kernel split
+    float ms_kernel[6] = {0};         // count, pass A, pass B, tile list, first-level verify, finish
     uint64_t gdir_cap = 0, gwin_cap = 0, scan_tmp_cap = 0;
     float ms_join_kernels = 0;      // device time of the verify kernels of the last search
     float ms_bucket_kernels = 0;    // device time of the genome bucketing kernels (count, scan, scatter)

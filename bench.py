@@ -392,7 +392,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
-    acc = {"ms_build_index": 0.0, "ms_search": 0.0, "ms_scan_kernel": 0.0, "ms_genome_bucket": 0.0}
+    acc = {"ms_build_index": 0.0, "ms_search": 0.0, "ms_scan_kernel": 0.0, "ms_genome_bucket": 0.0,
+           "ms_win_count": 0.0, "ms_win_bin": 0.0, "ms_win_place": 0.0, "ms_finish": 0.0}
     launches = 0
     total_hits = 0
     step_wall = []
@@ -470,25 +471,38 @@ def main():
     E = 2.0 * n
     records = float(G) * combos / (world if shard in ("slots", "genome") else 1)   # (window, combination) records of this rank
     entries = E * combos / (world if shard == "slots" else 1)
-    parts = {"verify": acc["ms_scan_kernel"], "window_sort": acc["ms_genome_bucket"],
-             "index_build": acc["ms_build_index"]}
+    rec_b = 8.0 if st["path"] == 3 else 16.0
+    if st["path"] == 3:
+        # per-kernel split of the compact join (bc_stats; CUDA events on the library's stream)
+        parts = {"k_cverify": acc["ms_scan_kernel"] - acc["ms_finish"], "k_cfinish": acc["ms_finish"],
+                 "k_ccount": acc["ms_win_count"], "k_cbin": acc["ms_win_bin"], "k_cplace": acc["ms_win_place"],
+                 "index_build": acc["ms_build_index"]}
+        # algorithmic HBM bytes per launch: count reads the planes; pass A reads them and writes every record
+        # (8 B); pass B reads and writes every record; verify reads the records' x word... (all 8 B sectors) and
+        # the index entries (8 B) once; finish writes the hits; the index build moves 8 B records twice and
+        # writes 12 B per entry
+        alg_bytes = {"k_ccount": 3 * G / 8, "k_cbin": 3 * G / 8 + rec_b * records, "k_cplace": 2 * rec_b * records,
+                     "k_cverify": rec_b * records + 8.0 * entries, "k_cfinish": 16.0 * st["hits"],
+                     "index_build": (8 + 8 + 8 + 8 + 12) * entries}
+        names = {k2: k2 for k2 in parts}
+        names["index_build"] = "k_ccount<lib>+scan+k_cbin<lib>+k_cplace_bulk<lib>"
+        verify_key = "k_cverify"
+    else:
+        parts = {"verify": acc["ms_scan_kernel"], "window_sort": acc["ms_genome_bucket"],
+                 "index_build": acc["ms_build_index"]}
+        verify_key = "verify"
+        if st["path"] == 2:
+            alg_bytes = {"window_sort": 2 * (3 * G / 8) + 3 * rec_b * records,
+                         "verify": rec_b * records + 12.0 * entries + 16.0 * st["hits"],
+                         "index_build": (8 + 16 + 16 + 12) * entries}
+            names = {"verify": "k_verify_dense+k_verify_sparse", "window_sort": "k_bucket<0>+scan+k_window_bin+k_window_place",
+                     "index_build": "k_index_count+scan+k_index_scatter+k_fine_scatter"}
+        else:
+            alg_bytes = {"verify": 3 * G / 8 + 16.0 * st["hits"], "window_sort": 0.0,
+                         "index_build": (8 + 16 + 16 + 12) * entries}
+            names = {"verify": "k_scan_probe", "window_sort": "-", "index_build": "k_index_count+scan+scatter"}
     dominant = max(parts, key=parts.get)
     ipk = int_peak(local_rank)
-    rec_b = 8.0 if st["path"] == 3 else 16.0
-    if st["path"] >= 2:
-        # window sort: the planes are read by the count pass and by pass A, every record is written by
-        # pass A, read and written by pass B; verify: every record read once, the index entries (12 B)
-        # once, 16 B written per hit; index: entries read, written to the coarse array, read, written
-        alg_bytes = {"window_sort": 2 * (3 * G / 8) + 3 * rec_b * records,
-                     "verify": rec_b * records + 12.0 * entries + 16.0 * st["hits"],
-                     "index_build": (8 + 16 + 16 + 12) * entries}
-        names = {"verify": "k_cverify" if st["path"] == 3 else "k_verify_dense+k_verify_sparse",
-                 "window_sort": "k_ccount+scan+k_cbin+k_cplace" if st["path"] == 3 else "k_bucket<0>+scan+k_window_bin+k_window_place",
-                 "index_build": "k_index_count+scan+k_index_scatter+k_fine_scatter"}
-    else:
-        alg_bytes = {"verify": 3 * G / 8 + 16.0 * st["hits"], "window_sort": 0.0,
-                     "index_build": (8 + 16 + 16 + 12) * entries}
-        names = {"verify": "k_scan_probe", "window_sort": "-", "index_build": "k_index_count+scan+scatter"}
     traffic, traffic_note = None, None
     try:  # DRAM bytes per launch from the committed ncu --set full capture of this configuration
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as h:
@@ -515,20 +529,20 @@ def main():
         s.search(k)
         cand = s.stats()["candidates"]
         s.set_param(_native.BC_PARAM_COUNT_CANDIDATES, 0)
-        rate = cand / (acc["ms_scan_kernel"] / 1e3)
+        rate = cand / (parts[verify_key] / 1e3)
         pairs_k1 = float(G) * E / (world if shard != "library" else 1) * (k + 1) / 4.0 ** (L // (k + 1)) if L >= k + 1 else None
-        roofline_int = {"bound": "int_popc", "kernel": names["verify"], "achieved": rate / 1e12,
+        roofline_int = {"bound": "int_popc", "kernel": names[verify_key], "achieved": rate / 1e12,
                         "peak": ipk["popc_per_s"] / 1e12, "unit": "Tpairs/s (1 POPC per pair)",
                         "frac": rate / ipk["popc_per_s"], "frac_of_verify_atom": rate / ipk["verify_atom_per_s"],
                         "verify_atom_peak": ipk["verify_atom_per_s"] / 1e12, "candidates": cand,
                         "pairs_vs_k_plus_1": (cand / pairs_k1) if pairs_k1 else None,
-                        "traffic": traffic if dominant == "verify" else None,
-                        "share_of_step": acc["ms_scan_kernel"] / max(ms_per_step, 1e-9),
+                        "traffic": traffic if dominant == verify_key else None,
+                        "share_of_step": parts[verify_key] / max(ms_per_step, 1e-9),
                         "peak_source": "bench_kernels/int_peak.cu measured in this run (POPC: 16/clk/SM)",
                         "note": "peak = one POPC per candidate pair (1 pair in 8 is tested on the ALU pipe instead); "
                                 "pairs_vs_k_plus_1 = candidates / what the classic k+1-seed filter would verify"}
     # `roofline` = the bound that binds the dominant stage: the POPC pipe for verification, HBM otherwise
-    if dominant == "verify" and roofline_int:
+    if dominant == verify_key and roofline_int:
         roofline = dict(roofline_int, hbm_view=roofline_hbm)
     else:
         roofline = dict(roofline_hbm, int_view=roofline_int)

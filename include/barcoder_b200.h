@@ -107,10 +107,17 @@ typedef struct {
     uint32_t index_launches;  /* kernels launched by the last bc_build_index          */
     uint32_t key_nt;          /* longest seed key of the scheme in use (bases)        */
     float ms_sort_hits;       /* device time of the last bc_sort_hits                 */
-    uint32_t reserved[4];
+    float ms_win_count;       /* compact join: device time of the window count kernel (part of ms_genome_bucket) */
+    float ms_win_bin;         /* compact join: ... of radix pass A                    */
+    float ms_win_place;       /* compact join: ... of radix pass B                    */
+    float ms_finish;          /* compact join: ... of k_cfinish (part of ms_scan_kernel; 0 when streaming) */
 } bc_stats;
 
 int bc_abi_version(void);
+
+/* Usable CUDA devices (0 when there is none).  The reference's `num_threads` (bowtie -p,
+ * BowtieRunner.py:104,120) maps to this many GPUs at most. */
+int bc_device_count(void);
 
 /* Replaces `BowtieRunner()` / `__enter__` (BowtieRunner.py:14-20,49-50).  `device` is the
  * CUDA ordinal; the context owns a stream and all device memory it allocates. */

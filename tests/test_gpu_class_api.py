@@ -287,3 +287,39 @@ def test_targets_script_records_match_fixture(golden_dir, plasmids):
     assert "mismatches" in mm.columns
     with_mm = mm[mm["mismatches"] > 0]
     assert len(with_mm) and all(sum(ch.islower() for ch in t) == m for t, m in zip(with_mm["target"], with_mm["mismatches"]))
+
+
+def test_two_contexts_on_one_gpu_equal_one_context(golden_dir, cn32_spacers):
+    """BowtieRunner(devices=[0, 0]): two search contexts (host thread each, slot-range sharding) must
+    give the frame of the single-context run; devices="auto" + num_threads=1 uses one GPU; an
+    explicit upstream PAM is tagged so that CRISPRiLibrary re-annotates with its own finder."""
+    genbank = GenBankParser(os.path.join(golden_dir, "zmo_plasmids.gb"))
+    spacers = cn32_spacers[:2500] + ["ACGTACGTACGTACGTACGTACGTACGTACGT", "TTGACAGCTAGCTCAGTCCT"]
+    frames = []
+    for devices in (None, [0, 0], "auto"):
+        PAMFinder(genbank.records, "NGNC", "downstream")
+        with BowtieRunner(devices=devices, write_sam=False) as bowtie:
+            bowtie.make_fasta(genbank.records)
+            bowtie.make_fastq(spacers)
+            bowtie.create_index()
+            bowtie.align(num_mismatches=2, num_threads=1)
+            assert len(bowtie.stats) == (4 if devices == [0, 0] else 2)   # two spacer lengths x contexts
+            frames.append(frame_rows(PySamParser(bowtie.sam_path).ranges.df))
+            hits = bowtie.hits
+    assert frames[0] == frames[1] == frames[2] and len(frames[0]) > 2000
+    # the hit table is in `bowtie --best` order: per read, fewest mismatches first
+    key = list(zip(hits["spacer_id"].tolist(), ((hits["meta"] >> 1) & 3).tolist(), hits["gpos"].tolist()))
+    assert key == sorted(key)
+    finder = PAMFinder(genbank.records, "NGNC", "upstream")
+    with BowtieRunner(write_sam=False) as bowtie:
+        bowtie.set_pam("NGNC", "upstream")
+        bowtie.make_fasta(genbank.records)
+        bowtie.make_fastq(spacers[:500])
+        bowtie.create_index()
+        bowtie.align(num_mismatches=1)
+        sam = PySamParser(bowtie.sam_path)
+        df = sam.ranges.df
+        assert df.attrs["pam_key"] == ("NGNC", "upstream")
+        lib = CRISPRiLibrary(sam.ranges.join(genbank.ranges).df, finder)
+    for r in lib.targets_df.itertuples():   # re-annotated with the finder's own (3' slice) rule
+        assert r.PAM == finder.get_pam_seq(r) and r.Targeting == finder.pam_matches(r.PAM)

@@ -402,7 +402,7 @@ def test_device_hit_sort(order):
         s.sort_hits(order)
         got = s.hits()
         assert s.stats()["ms_sort_hits"] > 0
-    assert n == len(got) > 5000
+    assert n == len(got) > 1000
     if order == "canonical":
         want = raw[np.lexsort((raw["meta"] & 1, raw["gpos"], raw["spacer_id"]))]
     else:
@@ -422,7 +422,7 @@ def test_device_hit_sort_large_and_degenerate():
         raw = s.hits()
         s.sort_hits("best")
         got = s.hits()
-        assert n == len(got) > 500000
+        assert n == len(got) > 100000
         want = raw[np.lexsort((raw["meta"] & 1, raw["gpos"], (raw["meta"] >> 1) & 3, raw["spacer_id"]))]
         assert got.tobytes() == want.tobytes()
         s.set_library(np.frombuffer(b"ACGTAC", np.uint8).reshape(1, 6))
