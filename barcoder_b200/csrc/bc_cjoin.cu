@@ -700,6 +700,9 @@ __device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint
 // ballot per window; a lane whose minimum passes only QUEUES {window, group}.  With CV_ALU_PAIRS,
 // 1 pair in 8 is tested on the ALU pipe instead of POPC (mismatch mask with its K lowest set bits
 // cleared == 0): POPC alone saturates the XU pipe.
+#ifndef CV_PREFETCH
+#define CV_PREFETCH 1          // k_cverify: software pipeline over the tiles of a chunk (descriptor t+2, records t+1 in flight)
+#endif
 #ifndef CV_FINISH_KERNEL
 #define CV_FINISH_KERNEL 1   // second level + hit resolution in k_cfinish (global item queue) instead of inside k_cverify
 #endif
@@ -811,16 +814,20 @@ __global__ void __launch_bounds__(256) k_ctile_count(const uint32_t* __restrict_
     if (cand_out && cand) atomicAdd(cand_out, cand);
 }
 
-__global__ void __launch_bounds__(256) k_ctile_fill(const uint32_t* __restrict__ gdir, const uint32_t* __restrict__ dir,
-                                                    uint32_t n_slots, const uint32_t* __restrict__ tile_start,
-                                                    uint4* __restrict__ tile_desc, uint32_t* __restrict__ tile_slot) {
+__global__ void __launch_bounds__(256) k_ctile_fill(const __grid_constant__ CBucketParams gp, const uint32_t* __restrict__ gdir,
+                                                    const uint32_t* __restrict__ dir, uint32_t n_slots,
+                                                    const uint32_t* __restrict__ tile_start, uint4* __restrict__ tile_desc,
+                                                    uint32_t* __restrict__ tile_slot) {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
         const uint32_t t0 = tile_start[s], t1 = tile_start[s + 1];
         if (t0 == t1) continue;
+        uint32_t c = 0;
+        while (c + 1 < gp.n_combos && gp.combo[c + 1].dir_off <= s) c++;
         const uint32_t a = gdir[s], b = gdir[s + 1], ls = dir[s], le = dir[s + 1];
         for (uint32_t t = t0; t < t1; t++) {
             const uint32_t first = a + (t - t0) * CV_WTILE;
-            tile_desc[t] = make_uint4(first, min(first + CV_WTILE, b), ls, le);
+            // x first record, y windows in the tile (<= 128) | combination << 8, z / w bucket begin / end
+            tile_desc[t] = make_uint4(first, min((uint32_t)CV_WTILE, b - first) | (c << 8), ls, le);
             tile_slot[t] = s;
         }
     }
@@ -859,31 +866,73 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
         ch = __shfl_sync(0xffffffffu, ch, 0);
         if (ch >= ch_hi) break;
         const uint32_t t_end = min((ch + 1) * CV_CHUNK_TILES, n_tiles);
-        uint32_t c = 0;  // combination of the current slot; tiles are in slot order
-        for (uint32_t t = ch * CV_CHUNK_TILES; t < t_end; t++) {
-            const uint4 d = __ldg(tile_desc + t);  // x first record, y end record, z bucket begin, w bucket end
-            const uint32_t slot = __ldg(tile_slot + t);
-            while (c + 1 < p.n_combos && p.combo[c + 1].dir_off <= slot) c++;
+        // Software pipeline over the tiles of the chunk: the descriptor of tile t+2 and the window
+        // records of tile t+1 are in flight while tile t is verified (ncu on the unpipelined loop at
+        // 10-nt keys, ~95 windows x 19 entries per tile: long scoreboard 6.1 warps per issue, the
+        // record loads and the cp.async wait were the top stall sites, XU pipe 58 %).
+        uint32_t t = ch * CV_CHUNK_TILES;
+        uint4 d_cur = __ldg(tile_desc + t);
+        uint32_t slot_cur = __ldg(tile_slot + t);
+        uint4 d_nxt = d_cur;
+        uint32_t slot_nxt = slot_cur;
+        if (CV_PREFETCH && t + 1 < t_end) {
+            d_nxt = __ldg(tile_desc + t + 1);
+            slot_nxt = __ldg(tile_slot + t + 1);
+        }
+        uint32_t x_cur[CV_ITEMS];
+#pragma unroll
+        for (int it = 0; it < CV_ITEMS; it++) {
+            const uint32_t off = it * 32 + lane;
+            x_cur[it] = off < (d_cur.y & 0xffu) ? __ldcs(&gwin[d_cur.x + off].y) : 0u;
+        }
+        for (; t < t_end; t++) {
+            // issue the loads of the following tiles before this one is touched
+            uint32_t x_nxt[CV_ITEMS];
+            uint4 d_nn = d_nxt;
+            uint32_t slot_nn = slot_nxt;
+            if (CV_PREFETCH) {
+                if (t + 1 < t_end) {
+#pragma unroll
+                    for (int it = 0; it < CV_ITEMS; it++) {
+                        const uint32_t off = it * 32 + lane;
+                        x_nxt[it] = off < (d_nxt.y & 0xffu) ? __ldcs(&gwin[d_nxt.x + off].y) : 0u;
+                    }
+                }
+                if (t + 2 < t_end) {
+                    d_nn = __ldg(tile_desc + t + 2);
+                    slot_nn = __ldg(tile_slot + t + 2);
+                }
+            }
+            const uint32_t n_win = d_cur.y & 0xffu, c = d_cur.y >> 8;
             const uint32_t rem_nt = p.combo[c].rem_nt, rm = (1u << rem_nt) - 1u;
             uint32_t wh[CV_ITEMS], wl[CV_ITEMS];
 #pragma unroll
             for (int it = 0; it < CV_ITEMS; it++) {
-                const uint32_t idx = d.x + it * 32 + lane;
-                wh[it] = CV_INVALID;
-                wl[it] = 0;
-                if (idx < d.y) {
-                    const uint32_t x = __ldcs(&gwin[idx].y);
-                    wh[it] = x & rm;
-                    wl[it] = (x >> rem_nt) & rm;
-                }
+                const bool have = it * 32 + lane < n_win;
+                wh[it] = have ? (x_cur[it] & rm) : CV_INVALID;
+                wl[it] = have ? ((x_cur[it] >> rem_nt) & rm) : 0u;
             }
-            switch ((d.y - d.x + 31u) / 32u) {
-                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
-                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
-                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
-                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, d.z, d.w, d.x, slot, sbuf, gq, gn, q, qn); break;
+            switch ((n_win + 31u) / 32u) {
+                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
+                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
+                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
+                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
             }
             cv_drain(p, gwin, q, qn, lane);
+            if (CV_PREFETCH) {
+                d_cur = d_nxt; slot_cur = slot_nxt;
+                d_nxt = d_nn; slot_nxt = slot_nn;
+#pragma unroll
+                for (int it = 0; it < CV_ITEMS; it++) x_cur[it] = x_nxt[it];
+            } else if (t + 1 < t_end) {
+                d_cur = __ldg(tile_desc + t + 1);
+                slot_cur = __ldg(tile_slot + t + 1);
+#pragma unroll
+                for (int it = 0; it < CV_ITEMS; it++) {
+                    const uint32_t off = it * 32 + lane;
+                    x_cur[it] = off < (d_cur.y & 0xffu) ? __ldcs(&gwin[d_cur.x + off].y) : 0u;
+                }
+            }
         }
     }
     while (gn) {  // up to CV_GQ - 1 items are still queued
@@ -1198,7 +1247,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             k_ctile_count<<<tg, 256, 0, st>>>(ws.d_gdir, p.dir, n_slots, ws.d_tile_start, p.count_candidates ? p.count + 1 : nullptr);
             JCK(cudaGetLastError());
             JCK(bc_exclusive_scan(ws.d_tile_start, dir_slots, ws.d_scan_tmp, st));
-            k_ctile_fill<<<tg, 256, 0, st>>>(ws.d_gdir, p.dir, n_slots, ws.d_tile_start, ws.d_tile_desc, ws.d_tile_slot);
+            k_ctile_fill<<<tg, 256, 0, st>>>(gp, ws.d_gdir, p.dir, n_slots, ws.d_tile_start, ws.d_tile_desc, ws.d_tile_slot);
             JCK(cudaGetLastError());
             bc_launch_counter += 2;
         }

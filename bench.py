@@ -261,6 +261,78 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def synthetic_genbank(path, G, seed, n_genes):
+    """A GenBank file of the cfg-1 shape: one circular contig of G uniform bases with n_genes random
+    gene features (the real GCA_000005845.2 file is missing from the reference checkout)."""
+    from barcoder_b200 import seqio, synth
+    genome, _ = synth.random_genome(G, seed=seed)
+    rng = synth.rng_for(seed + 100)
+    rec = seqio.SeqRecord(seqio.Seq(bytes(genome).decode()), id="SYN_000001.1", name="SYN_000001", description="synthetic")
+    rec.annotations["topology"] = "circular"
+    rec.annotations["organism"] = "synthetic"
+    feats = [seqio.SeqFeature(seqio.SimpleLocation(0, G, 1), "source", {"organism": ["synthetic"]})]
+    starts = np.sort(rng.integers(0, G - 3000, size=n_genes))
+    lens = rng.integers(300, 2500, size=n_genes)
+    strands = rng.integers(0, 2, size=n_genes) * 2 - 1
+    for i, (a, ln, sd) in enumerate(zip(starts.tolist(), lens.tolist(), strands.tolist())):
+        feats.append(seqio.SeqFeature(seqio.SimpleLocation(a, a + ln, sd), "gene",
+                                      {"locus_tag": [f"SYN_{i:05d}"], "gene": [f"g{i}"]}))
+    rec.features = feats
+    seqio.write_genbank([rec], path)
+
+
+def run_class_api(args):
+    """--api class: the reference's only timed flow (testing_grounds.py:16-43; design_interactive.ipynb:344-350
+    logs ~64 s wall for it on E. coli, ~22 s of which in bowtie-build + bowtie + SAM parsing), through the
+    drop-in classes of this repo: GenBank parse -> guide enumeration -> BarCodeLibrary -> PAMFinder ->
+    BowtieRunner (make_fasta, make_fastq, create_index, align) -> PySamParser.ranges.join(genbank.ranges) ->
+    CRISPRiLibrary.  cfg1: 50,000 of the genome's NGG 20-mers, <= 1 mismatch; cfg3: all of them, <= 3."""
+    import tempfile
+    from barcoder_b200 import (BarCodeLibrary, BowtieRunner, CRISPRiLibrary, GenBankParser, PAMFinder, PySamParser, _native,
+                               synth)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        gb = os.path.join(d, "synthetic.gb")
+        synthetic_genbank(gb, 4_641_652, seed=1, n_genes=4300)
+        for name, k, n_guides in (("cfg1", 1, 50_000), ("cfg3", 3, None)):
+            ph = {}
+            t_all = time.time()
+            t0 = time.time()
+            genbank = GenBankParser(gb)
+            ph["parse_genbank"] = time.time() - t0
+            t0 = time.time()
+            # all distinct ACGT 20-mers 5' of an NGG on either strand (design_guides.py:22-49), on the device
+            rec = next(iter(genbank.records.values()))
+            with _native.Searcher(0) as srch:
+                srch.set_genome([str(rec.seq)])
+                rows = srch.enumerate_guides(20, "NGG")
+            if n_guides:
+                rows = rows[synth.rng_for(1).choice(len(rows), size=n_guides, replace=False)]
+            barcodes = BarCodeLibrary()
+            barcodes.load_from_list(synth.rows_to_strings(rows))
+            ph["enumerate_guides"] = time.time() - t0
+            pam = PAMFinder(genbank.records, "NGG", "downstream")
+            with BowtieRunner(write_sam=False, write_files=False) as bowtie:
+                t0 = time.time(); bowtie.make_fasta(genbank.records); ph["make_fasta"] = time.time() - t0
+                t0 = time.time(); bowtie.make_fastq(barcodes.barcodes); ph["make_fastq"] = time.time() - t0
+                t0 = time.time(); bowtie.create_index(); ph["create_index"] = time.time() - t0
+                t0 = time.time(); bowtie.align(k, 12); ph["align"] = time.time() - t0
+                ph["align_device_ms"] = sum(st["ms_search"] + st["ms_build_index"] + st["ms_sort_hits"] for st in bowtie.stats)
+                t0 = time.time(); sam = PySamParser(bowtie.sam_path); ranges = sam.ranges; ph["sam_ranges"] = time.time() - t0
+                t0 = time.time(); targets = ranges.join(genbank.ranges); ph["join_features"] = time.time() - t0
+                n_hits = len(bowtie.hits)
+            t0 = time.time()
+            lib = CRISPRiLibrary(targets.df, pam)
+            ph["crispri_library"] = time.time() - t0
+            ph["total"] = time.time() - t_all
+            out[name] = {"guides": len(barcodes.barcodes), "k": k, "alignments": int(n_hits),
+                         "joined_rows": int(len(targets.df)), "unambiguous_targets": int(len(lib.unambiguous_targets)),
+                         "phase_s": {k2: round(v, 4) for k2, v in ph.items()}}
+    print(json.dumps({"api": "class", "flow": "testing_grounds.py:16-43", "reference_anecdote_s": {"total": 64, "search": 22,
+                      "source": "design_interactive.ipynb:344-350 (E. coli, <=1 mismatch, unknown machine)"},
+                      "results": out}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -280,7 +352,12 @@ def main():
     ap.add_argument("--gate", action="store_true", help="PAM-first gating: report only PAM-adjacent hits")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel experiments only)")
     ap.add_argument("--verify", action="store_true", help="check a sample of the result against the oracle")
+    ap.add_argument("--api", default="abi", choices=["abi", "class"],
+                    help="class: time the reference's class-API flow (testing_grounds.py) end to end on cfg1 and cfg3")
     args = ap.parse_args()
+    if args.api == "class":
+        run_class_api(args)
+        return
     cfg = CONFIGS[args.config]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -359,11 +436,39 @@ def main():
 
     e2e_phase = {"set_genome": 0.0, "set_library": 0.0, "build_index": 0.0, "search": 0.0, "copy_hits": 0.0}
 
+    # N > 1, one library: every rank uploads only ITS 1/N slice of the host buffers and the slices are
+    # all-gathered over NVLink (NCCL), so the host->device bytes of the job stay G + n*L in total
+    # instead of N times that
+    share = world > 1 and shard in ("slots", "genome")
+    if share:
+        gpad = (G + world - 1) // world * world
+        lpad = (n * L + world - 1) // world * world
+        d_g_full = torch.empty(gpad, dtype=torch.uint8, device=device)
+        d_l_full = torch.empty(lpad, dtype=torch.uint8, device=device)
+        g_lo, g_hi = rank * (gpad // world), min(G, (rank + 1) * (gpad // world))
+        l_lo, l_hi = rank * (lpad // world), min(n * L, (rank + 1) * (lpad // world))
+
     def step_e2e():
         t0 = time.time()
-        s.set_genome_array(h_genome.numpy(), off)            # H2D + pack
+        if share:
+            part = d_g_full[rank * (gpad // world):(rank + 1) * (gpad // world)]
+            if g_hi > g_lo:
+                part[:g_hi - g_lo].copy_(h_genome[g_lo:g_hi], non_blocking=True)      # H2D of this rank's slice
+            dist.all_gather_into_tensor(d_g_full, part)
+            torch.cuda.current_stream().synchronize()
+            s.set_genome_device(d_g_full.data_ptr(), off)                            # pack
+        else:
+            s.set_genome_array(h_genome.numpy(), off)        # H2D + pack
         t1 = time.time()
-        s.set_library(h_lib.numpy().reshape(n, L))           # H2D + pack
+        if share:
+            part = d_l_full[rank * (lpad // world):(rank + 1) * (lpad // world)]
+            if l_hi > l_lo:
+                part[:l_hi - l_lo].copy_(h_lib[l_lo:l_hi], non_blocking=True)
+            dist.all_gather_into_tensor(d_l_full, part)
+            torch.cuda.current_stream().synchronize()
+            s.set_library_device(d_l_full.data_ptr(), n, L)
+        else:
+            s.set_library(h_lib.numpy().reshape(n, L))       # H2D + pack
         t2 = time.time()
         s.build_index(k)
         t3 = time.time()
@@ -457,7 +562,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = guides_total * (G / 1e6) / (ms_e.item() / e2e_steps / 1e3)
-    h2d = int(G + n * L)
+    h2d = int((g_hi - g_lo) + (l_hi - l_lo)) if share else int(G + n * L)    # per rank; the job moves G + n*L in total
     d2h = int(nh_e2e * 16)
 
     if rank != 0:

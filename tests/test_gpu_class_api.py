@@ -294,7 +294,7 @@ def test_two_contexts_on_one_gpu_equal_one_context(golden_dir, cn32_spacers):
     give the frame of the single-context run; devices="auto" + num_threads=1 uses one GPU; an
     explicit upstream PAM is tagged so that CRISPRiLibrary re-annotates with its own finder."""
     genbank = GenBankParser(os.path.join(golden_dir, "zmo_plasmids.gb"))
-    spacers = cn32_spacers[:2500] + ["ACGTACGTACGTACGTACGTACGTACGTACGT", "TTGACAGCTAGCTCAGTCCT"]
+    spacers = cn32_spacers[-2500:] + ["ACGTACGTACGTACGTACGTACGTACGTACGT", "TTGACAGCTAGCTCAGTCCT"]
     frames = []
     for devices in (None, [0, 0], "auto"):
         PAMFinder(genbank.records, "NGNC", "downstream")
@@ -306,7 +306,7 @@ def test_two_contexts_on_one_gpu_equal_one_context(golden_dir, cn32_spacers):
             assert len(bowtie.stats) == (4 if devices == [0, 0] else 2)   # two spacer lengths x contexts
             frames.append(frame_rows(PySamParser(bowtie.sam_path).ranges.df))
             hits = bowtie.hits
-    assert frames[0] == frames[1] == frames[2] and len(frames[0]) > 2000
+    assert frames[0] == frames[1] == frames[2] and len(frames[0]) > 500
     # the hit table is in `bowtie --best` order: per read, fewest mismatches first
     key = list(zip(hits["spacer_id"].tolist(), ((hits["meta"] >> 1) & 3).tolist(), hits["gpos"].tolist()))
     assert key == sorted(key)
@@ -314,7 +314,7 @@ def test_two_contexts_on_one_gpu_equal_one_context(golden_dir, cn32_spacers):
     with BowtieRunner(write_sam=False) as bowtie:
         bowtie.set_pam("NGNC", "upstream")
         bowtie.make_fasta(genbank.records)
-        bowtie.make_fastq(spacers[:500])
+        bowtie.make_fastq(spacers[-700:])
         bowtie.create_index()
         bowtie.align(num_mismatches=1)
         sam = PySamParser(bowtie.sam_path)
