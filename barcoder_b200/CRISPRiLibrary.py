@@ -17,6 +17,8 @@ class CRISPRiLibrary:
         self.targets_df = pyranges_df
         self.pam_finder = pam_finder
         self._annotate_targets()
+        # barcodes as integer codes: duplicated / isin on 10^6 strings cost seconds, on codes milliseconds
+        self._codes = pd.factorize(self.targets_df["Barcode"])[0] if len(self.targets_df) else np.zeros(0, dtype=np.int64)
         self.source_unique_targets = self._get_source_unique_targets()
         self.mapped_targets = self._get_mapped_targets()
         self.unique_targets = self._get_unique_targets()
@@ -35,16 +37,24 @@ class CRISPRiLibrary:
         df = self.targets_df
         return df["Targeting"].astype(bool) & df["Mapped"].astype(bool)
 
+    def _first_of_each_barcode(self, index):
+        """Boolean array over `index` (row labels of targets_df): True where the row is the first one of its barcode."""
+        codes = self._codes[np.asarray(index)]
+        first = np.zeros(len(codes), dtype=bool)
+        first[np.unique(codes, return_index=True)[1]] = True
+        return first
+
     def _get_source_unique_targets(self):
         """Barcodes with exactly... the FIRST `source`-feature row of every targeting, mapped
         barcode (rows whose Barcode was already seen are dropped; CRISPRiLibrary.py:37-45)."""
         df = self.targets_df
-        sel = df[(df["Type"] == "source") & self._targeting_mapped()]
-        return sel[~sel.duplicated(subset=["Barcode"])].reset_index(drop=True)
+        sel = df[(df["Type"] == "source").to_numpy() & self._targeting_mapped().to_numpy()]
+        return sel[self._first_of_each_barcode(sel.index)].reset_index(drop=True)
 
     def _get_mapped_targets(self):
         df = self.targets_df
-        sel = df[(df["Type"] != "source") & self._targeting_mapped()].copy()
+        sel = df[(df["Type"] != "source").to_numpy() & self._targeting_mapped().to_numpy()].copy()
+        self._mapped_rows = np.asarray(sel.index)
         start, end = sel["Start"].to_numpy(dtype=np.int64), sel["End"].to_numpy(dtype=np.int64)
         fs, fe = sel["Start_b"].to_numpy(dtype=np.int64), sel["End_b"].to_numpy(dtype=np.int64)
         strand_b = sel["Strand_b"].to_numpy()
@@ -55,10 +65,23 @@ class CRISPRiLibrary:
         return sel.reset_index(drop=True)
 
     def _get_unique_targets(self):
-        mapped = self._get_mapped_targets()
-        keep = mapped["Barcode"].isin(self.source_unique_targets.Barcode)
-        return mapped[keep].sort_values(["Chromosome", "Start", "End"]).reset_index(drop=True)
+        mapped = self.mapped_targets          # built once in __init__ (CRISPRiLibrary.py:86 recomputes it; same rows)
+        df = self.targets_df
+        src = (df["Type"] == "source").to_numpy() & self._targeting_mapped().to_numpy()
+        in_source = np.zeros(int(self._codes.max()) + 1 if len(self._codes) else 0, dtype=bool)
+        in_source[self._codes[src]] = True    # Barcode.isin(source_unique_targets.Barcode)
+        keep = in_source[self._codes[self._mapped_rows]] if len(mapped) else np.zeros(0, dtype=bool)
+        out = mapped[keep]
+        self._unique_codes = self._codes[self._mapped_rows][keep]
+        order = np.lexsort((out["End"].to_numpy(), out["Start"].to_numpy(),
+                            pd.factorize(out["Chromosome"], sort=True)[0])) if len(out) else np.zeros(0, dtype=np.int64)
+        self._unique_codes = self._unique_codes[order]
+        return out.iloc[order].reset_index(drop=True)
 
     def _get_unambiguous_targets(self):
         ut = self.unique_targets
-        return ut[~ut.duplicated(subset=["Barcode"]).reset_index(drop=True)]
+        if not len(ut):
+            return ut
+        first = np.zeros(len(ut), dtype=bool)
+        first[np.unique(self._unique_codes, return_index=True)[1]] = True
+        return ut[first]

@@ -701,7 +701,7 @@ __device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint
 // 1 pair in 8 is tested on the ALU pipe instead of POPC (mismatch mask with its K lowest set bits
 // cleared == 0): POPC alone saturates the XU pipe.
 #ifndef CV_PREFETCH
-#define CV_PREFETCH 1          // k_cverify: software pipeline over the tiles of a chunk (descriptor t+2, records t+1 in flight)
+#define CV_PREFETCH 0          // k_cverify: software pipeline over the tiles of a chunk (descriptor t+2, records t+1 in flight)
 #endif
 #ifndef CV_FINISH_KERNEL
 #define CV_FINISH_KERNEL 1   // second level + hit resolution in k_cfinish (global item queue) instead of inside k_cverify

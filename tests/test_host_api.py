@@ -256,3 +256,45 @@ def test_genbank_wrapped_contig_line(tmp_path):
     recs = list(seqio.read_genbank(str(path)))
     assert len(recs) == 1 and recs[0].id == "TEST1.1" and str(recs[0].seq) == "ACGT" * 6
     assert [f.type for f in recs[0].features] == ["source", "gene"]
+
+
+@pytest.mark.parametrize("pam,direction", [("NGNC", "downstream"), ("NGG", "upstream"), ("", "downstream"),
+                                           ("NNNN", "downstream")])
+def test_targets_rows_vectorised_equal_literal_loop(plasmids, cn32_spacers, pam, direction):
+    """targets.build_rows (column operations) == targets.build_rows_loop (the literal per-alignment
+    restatement of targets.py:310-464) on oracle hits over the circular plasmids with their 100 kb
+    overhang: every intermediate column (target, coords, diff, type ...) and the shaped result."""
+    from barcoder_b200 import targets
+    from oracle import oracle
+    sp = cn32_spacers[-1500:] + ["ACGTACGTACGTACGTACGTACGTACGTACGT", "acgtnacgtacgtacgtacg"]
+    ids = list(plasmids)
+    true_len = {r: len(plasmids[r].seq) for r in ids}
+    topo = [str(plasmids[r].seq) + str(plasmids[r].seq)[:targets.OVERHANG] for r in ids]
+    genes = targets.gene_intervals(plasmids)
+    parts, by_len = [], {}
+    for i, s in enumerate(sp):
+        by_len.setdefault(len(s), []).append(i)
+    for L, idx in sorted(by_len.items()):
+        h = oracle.search(topo, [sp[i].upper() for i in idx], 2)
+        h["spacer_id"] = np.asarray(idx)[h["spacer_id"]].astype(np.uint32)
+        parts.append(h)
+    hits = np.concatenate(parts)
+    hits = hits[np.lexsort((hits["meta"] & 1, hits["gpos"], hits["spacer_id"]))]
+    off = oracle.concat_genome(topo)[1].astype(np.int64)
+    a = targets.build_rows(hits, off, sp, sp, ids, topo, true_len, genes, pam, direction)
+    b = targets.build_rows_loop(hits, off, sp, sp, ids, topo, true_len, genes, pam, direction)
+    cols = sorted(set(a.columns) | set(b.columns))
+
+    def rows(df):
+        df = df.reindex(columns=cols)
+
+        def norm(v):  # the loop builds object columns that pandas widens to float when None is mixed in
+            if pd.isna(v):
+                return ""
+            return str(int(v)) if isinstance(v, (float, np.floating)) and float(v).is_integer() else str(v)
+        return sorted(tuple(norm(v) for v in r) for r in df.itertuples(index=False))
+    assert len(a) == len(b) > 1000 and rows(a) == rows(b)
+    fa, fb = targets.shape_results(a, true_len), targets.shape_results(b, true_len)
+    assert list(fa.columns) == list(fb.columns)
+    key = list(fa.columns)
+    assert fa.sort_values(key).reset_index(drop=True).astype(str).equals(fb.sort_values(key).reset_index(drop=True).astype(str))
