@@ -659,6 +659,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->pos_end = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)(ctx->par_scan_rank + 1) / (uint64_t)ctx->par_scan_world);
     p->n_contigs = ctx->n_contigs;
     p->slot_lo = ctx->slot_lo; p->slot_hi = ctx->slot_hi;
+    p->own_hash = ctx->par_slot_world > 1 ? 1u : 0u;  // balanced record counts across the slot-range shards
     p->sn = ctx->d_sn;
     p->lib_has_n = ctx->lib_has_n;
     p->L = ctx->L;

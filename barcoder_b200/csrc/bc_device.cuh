@@ -51,6 +51,7 @@ struct SearchParams {
     uint32_t n_words;           // words per plane (whole tiles + padding, bc_api.cu)
     uint32_t pos_begin, pos_end;  // window start positions this context scans (genome-range sharding)
     uint32_t slot_lo, slot_hi;    // directory slots this context owns (slot-range sharding; everything = [0, all slots))
+    uint32_t own_hash;            // ownership order: 0 = combination order, 1 = cyclic from a hash of (position, entry) (bc_owns)
     uint32_t n_contigs;
     // library
     const uint32_t* sn;         // [n] spacer-orientation mask of non-ACGT spacer characters
@@ -185,13 +186,22 @@ __device__ __forceinline__ bool bc_gate_window(const PamGate& g, const uint32_t*
 }
 
 // Ownership: several combinations may find the same alignment (every combination whose key
-// positions are mismatch-free does).  It is reported by the FIRST such combination in index order
-// and by no other, so every alignment is emitted exactly once and no dedup pass is needed.
-// m = mismatch mask in QUERY orientation; the caller found the pair through combination c, so
-// c's own key is mismatch-free by construction.
-__device__ __forceinline__ bool bc_owns(const SearchParams& p, uint32_t c, uint32_t m) {
-    for (uint32_t j = 0; j < c; j++)
+// positions are mismatch-free does).  It is reported by exactly ONE of them, so no dedup pass is
+// needed: the first such combination in index order (own_hash = 0), or in the CYCLIC order that
+// starts at a combination picked by a hash of (window position, entry) (own_hash = 1).  The plain
+// order is cheaper (no position / entry id needed to decide) but gives the low combinations most
+// of the multi-key hits: with the seed directory sharded over 8 GPUs, rank 0 then produced 1.66x
+// the average number of records and its merge / D2H became the tail, so slot-range sharding uses
+// the hashed order.  m = mismatch mask in QUERY orientation; the caller found the pair through
+// combination c, so c's own key is mismatch-free by construction.
+__device__ __forceinline__ bool bc_owns(const SearchParams& p, uint32_t c, uint32_t m, uint32_t pos, uint32_t e) {
+    const uint32_t n = p.n_combos;
+    uint32_t j = 0;
+    if (p.own_hash) j = (uint32_t)(((unsigned long long)((pos * 2654435761u) ^ (e * 2246822519u)) * n) >> 32);  // uniform in [0, n)
+    while (j != c) {
         if (!(m & p.combo[j].key_mask)) return false;
+        j = j + 1 == n ? 0u : j + 1;
+    }
     return true;
 }
 
@@ -211,7 +221,7 @@ static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t 
         m |= nm;
         if (__popc(m) > (int)p.k) return false;
     }
-    if (!bc_owns(p, c, m)) return false;
+    if (!bc_owns(p, c, m, pos, e)) return false;
 
     // contig of the window
     uint32_t lo = 0, hi = p.n_contigs;
