@@ -29,6 +29,7 @@ BC_PARAM_JOIN_CHUNK = 8
 BC_PARAM_KEY_NT = 9
 BC_PARAM_SLOT_PART = 10
 BC_PARAM_INDEX_SORT = 11
+BC_PARAM_KEY_CAP = 12
 PATH_AUTO, PATH_PROBE, PATH_JOIN, PATH_CJOIN = 0, 1, 2, 3
 
 META_PAM_OK = 1 << 3

@@ -45,7 +45,7 @@ struct bc_ctx {
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
     int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0, par_join_chunk = 0, par_key_nt = 0;
-    int64_t par_slot_rank = 0, par_slot_world = 1, par_index_sort = 0;
+    int64_t par_slot_rank = 0, par_slot_world = 1, par_index_sort = 0, par_key_cap = 0;
 
     // index
     bool have_index = false;
@@ -343,6 +343,9 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
             if (world < 1 || rank >= world) return fail(ctx, BC_EINVAL, "slot part must be rank | world << 16 with rank < world");
             ctx->par_slot_rank = rank; ctx->par_slot_world = world; ctx->have_index = false; return BC_OK;
         }
+        case BC_PARAM_KEY_CAP:
+            if (value < 0 || value > BC_KEY_MAX_NT) return fail(ctx, BC_EINVAL, "key cap must be 0..12");
+            ctx->par_key_cap = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_INDEX_SORT:
             if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "index sort must be 0, 1 or 2");
             ctx->par_index_sort = value; ctx->have_index = false; return BC_OK;
@@ -529,6 +532,7 @@ static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_o
     const uint64_t E = 2ull * ctx->n;
     uint32_t cap = 4;
     while (cap < BC_KEY_MAX_NT && (1ull << (2 * cap)) < 16 * (E ? E : 1)) cap++;
+    if (ctx->par_key_cap && cap > (uint32_t)ctx->par_key_cap) cap = (uint32_t)ctx->par_key_cap;
     double best_cost = 0;
     bool found = false;
     uint32_t best_path = 1;

@@ -1252,8 +1252,11 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             bc_launch_counter += 2;
         }
         JCK(cudaEventRecord(ws.ev_a, st));
-        // Streamed delivery: the slices halve (1/2, 1/4, ... and the last one repeated)
-        const uint32_t n_slices = sink ? BC_SINK_SLICES : 1;
+        // Streamed delivery: the slices halve (1/2, 1/4, ... and the last one repeated).  Short verify
+        // stages (a slot-range shard of an 8-GPU job runs ~3 ms) get fewer slices: every slice costs a
+        // launch tail and a host round trip
+        const double est_rec = (double)npos * p.n_combos * ((double)(p.slot_hi - p.slot_lo) / (double)(n_slots ? n_slots : 1));
+        const uint32_t n_slices = !sink ? 1u : est_rec > 6e8 ? (uint32_t)BC_SINK_SLICES : est_rec > 1.5e8 ? 3u : 2u;
         JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
             const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));

@@ -344,6 +344,7 @@ def main():
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 probe, 2 join, 3 compact join")
     ap.add_argument("--blocks", type=int, default=0)
     ap.add_argument("--key-nt", type=int, default=0, help="force a seed covering design with keys of this length")
+    ap.add_argument("--key-cap", type=int, default=0, help="cap the key length of block schemes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default=None, choices=["slots", "library", "genome"],
                     help="multi-GPU partitioning: slot ranges of the seed directory (strong scaling of one "
@@ -407,6 +408,8 @@ def main():
         s.set_param(_native.BC_PARAM_BLOCKS, args.blocks)
     if args.key_nt:
         s.set_param(_native.BC_PARAM_KEY_NT, args.key_nt)
+    if args.key_cap:
+        s.set_param(_native.BC_PARAM_KEY_CAP, args.key_cap)
     s.set_genome_device(d_genome.data_ptr(), off)
     s.set_library_device(d_lib.data_ptr(), n, L)
 

@@ -80,6 +80,8 @@ typedef struct {
                                         genome and library but indexes, sorts and verifies only its 1/world
                                         range of the seed directory; the contexts' hit sets are disjoint and
                                         their union is the whole result                                  */
+#define BC_PARAM_KEY_CAP 12           /* upper bound on the seed key length of block schemes (bases; 0 = from the
+                                        library size, at most 12): shorter keys = smaller directories    */
 #define BC_PARAM_INDEX_SORT 11        /* compact join path, library-side sort: 0 auto (radix passes), 1 two-level
                                         atomic scatter (the builder of the other paths), 2 radix passes   */
 #define BC_PARAM_JOIN_CHUNK 8        /* bucket-join path: upper bound on the window positions sorted per
