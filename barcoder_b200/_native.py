@@ -30,6 +30,7 @@ BC_PARAM_KEY_NT = 9
 BC_PARAM_SLOT_PART = 10
 BC_PARAM_INDEX_SORT = 11
 BC_PARAM_KEY_CAP = 12
+BC_PARAM_COMPACT_DIR = 13
 PATH_AUTO, PATH_PROBE, PATH_JOIN, PATH_CJOIN = 0, 1, 2, 3
 
 META_PAM_OK = 1 << 3

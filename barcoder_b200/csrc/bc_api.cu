@@ -45,7 +45,7 @@ struct bc_ctx {
     // params
     int64_t par_blocks = 0, par_path = 0, par_count = 0, par_hit_cap = 0, par_id_base = 0;
     int64_t par_scan_rank = 0, par_scan_world = 1, par_window_sort = 0, par_join_chunk = 0, par_key_nt = 0;
-    int64_t par_slot_rank = 0, par_slot_world = 1, par_index_sort = 0, par_key_cap = 0;
+    int64_t par_slot_rank = 0, par_slot_world = 1, par_index_sort = 0, par_key_cap = 0, par_compact_dir = 0;
 
     // index
     bool have_index = false;
@@ -59,6 +59,10 @@ struct bc_ctx {
     uint4* d_ent_tmp = nullptr;       // level-1 (coarse) output of the index scatter
     uint32_t* d_coarse_cursor = nullptr;
     uint64_t ent_cap = 0, dir_cap = 0, scan_tmp_cap = 0;
+    uint16_t* d_dir16 = nullptr;      // probe path: compact directory + entry fingerprints (bc_launch_dir_compact)
+    uint32_t *d_dir_base = nullptr, *d_ent_fp = nullptr, *d_dir_overflow = nullptr;
+    uint64_t dir16_cap = 0, fp_cap = 0;
+    bool compact_dir = false;
 
     // join workspace
     JoinWorkspace join;
@@ -149,6 +153,7 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn); dfree(ctx->d_any_n);
     dfree(ctx->d_dir); dfree(ctx->d_cursor); dfree(ctx->d_scan_tmp); dfree(ctx->d_ent_id); dfree(ctx->d_ent_hl);
     dfree(ctx->d_ent_tmp); dfree(ctx->d_coarse_cursor);
+    dfree(ctx->d_dir16); dfree(ctx->d_dir_base); dfree(ctx->d_ent_fp); dfree(ctx->d_dir_overflow);
     dfree(ctx->d_hits); dfree(ctx->d_count);
     dfree(ctx->d_sort_scratch); dfree(ctx->d_sort_hist); dfree(ctx->d_sort_tmp); dfree(ctx->d_sort_orand);
     bc_join_free(ctx->join);
@@ -343,6 +348,9 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
             if (world < 1 || rank >= world) return fail(ctx, BC_EINVAL, "slot part must be rank | world << 16 with rank < world");
             ctx->par_slot_rank = rank; ctx->par_slot_world = world; ctx->have_index = false; return BC_OK;
         }
+        case BC_PARAM_COMPACT_DIR:
+            if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "compact dir must be 0 (auto), 1 (off) or 2 (on)");
+            ctx->par_compact_dir = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_KEY_CAP:
             if (value < 0 || value > BC_KEY_MAX_NT) return fail(ctx, BC_EINVAL, "key cap must be 0..12");
             ctx->par_key_cap = value; ctx->have_index = false; return BC_OK;
@@ -644,6 +652,32 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     else
         CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_tmp,
                                  ctx->d_coarse_cursor, ctx->d_ent_hl, ctx->d_ent_id, ctx->sm_count, ctx->stream));
+    ctx->compact_dir = false;
+    if (path == 1 && ctx->par_compact_dir != 1 && (s.dir_slots > (1ull << 22) || ctx->par_compact_dir == 2)) {
+        // big directories on the probe path: 16-bit offsets + entry fingerprints (smaller L2 footprint)
+        const uint32_t n_slots = (uint32_t)(s.dir_slots - 1);
+        const uint64_t n16 = (uint64_t)((n_slots + 255) >> 8) * 257 + 2;
+        if (n16 > ctx->dir16_cap) {
+            dfree(ctx->d_dir16); dfree(ctx->d_dir_base);
+            ctx->dir16_cap = 0;
+            CK(cudaMalloc(&ctx->d_dir16, n16 * sizeof(uint16_t)));
+            CK(cudaMalloc(&ctx->d_dir_base, (((uint64_t)n_slots + 255) / 256 + 2) * sizeof(uint32_t)));
+            ctx->dir16_cap = n16;
+        }
+        if (ent_needed + 1 > ctx->fp_cap) {
+            dfree(ctx->d_ent_fp);
+            ctx->fp_cap = 0;
+            CK(cudaMalloc(&ctx->d_ent_fp, (ent_needed + 1) * sizeof(uint32_t)));
+            ctx->fp_cap = ent_needed + 1;
+        }
+        if (!ctx->d_dir_overflow) CK(cudaMalloc(&ctx->d_dir_overflow, sizeof(uint32_t)));
+        CK(bc_launch_dir_compact(ctx->d_dir, n_slots, ctx->d_dir16, ctx->d_dir_base, ctx->d_dir_overflow, ctx->d_ent_hl,
+                                 (uint32_t)ent_needed, ctx->d_ent_fp, ctx->sm_count, ctx->stream));
+        uint32_t overflow = 0;
+        CK(cudaMemcpyAsync(&overflow, ctx->d_dir_overflow, sizeof overflow, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->compact_dir = overflow == 0;
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev0, ctx->ev1));
@@ -676,6 +710,9 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->ent_hl = ctx->d_ent_hl;
     p->ent_id = ctx->d_ent_id;
     p->dir_entries = 2ull * ctx->n * ctx->n_combos;
+    p->dir16 = ctx->compact_dir ? ctx->d_dir16 : nullptr;
+    p->dir_base = ctx->compact_dir ? ctx->d_dir_base : nullptr;
+    p->ent_fp = ctx->compact_dir ? ctx->d_ent_fp : nullptr;
     p->P = ctx->P;
     p->pam_dir = ctx->pam_dir;
     p->pam_flags = ctx->pam_flags;
@@ -732,7 +769,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
                                (ctx->sink.host || ctx->sink.fn) ? &ctx->sink : nullptr));
         } else {
             CK(cudaEventRecord(ctx->ev2, ctx->stream));
-            CK(bc_launch_scan_probe(p, ctx->dir_slots * 4ull, ctx->sm_count, ctx->stream));
+            CK(bc_launch_scan_probe(p, ctx->compact_dir ? ctx->dir16_cap * 2ull : ctx->dir_slots * 4ull, ctx->sm_count, ctx->stream));
             CK(cudaEventRecord(ctx->ev3, ctx->stream));
             launches = 1;
         }

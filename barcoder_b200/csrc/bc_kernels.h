@@ -69,3 +69,7 @@ cudaError_t bc_sort_records(uint4* rec, uint4* scratch, uint64_t n, int order, u
                             uint32_t* d_scan_tmp, uint32_t* d_orand, int sm_count, cudaStream_t st, uint4** result,
                             uint32_t* passes_out);
 size_t bc_sort_hist_words(uint64_t n);
+
+// probe path: 16-bit directory (257 offsets per block of 256 slots) + block bases + entry fingerprints
+cudaError_t bc_launch_dir_compact(const uint32_t* dir, uint32_t n_slots, uint16_t* dir16, uint32_t* base, uint32_t* overflow,
+                                  const uint2* ent_hl, uint32_t n_entries, uint32_t* fp, int sm_count, cudaStream_t st);
