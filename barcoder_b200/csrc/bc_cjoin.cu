@@ -594,9 +594,9 @@ static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint
         const uint4 qe = q[lane];  // x record index, y rem mismatch mask, z index entry, w slot
         const uint32_t c = cv_combo_of_slot(p, qe.w);
         const uint32_t m = bc_combo_rem_expand(p.combo[c], qe.y);
-        // plain ownership order: decided from the mask alone, before the position and the entry id
-        // (two random DRAM sectors) are fetched - nearly half of the candidates are not owned
-        if (p.lib_has_n || p.own_hash || bc_owns(p, c, m, 0u, 0u)) {
+        // ownership is decided from the mask alone, before the position and the entry id (two random
+        // DRAM sectors) are fetched - nearly half of the candidates are not owned
+        if (p.lib_has_n || bc_owns(p, c, m)) {
             const uint32_t pos = __ldg(&gwin[qe.x].x), e = __ldg(p.ent_id + qe.z);
             ok = bc_make_hit(p, c, pos, e, m, &rec);
         }

@@ -193,22 +193,32 @@ __device__ __forceinline__ bool bc_gate_window(const PamGate& g, const uint32_t*
 
 // Ownership: several combinations may find the same alignment (every combination whose key
 // positions are mismatch-free does).  It is reported by exactly ONE of them, so no dedup pass is
-// needed: the first such combination in index order (own_hash = 0), or in the CYCLIC order that
-// starts at a combination picked by a hash of (window position, entry) (own_hash = 1).  The plain
-// order is cheaper (no position / entry id needed to decide) but gives the low combinations most
-// of the multi-key hits: with the seed directory sharded over 8 GPUs, rank 0 then produced 1.66x
-// the average number of records and its merge / D2H became the tail, so slot-range sharding uses
-// the hashed order.  m = mismatch mask in QUERY orientation; the caller found the pair through
-// combination c, so c's own key is mismatch-free by construction.
-__device__ __forceinline__ bool bc_owns(const SearchParams& p, uint32_t c, uint32_t m, uint32_t pos, uint32_t e) {
-    const uint32_t n = p.n_combos;
-    uint32_t j = 0;
-    if (p.own_hash) j = (uint32_t)(((unsigned long long)((pos * 2654435761u) ^ (e * 2246822519u)) * n) >> 32);  // uniform in [0, n)
-    while (j != c) {
-        if (!(m & p.combo[j].key_mask)) return false;
-        j = j + 1 == n ? 0u : j + 1;
+// needed.  The owner is a function of the mismatch mask alone (the same for every combination that
+// finds the pair, and known before the position or the entry id are fetched):
+//   own_hash = 0   the first combination in index order whose key is mismatch-free;
+//   own_hash = 1   the (hash(m) mod n_free)-th of the n_free mismatch-free combinations.
+// The plain order gives the low combinations most of the multi-key hits: with the seed directory
+// sharded over 8 GPUs, rank 0 then produced 1.66x the average number of records and its merge / D2H
+// became the tail, so slot-range sharding uses the hashed pick.  (A hash of (position, entry) would
+// balance just as well but needs two random DRAM sectors per candidate before it can decide:
+// measured +30 % on the finish kernel.)  m = mismatch mask in QUERY orientation; the caller found the
+// pair through combination c, so c's own key is mismatch-free by construction.
+__device__ __forceinline__ bool bc_owns(const SearchParams& p, uint32_t c, uint32_t m) {
+    if (!p.own_hash) {
+        for (uint32_t j = 0; j < c; j++)
+            if (!(m & p.combo[j].key_mask)) return false;
+        return true;
     }
-    return true;
+    uint32_t n_free = 0, mine = 0;
+    for (uint32_t j = 0; j < p.n_combos; j++) {
+        if (j == c) mine = n_free;
+        n_free += (m & p.combo[j].key_mask) ? 0u : 1u;
+    }
+    uint32_t h = m * 2654435761u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    return (uint32_t)(((unsigned long long)h * n_free) >> 32) == mine;
 }
 
 // Rare path: a (window, entry) pair passed the popcount filter in seed combination `c`.
@@ -227,7 +237,7 @@ static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t 
         m |= nm;
         if (__popc(m) > (int)p.k) return false;
     }
-    if (!bc_owns(p, c, m, pos, e)) return false;
+    if (!bc_owns(p, c, m)) return false;
 
     // contig of the window
     uint32_t lo = 0, hi = p.n_contigs;
