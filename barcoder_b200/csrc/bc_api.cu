@@ -59,10 +59,9 @@ struct bc_ctx {
     uint4* d_ent_tmp = nullptr;       // level-1 (coarse) output of the index scatter
     uint32_t* d_coarse_cursor = nullptr;
     uint64_t ent_cap = 0, dir_cap = 0, scan_tmp_cap = 0;
-    uint16_t* d_dir16 = nullptr;      // probe path: compact directory + entry fingerprints (bc_launch_dir_compact)
-    uint32_t *d_dir_base = nullptr, *d_ent_fp = nullptr, *d_dir_overflow = nullptr;
-    uint64_t dir16_cap = 0, fp_cap = 0;
-    bool compact_dir = false;
+    uint32_t* d_pdir = nullptr;       // probe path: packed directory (bc_launch_dir_pack)
+    uint64_t pdir_cap = 0;
+    bool packed_dir = false;
 
     // join workspace
     JoinWorkspace join;
@@ -153,7 +152,7 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     dfree(ctx->d_qh); dfree(ctx->d_ql); dfree(ctx->d_sn); dfree(ctx->d_any_n);
     dfree(ctx->d_dir); dfree(ctx->d_cursor); dfree(ctx->d_scan_tmp); dfree(ctx->d_ent_id); dfree(ctx->d_ent_hl);
     dfree(ctx->d_ent_tmp); dfree(ctx->d_coarse_cursor);
-    dfree(ctx->d_dir16); dfree(ctx->d_dir_base); dfree(ctx->d_ent_fp); dfree(ctx->d_dir_overflow);
+    dfree(ctx->d_pdir);
     dfree(ctx->d_hits); dfree(ctx->d_count);
     dfree(ctx->d_sort_scratch); dfree(ctx->d_sort_hist); dfree(ctx->d_sort_tmp); dfree(ctx->d_sort_orand);
     bc_join_free(ctx->join);
@@ -349,7 +348,7 @@ extern "C" int bc_set_param(bc_ctx* ctx, int key, int64_t value) {
             ctx->par_slot_rank = rank; ctx->par_slot_world = world; ctx->have_index = false; return BC_OK;
         }
         case BC_PARAM_COMPACT_DIR:
-            if (value < 0 || value > 2) return fail(ctx, BC_EINVAL, "compact dir must be 0 (auto), 1 (off) or 2 (on)");
+            if (value < 0 || value > 1) return fail(ctx, BC_EINVAL, "packed directory must be 0 (auto) or 1 (off)");
             ctx->par_compact_dir = value; ctx->have_index = false; return BC_OK;
         case BC_PARAM_KEY_CAP:
             if (value < 0 || value > BC_KEY_MAX_NT) return fail(ctx, BC_EINVAL, "key cap must be 0..12");
@@ -652,31 +651,17 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     else
         CK(bc_launch_index_build(ip, s.n_combos, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp, ctx->d_ent_tmp,
                                  ctx->d_coarse_cursor, ctx->d_ent_hl, ctx->d_ent_id, ctx->sm_count, ctx->stream));
-    ctx->compact_dir = false;
-    if (path == 1 && ctx->par_compact_dir != 1 && (s.dir_slots > (1ull << 22) || ctx->par_compact_dir == 2)) {
-        // big directories on the probe path: 16-bit offsets + entry fingerprints (smaller L2 footprint)
-        const uint32_t n_slots = (uint32_t)(s.dir_slots - 1);
-        const uint64_t n16 = (uint64_t)((n_slots + 255) >> 8) * 257 + 2;
-        if (n16 > ctx->dir16_cap) {
-            dfree(ctx->d_dir16); dfree(ctx->d_dir_base);
-            ctx->dir16_cap = 0;
-            CK(cudaMalloc(&ctx->d_dir16, n16 * sizeof(uint16_t)));
-            CK(cudaMalloc(&ctx->d_dir_base, (((uint64_t)n_slots + 255) / 256 + 2) * sizeof(uint32_t)));
-            ctx->dir16_cap = n16;
+    ctx->packed_dir = false;
+    if (path == 1 && ctx->par_compact_dir != 1 && ent_needed < (1ull << 26)) {
+        // probe path: one 4-byte load per directory probe instead of two
+        if (s.dir_slots > ctx->pdir_cap) {
+            dfree(ctx->d_pdir);
+            ctx->pdir_cap = 0;
+            CK(cudaMalloc(&ctx->d_pdir, s.dir_slots * sizeof(uint32_t)));
+            ctx->pdir_cap = s.dir_slots;
         }
-        if (ent_needed + 1 > ctx->fp_cap) {
-            dfree(ctx->d_ent_fp);
-            ctx->fp_cap = 0;
-            CK(cudaMalloc(&ctx->d_ent_fp, (ent_needed + 1) * sizeof(uint32_t)));
-            ctx->fp_cap = ent_needed + 1;
-        }
-        if (!ctx->d_dir_overflow) CK(cudaMalloc(&ctx->d_dir_overflow, sizeof(uint32_t)));
-        CK(bc_launch_dir_compact(ctx->d_dir, n_slots, ctx->d_dir16, ctx->d_dir_base, ctx->d_dir_overflow, ctx->d_ent_hl,
-                                 (uint32_t)ent_needed, ctx->d_ent_fp, ctx->sm_count, ctx->stream));
-        uint32_t overflow = 0;
-        CK(cudaMemcpyAsync(&overflow, ctx->d_dir_overflow, sizeof overflow, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->compact_dir = overflow == 0;
+        CK(bc_launch_dir_pack(ctx->d_dir, (uint32_t)(s.dir_slots - 1), ctx->d_pdir, ctx->sm_count, ctx->stream));
+        ctx->packed_dir = true;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -710,9 +695,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->ent_hl = ctx->d_ent_hl;
     p->ent_id = ctx->d_ent_id;
     p->dir_entries = 2ull * ctx->n * ctx->n_combos;
-    p->dir16 = ctx->compact_dir ? ctx->d_dir16 : nullptr;
-    p->dir_base = ctx->compact_dir ? ctx->d_dir_base : nullptr;
-    p->ent_fp = ctx->compact_dir ? ctx->d_ent_fp : nullptr;
+    p->pdir = ctx->packed_dir ? ctx->d_pdir : nullptr;
     p->P = ctx->P;
     p->pam_dir = ctx->pam_dir;
     p->pam_flags = ctx->pam_flags;
@@ -769,7 +752,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
                                (ctx->sink.host || ctx->sink.fn) ? &ctx->sink : nullptr));
         } else {
             CK(cudaEventRecord(ctx->ev2, ctx->stream));
-            CK(bc_launch_scan_probe(p, ctx->compact_dir ? ctx->dir16_cap * 2ull : ctx->dir_slots * 4ull, ctx->sm_count, ctx->stream));
+            CK(bc_launch_scan_probe(p, ctx->dir_slots * 4ull, ctx->sm_count, ctx->stream));
             CK(cudaEventRecord(ctx->ev3, ctx->stream));
             launches = 1;
         }

@@ -64,12 +64,7 @@ struct SearchParams {
     const uint2* ent_hl;
     const uint32_t* ent_id;
     unsigned long long dir_entries;  // index entries over all combinations
-    // probe path, compact directory (smaller L2 footprint): 16-bit bucket offsets inside blocks of 256 slots
-    // (257 per block: the last one is the block total), one 32-bit base per block, and a 4-byte
-    // fingerprint per entry (low 16 positions of both planes) that is tested before the full entry
-    const uint16_t* dir16;
-    const uint32_t* dir_base;
-    const uint32_t* ent_fp;
+    const uint32_t* pdir;            // probe path: packed directory (start | count << 26), one load per probe; or null
     // PAM
     uint32_t P, pam_dir, pam_flags;
     uint32_t pam_sets[8];       // per PAM position: allowed set over {A=1,C=2,G=4,T=8}

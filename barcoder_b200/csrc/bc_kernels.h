@@ -70,6 +70,5 @@ cudaError_t bc_sort_records(uint4* rec, uint4* scratch, uint64_t n, int order, u
                             uint32_t* passes_out);
 size_t bc_sort_hist_words(uint64_t n);
 
-// probe path: 16-bit directory (257 offsets per block of 256 slots) + block bases + entry fingerprints
-cudaError_t bc_launch_dir_compact(const uint32_t* dir, uint32_t n_slots, uint16_t* dir16, uint32_t* base, uint32_t* overflow,
-                                  const uint2* ent_hl, uint32_t n_entries, uint32_t* fp, int sm_count, cudaStream_t st);
+// probe path: packed directory, one 4-byte load per probe (start | count << 26)
+cudaError_t bc_launch_dir_pack(const uint32_t* dir, uint32_t n_slots, uint32_t* pdir, int sm_count, cudaStream_t st);

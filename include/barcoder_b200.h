@@ -82,8 +82,8 @@ typedef struct {
                                         their union is the whole result                                  */
 #define BC_PARAM_KEY_CAP 12           /* upper bound on the seed key length of block schemes (bases; 0 = from the
                                         library size, at most 12): shorter keys = smaller directories    */
-#define BC_PARAM_COMPACT_DIR 13       /* probe path: 0 auto (16-bit directory + entry fingerprints for big
-                                        directories), 1 off, 2 on                                    */
+#define BC_PARAM_COMPACT_DIR 13       /* probe path: 0 auto (packed directory, one 4-byte load per probe, when the
+                                        index has fewer than 2^26 entries), 1 off                      */
 #define BC_PARAM_INDEX_SORT 11        /* compact join path, library-side sort: 0 auto (radix passes), 1 two-level
                                         atomic scatter (the builder of the other paths), 2 radix passes   */
 #define BC_PARAM_JOIN_CHUNK 8        /* bucket-join path: upper bound on the window positions sorted per

@@ -431,13 +431,14 @@ def test_device_hit_sort_large_and_degenerate():
         assert len(s.hits()) == s.stats()["hits"]
 
 
-@pytest.mark.parametrize("L,k,blocks", [(32, 2, 3), (20, 3, 4), (20, 1, 2), (12, 0, 1)])
-def test_probe_compact_directory_and_fingerprints(L, k, blocks):
-    """Probe path with the 16-bit directory + 4-byte entry fingerprints forced on
-    (BC_PARAM_COMPACT_DIR = 2; automatic for big directories such as cfg 5's): same records,
-    including spacers with non-ACGT characters and duplicate-heavy buckets."""
+@pytest.mark.parametrize("packed", [0, 1])
+@pytest.mark.parametrize("L,k,blocks", [(32, 2, 3), (20, 3, 4), (12, 0, 1)])
+def test_probe_packed_directory(L, k, blocks, packed):
+    """Probe path with the packed directory (one 4-byte load per probe: start | count << 26; the
+    default) and without it (BC_PARAM_COMPACT_DIR = 1): same records, including buckets of 63 or
+    more equal entries, which fall back to the 32-bit directory."""
     genome, off, lib = small_case(L, k, seed=555 + L + k, n=3000, G=300000, n_contigs=5, nfrac=0.004)
-    lib[100:140] = lib[99]          # a bucket with many equal entries
+    lib[100:240] = lib[99]          # a bucket with 141 equal entries (> 63)
     ref = run_oracle(genome, off, lib, k, pam="NGG")
     with _native.Searcher(0) as s:
         s.set_genome_array(genome, off)
@@ -445,7 +446,7 @@ def test_probe_compact_directory_and_fingerprints(L, k, blocks):
         s.set_pam("NGG", "downstream")
         s.set_param(_native.BC_PARAM_PATH, 1)
         s.set_param(_native.BC_PARAM_BLOCKS, blocks)
-        s.set_param(_native.BC_PARAM_COMPACT_DIR, 2)
+        s.set_param(_native.BC_PARAM_COMPACT_DIR, packed)
         n = s.search(k)
         assert n == len(ref) and s.stats()["path"] == 1
         assert_same(_native.canonical_sort(s.hits()), ref)
