@@ -136,7 +136,7 @@ extern "C" int bc_create(bc_ctx** out, int device) {
         cudaMalloc(&ctx->d_count, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_any_n, sizeof(uint32_t)) != cudaSuccess) {
         g_create_err = std::string("CUDA context setup failed: ") + cudaGetErrorString(cudaGetLastError());
-        delete ctx;
+        bc_destroy(ctx);  // releases whatever was created before the failing call
         return BC_ECUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
@@ -180,6 +180,7 @@ static int set_genome_common(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t
     if (contig_offsets[0] != 0) return fail(ctx, BC_EINVAL, "contig_offsets[0] must be 0");
     if (G + n_contigs + 8192 >= (1ull << 32)) return fail(ctx, BC_ELIMIT, "genome longer than 2^32 - 8192 positions");
     ctx->have_genome = false;
+    ctx->have_index = false;  // the seed scheme and the scan path were costed with the previous genome size
     ctx->G = G;
     ctx->n_contigs = n_contigs;
     ctx->coff.assign(contig_offsets, contig_offsets + n_contigs + 1);

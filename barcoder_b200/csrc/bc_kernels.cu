@@ -475,6 +475,9 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_const
     }
 }
 
+static thread_local size_t g_l2_prev_limit = 0;
+static thread_local bool g_l2_saved = false;
+
 cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int sm_count, cudaStream_t st) {
     if (p.pos_end <= p.pos_begin) return cudaSuccess;
     uint32_t n_tiles = (p.pos_end + PROBE_TILE_POS - 1) / PROBE_TILE_POS;  // one past the last tile
@@ -491,7 +494,12 @@ cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int 
     const bool pin = BC_PROBE_PIN_DIRECTORY && max_persist > 0 && max_window > 0 && dir_bytes >= (8u << 20);
     if (pin) {
         uint64_t want = dir_bytes < (uint64_t)max_persist ? dir_bytes : (uint64_t)max_persist;
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want);
+        // device-wide setting: remember what the host application had and put it back afterwards
+        if (!g_l2_saved) {
+            cudaDeviceGetLimit(&g_l2_prev_limit, cudaLimitPersistingL2CacheSize);
+            g_l2_saved = true;
+        }
+        if ((size_t)want > g_l2_prev_limit) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)want);
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof attr);
         attr.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(p.pdir ? p.pdir : p.dir);
@@ -513,11 +521,13 @@ cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int 
     return e;
 }
 
-// called after the probe kernel has finished: give the L2 set-aside back to everybody
+// called after the probe kernel has finished: restore the caller's persisting-L2 limit.  Only this
+// stream's access-policy window was changed (cleared right after the launch); other users' persisting
+// lines are left alone (no cudaCtxResetPersistingL2Cache).
 void bc_probe_release_l2() {
-    if (!BC_PROBE_PIN_DIRECTORY) return;
-    cudaCtxResetPersistingL2Cache();
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    if (!BC_PROBE_PIN_DIRECTORY || !g_l2_saved) return;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_l2_prev_limit);
+    g_l2_saved = false;
 }
 
 cudaError_t bc_launch_pack_genome(const uint8_t* d_ascii, const uint64_t* d_coff, const uint32_t* d_start_dev,

@@ -10,6 +10,9 @@
  * All functions return BC_OK (0) or a negative BC_E* code; bc_last_error() gives the
  * text.  There is no CPU fallback: without a usable CUDA device bc_create fails.
  * A context is bound to one GPU and must be used from one host thread at a time.
+ * Side effects on the calling thread: every entry point makes the context's device current
+ * (cudaSetDevice) and leaves it current; the probe kernel raises the device's persisting-L2 limit
+ * for the duration of a search and restores the previous value afterwards.
  */
 #ifndef BARCODER_B200_H
 #define BARCODER_B200_H
@@ -153,8 +156,11 @@ int bc_set_pam(bc_ctx* ctx, const char* pam, int direction, uint32_t flags);
 
 int bc_set_param(bc_ctx* ctx, int key, int64_t value);
 
-/* Replaces create_index (BowtieRunner.py:78-102) for the library side: builds the
- * pigeonhole seed index for <= k mismatches on device (0 <= k <= 3). */
+/* Replaces create_index (BowtieRunner.py:78-102) for the library side: builds the seed index for
+ * <= k mismatches on device (0 <= k <= 3).  Both the library and the genome must be loaded: the seed
+ * scheme (block scheme or covering design, key length) and the scan path are chosen by a cost model
+ * that needs the genome size; a later bc_set_genome / bc_set_library invalidates the index and
+ * bc_search rebuilds it. */
 int bc_build_index(bc_ctx* ctx, int k);
 
 /* Replaces align (BowtieRunner.py:104-141): every ungapped end-to-end alignment of every
