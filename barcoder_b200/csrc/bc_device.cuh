@@ -108,6 +108,10 @@ __device__ __forceinline__ uint32_t bc_combo_gather_key(const ComboDesc& cd, uin
 // Seed key of a window / query under a combination: the key positions of the hi plane above those
 // of the lo plane.  Any bijection works as long as the library index and the genome side agree.
 __device__ __forceinline__ uint32_t bc_combo_key(const ComboDesc& cd, uint32_t h, uint32_t l) {
+    if (cd.n_pieces == 1) {  // one contiguous run (every k+1-seed block scheme): no loop
+        const uint32_t st = cd.start[0], m = (1u << cd.key_nt) - 1u;
+        return (((h >> st) & m) << cd.key_nt) | ((l >> st) & m);
+    }
     return (bc_combo_gather_key(cd, h) << cd.key_nt) | bc_combo_gather_key(cd, l);
 }
 
@@ -271,7 +275,9 @@ static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t 
 // Hit records are staged per CTA in shared memory and flushed with ONE global atomic per flush:
 // a single-address atomicAdd per hit serialises in L2 (~2.4 ns each, measured) and would cap
 // cfg 4 (5.9e7 hits) at ~140 ms on its own.
+#ifndef BC_STAGE_CAP
 #define BC_STAGE_CAP 1024
+#endif
 
 struct HitStage {
     uint32_t n;

@@ -340,7 +340,10 @@ cudaError_t bc_launch_dir_pack(const uint32_t* dir, uint32_t n_slots, uint32_t* 
 //   B  one survivor per lane: seed keys, directory probes (loads batched), non-empty buckets are
 //      pushed to a per-warp list {window, combination, begin, end};
 //   C  one bucket per lane: XOR/LOP3 + POPC over its entries, hits staged per CTA.
-__global__ void __launch_bounds__(PROBE_THREADS) k_scan_probe(const __grid_constant__ SearchParams p,
+#ifndef PROBE_MINBLOCKS
+#define PROBE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(const __grid_constant__ SearchParams p,
                                                               uint32_t n_tiles) {
     // plane words [w0 - 1, w0 + 66): the tile, the word before it (PAM left of the first window)
     // and two after it (window + PAM right of the last window)
@@ -482,7 +485,7 @@ cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int 
     if (p.pos_end <= p.pos_begin) return cudaSuccess;
     uint32_t n_tiles = (p.pos_end + PROBE_TILE_POS - 1) / PROBE_TILE_POS;  // one past the last tile
     uint32_t my_tiles = n_tiles - p.pos_begin / PROBE_TILE_POS;
-    uint32_t grid = (uint32_t)sm_count * 8u;
+    uint32_t grid = (uint32_t)sm_count * (PROBE_MINBLOCKS > 8 ? PROBE_MINBLOCKS : 8u);
     if (grid > my_tiles) grid = my_tiles;
     // Every window costs C random 8-byte reads of the directory; on a large genome the streaming
     // planes and the hit records would keep evicting it (cfg 5: L2 hit rate 63 %, 37 % of the probe
