@@ -65,7 +65,7 @@ class BcStats(ctypes.Structure):
         ("ms_scan_kernel", ctypes.c_float), ("ms_genome_bucket", ctypes.c_float),
         ("index_launches", ctypes.c_uint32), ("key_nt", ctypes.c_uint32), ("ms_sort_hits", ctypes.c_float),
         ("ms_win_count", ctypes.c_float), ("ms_win_bin", ctypes.c_float), ("ms_win_place", ctypes.c_float),
-        ("ms_finish", ctypes.c_float),
+        ("ms_finish", ctypes.c_float), ("search_attempts", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
     ]
 
     def as_dict(self):

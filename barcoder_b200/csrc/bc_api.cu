@@ -738,7 +738,9 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         ctx->hit_cap = want;
     }
     float ms_total = 0, ms_scan = 0, ms_bucket = 0;
+    ctx->stats.search_attempts = 0;
     for (int attempt = 0; attempt < 3; attempt++) {
+        ctx->stats.search_attempts++;
         SearchParams p;
         fill_params(ctx, &p);
         CK(cudaMemsetAsync(ctx->d_count, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -758,7 +760,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
             launches = 1;
         }
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
-        unsigned long long counts[4] = {0, 0, 0, 0};
+        unsigned long long counts[6] = {0, 0, 0, 0, 0, 0};
         CK(cudaMemcpyAsync(counts, ctx->d_count, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->stats.path == 1) bc_probe_release_l2();
@@ -771,6 +773,17 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         ctx->stats.scan_launches += launches;
         ctx->stats.candidates = counts[1];
         ctx->stats.probes = counts[2];
+        if (ctx->stats.path == 3 && counts[5] > ctx->join.item_cap) {
+            // compact join: the item queue between k_cverify and k_cfinish overflowed and batches were dropped.
+            // The demand is known now: repeat the search with a queue of that size.
+            if (ctx->sink.fn) {
+                ctx->stats.hits = counts[0];
+                return fail(ctx, BC_ELIMIT, "bc_search: verify item queue overflow with a slice callback installed (raise BC_PARAM_HIT_CAPACITY)");
+            }
+            if (attempt == 2) return fail(ctx, BC_ECUDA, "verify item queue kept overflowing");
+            ctx->join.item_want = counts[5] + counts[5] / 8 + 1024;
+            continue;
+        }
         if (counts[0] <= ctx->hit_cap) {
             ctx->n_hits = counts[0];
             break;

@@ -20,6 +20,7 @@
 //   k_cverify<K>  slot-aligned warp-tiles of <= 128 windows against the slot's library bucket
 #include "bc_join.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "bc_kernels.h"
@@ -567,6 +568,9 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
 #ifndef CV_MINBLOCKS
 #define CV_MINBLOCKS 4
 #endif
+#ifndef CV_ITEM_POS
+#define CV_ITEM_POS 1       // items handed to k_cfinish carry the window's dev position (fetched at flush time) instead of the record index
+#endif
 #define CV_INVALID 0xf0000000u  // rem plane of a missing window: 4 mismatches above the rem bits, never <= k
 
 __device__ __forceinline__ void cv_cp_async8(void* smem, const void* gmem) {
@@ -583,7 +587,10 @@ __device__ __forceinline__ uint32_t cv_combo_of_slot(const SearchParams& p, uint
 // Resolve up to 32 queued candidates {dev position, rem mismatch mask, index entry, slot} with all
 // lanes: mask back to query positions, ownership, PAM annotation, ONE global atomic for the batch,
 // coalesced store of the surviving records.
-static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* q, uint32_t n) {
+// ypos: the queue entries carry the dev position itself (k_cfinish: the verify kernel fetched it when it flushed
+// the item, while the record's sector was still in L2) instead of the record index.
+static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* q, uint32_t n,
+                                               bool ypos) {
 #ifdef CV_DEBUG_NO_RESOLVE  // timing experiment only: candidates are found but not turned into records
     if (p.cap != 1) return;
 #endif
@@ -597,7 +604,7 @@ static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint
         // ownership is decided from the mask alone, before the position and the entry id (two random
         // DRAM sectors) are fetched - nearly half of the candidates are not owned
         if (p.lib_has_n || bc_owns(p, c, m)) {
-            const uint32_t pos = __ldg(&gwin[qe.x].x), e = __ldg(p.ent_id + qe.z);
+            const uint32_t pos = ypos ? qe.x : __ldg(&gwin[qe.x].x), e = __ldg(p.ent_id + qe.z);
             ok = bc_make_hit(p, c, pos, e, m, &rec);
         }
     }
@@ -613,22 +620,22 @@ static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint
 }
 
 static __device__ __noinline__ void cv_overflow(const SearchParams& p, const uint2* __restrict__ gwin, uint32_t rec_idx,
-                                                uint32_t mr, uint32_t e, uint32_t slot) {
+                                                uint32_t mr, uint32_t e, uint32_t slot, bool ypos) {
     uint4 rec;
     const uint32_t c = cv_combo_of_slot(p, slot);
-    if (bc_make_hit(p, c, __ldg(&gwin[rec_idx].x), p.ent_id[e], bc_combo_rem_expand(p.combo[c], mr), &rec)) {
+    if (bc_make_hit(p, c, ypos ? rec_idx : __ldg(&gwin[rec_idx].x), p.ent_id[e], bc_combo_rem_expand(p.combo[c], mr), &rec)) {
         const unsigned long long g = atomicAdd(p.count, 1ull);
         if (g < p.cap) reinterpret_cast<uint4*>(p.hits)[g] = rec;
     }
 }
 
 __device__ __forceinline__ void cv_drain(const SearchParams& p, const uint2* __restrict__ gwin, uint4* q, uint32_t* qn,
-                                         uint32_t lane) {
+                                         uint32_t lane, bool ypos = false) {
     __syncwarp();
     uint32_t nq = min(*qn, (uint32_t)CV_WQ);
     if (nq >= 32) {
         do {
-            cv_resolve(p, gwin, q + (nq - 32), 32);
+            cv_resolve(p, gwin, q + (nq - 32), 32, ypos);
             nq -= 32;
         } while (nq >= 32);
         __syncwarp();
@@ -645,7 +652,7 @@ __device__ __forceinline__ void cv_drain(const SearchParams& p, const uint2* __r
 // contain a passing pair somewhere in the warp, and re-reading their records cost 13 GB of random
 // sectors - ncu: 31.7 GB read for 11.5 GB algorithmic.)
 static __device__ __noinline__ void cv_resolve_groups(const SearchParams& p, const uint2* __restrict__ gwin,
-                                                      const uint4* gq, uint32_t n, uint4* q, uint32_t* qn) {
+                                                      const uint4* gq, uint32_t n, uint4* q, uint32_t* qn, bool ypos) {
     const uint32_t lane = threadIdx.x & 31u;
     const int k = (int)p.k;
     __syncwarp();
@@ -664,20 +671,24 @@ static __device__ __noinline__ void cv_resolve_groups(const SearchParams& p, con
             if (item.z + j < le && __popc(m_) <= k) {
                 const uint32_t qs = atomicAdd(qn, 1u);
                 if (qs < CV_WQ) q[qs] = make_uint4(item.y, m_, item.z + j, item.w);
-                else cv_overflow(p, gwin, item.y, m_, item.z + j, item.w);
+                else cv_overflow(p, gwin, item.y, m_, item.z + j, item.w, ypos);
             }
         }
     }
-    cv_drain(p, gwin, q, qn, lane);
+    cv_drain(p, gwin, q, qn, lane, ypos);
 }
 
 // Hand n <= 32 queue items over to k_cfinish through the global item queue (one atomic, one coalesced
 // 16-byte store per lane).  Re-examining them inside the verify kernel cost it 45 % of its time
 // (timing experiment, cfg 4 at 9-nt keys: first level alone 22.6 ms, + second level 32.9 ms,
 // + hit resolution 39.1 ms): the dependent loads of the slow path stall warps that should be
-// feeding the POPC pipe.  If the queue is full the items are resolved here, as before.
-__device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* gq,
-                                               uint32_t n, uint4* q, uint32_t* qn) {
+// feeding the POPC pipe.  The verify kernel therefore contains no slow path at all - not even as a
+// fallback: a call inside its hot loop made ptxas keep loop state in local memory (324 bytes of
+// spills; with 214 KB of the SM's 256 KB carved out as shared memory those reloads miss L1: ncu put
+// 25 % of the stall samples on the instructions behind them).  If the queue is full the batch is
+// dropped, the demand keeps counting, k_cfinish records it in count[5] and bc_search repeats the
+// search with a queue of the demanded size (like a hit-buffer overflow).
+__device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* gq, uint32_t n) {
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long base = 0;
     __syncwarp();
@@ -686,11 +697,15 @@ __device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint
     if (lane == 0) base = atomicAdd(p.count + 4, 32ull);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base + 32ull <= p.item_cap) {
-        p.items[base + lane] = lane < n ? gq[lane] : make_uint4(0u, 0u, 0u, 0xffffffffu);
-        __syncwarp();
-    } else {
-        cv_resolve_groups(p, gwin, gq, n, q, qn);
+        uint4 item = lane < n ? gq[lane] : make_uint4(0u, 0u, 0u, 0xffffffffu);
+#if CV_ITEM_POS
+        // the item leaves with the window's dev position instead of its record index: the record's sector was read a
+        // moment ago (L2 hit), in k_cfinish the same fetch is a random DRAM sector per candidate
+        if (lane < n) item.y = __ldg(&gwin[item.y].x);
+#endif
+        p.items[base + lane] = item;
     }
+    __syncwarp();
 }
 
 // One warp-tile: `ITEMS` (1..CV_ITEMS, warp-uniform) resident windows per lane against the bucket
@@ -700,43 +715,114 @@ __device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint
 // ballot per window; a lane whose minimum passes only QUEUES {window, group}.  With CV_ALU_PAIRS,
 // 1 pair in 8 is tested on the ALU pipe instead of POPC (mismatch mask with its K lowest set bits
 // cleared == 0): POPC alone saturates the XU pipe.
-#ifndef CV_PREFETCH
-#define CV_PREFETCH 0          // k_cverify: software pipeline over the tiles of a chunk (descriptor t+2, records t+1 in flight)
-#endif
-#ifndef CV_FINISH_KERNEL
-#define CV_FINISH_KERNEL 1   // second level + hit resolution in k_cfinish (global item queue) instead of inside k_cverify
-#endif
+//
+// Tile pipeline (round 2).  At 10-nt keys a tile is ~95 windows x ~19 entries: ~70 POPC per lane
+// behind a chain of three dependent memory latencies (descriptor -> window records / bucket ->
+// cp.async wait), 15.7 million times.  ncu on the unpipelined loop: long scoreboard 6.1 warps per
+// issue, XU pipe 58 %.  A register software pipeline (descriptor t+2, records t+1 in flight) spilled
+// more than it hid.  Here everything a tile needs travels through shared memory with cp.async and
+// costs no registers: while tile t is verified, the window words and the first bucket stage of tile
+// t+1 and the descriptor of tile t+2 are in flight; the switch to the next tile is three LDS.
 #ifndef CV_ALU_PAIRS
 #define CV_ALU_PAIRS 1
 #endif
+#define CV_WTILE (32 * CV_ITEMS)
+#ifndef CV_TILE_INLINE
+#define CV_TILE_INLINE __forceinline__
+#endif
+// bytes of dynamic shared memory per warp of k_cverify
+#define CV_WARP_SMEM ((CV_GQ + 2) * 16 + 2 * CV_STAGE * 8 + 2 * CV_WTILE * 4 + 16)
+
+__device__ __forceinline__ void cv_cp_async4(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cv_cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// per-warp shared-memory staging of the tile pipeline
+struct CvPipe {
+    uint2* ent;        // [2][CV_STAGE] bucket stages (ping-pong by a running stage counter)
+    uint32_t* win;     // [2][CV_WTILE] x words of the window records, by tile parity
+    uint4* desc;       // [2] tile descriptors, by tile parity
+    uint32_t* dslot;   // [2] slot of the tile, by tile parity
+    const uint2* gwin;
+    const uint2* ent_hl;
+    const uint4* tile_desc;
+    const uint32_t* tile_slot;
+};
+
+// lane 0 requests descriptor t (no commit)
+__device__ __forceinline__ void cv_issue_desc(const CvPipe& pp, uint32_t t, uint32_t lane) {
+    if (lane == 0) {
+        cv_cp_async16(pp.desc + (t & 1u), pp.tile_desc + t);
+        cv_cp_async4(pp.dslot + (t & 1u), pp.tile_slot + t);
+    }
+}
+// window words of tile t (descriptor d) and stage `c` of its bucket into stage buffer `sb` (no commit)
+__device__ __forceinline__ void cv_issue_windows(const CvPipe& pp, uint32_t t, const uint4& d, uint32_t lane) {
+    const uint32_t n_win = d.y & 0xffu;
+    uint32_t* dst = pp.win + (t & 1u) * CV_WTILE;
+#pragma unroll
+    for (int it = 0; it < CV_ITEMS; it++) {
+        const uint32_t off = it * 32 + lane;
+        if (off < n_win) cv_cp_async4(dst + off, &pp.gwin[d.x + off].y);
+    }
+}
+__device__ __forceinline__ void cv_issue_stage(const CvPipe& pp, uint32_t ls, uint32_t le, uint32_t c, uint32_t sb, uint32_t lane) {
+    uint2* dst = pp.ent + (sb & 1u) * CV_STAGE;
+    const uint32_t n_ent = le - ls;
+#pragma unroll
+    for (int h = 0; h < CV_STAGE / 32; h++) {
+        const uint32_t i = c * CV_STAGE + h * 32 + lane;
+        if (i < n_ent) cv_cp_async8(dst + h * 32 + lane, pp.ent_hl + ls + i);
+    }
+}
+
+// Verifies tile t (descriptor d, slot) whose window words and first bucket stage were requested
+// earlier; before its last stage is computed the loads of tile t+1 (and descriptor t+2) are issued.
+// sc = running stage counter (selects the bucket stage buffer); returns the queue fill.
 template <int K, int ITEMS>
-__device__ __forceinline__ uint32_t cv_tile(const SearchParams& p, const uint2* __restrict__ gwin, const uint32_t (&wh)[CV_ITEMS],
-                                            const uint32_t (&wl)[CV_ITEMS], uint32_t ls, uint32_t le, uint32_t first,
-                                            uint32_t slot, uint2* sbuf, uint4* gq, uint32_t gn, uint4* q, uint32_t* qn) {
+static __device__ CV_TILE_INLINE uint32_t cv_tile(const SearchParams& p, const CvPipe& pp, uint32_t t, uint32_t t_end, const uint4 d,
+                                            uint32_t slot, uint32_t& sc, uint4* gq, uint32_t gn) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t ls = d.z, le = d.w, first = d.x;
     const uint32_t n_ent = le - ls;
     const uint32_t n_stage = (n_ent + CV_STAGE - 1) / CV_STAGE;
-    const uint2* bucket = p.ent_hl + ls;
-#define CV_ISSUE(C)                                                                        \
-    do {                                                                                   \
-        uint2* dst_ = sbuf + ((C) & 1u) * CV_STAGE;                                        \
-        _Pragma("unroll") for (int h = 0; h < CV_STAGE / 32; h++) {                        \
-            const uint32_t i_ = (C) * CV_STAGE + h * 32 + lane;                            \
-            if (i_ < n_ent) cv_cp_async8(dst_ + h * 32 + lane, bucket + i_);               \
-        }                                                                                  \
-        asm volatile("cp.async.commit_group;" ::: "memory");                               \
-    } while (0)
-    CV_ISSUE(0u);
+    uint32_t wh[ITEMS], wl[ITEMS];
     for (uint32_t c = 0; c < n_stage; c++) {
         if (c + 1 < n_stage) {
-            CV_ISSUE(c + 1);
+            cv_issue_stage(pp, ls, le, c + 1, sc + c + 1, lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
         } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");  // this tile's data and the next descriptor have landed
+            __syncwarp();
+            if (t + 1 < t_end) {
+                const uint4 dn = pp.desc[(t + 1) & 1u];
+                cv_issue_windows(pp, t + 1, dn, lane);
+                cv_issue_stage(pp, dn.z, dn.w, 0, sc + n_stage, lane);
+                if (t + 2 < t_end) cv_issue_desc(pp, t + 2, lane);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
         }
-        __syncwarp();
-        const uint4* sb = reinterpret_cast<const uint4*>(sbuf + (c & 1u) * CV_STAGE);
+        if (c == 0) {
+            const uint32_t n_win = d.y & 0xffu, cmb = d.y >> 8;
+            const uint32_t rem_nt = p.combo[cmb].rem_nt, rm = (1u << rem_nt) - 1u;
+            const uint32_t* sw = pp.win + (t & 1u) * CV_WTILE;
+#pragma unroll
+            for (int it = 0; it < ITEMS; it++) {
+                const bool have = it * 32 + lane < n_win;
+                const uint32_t x = have ? sw[it * 32 + lane] : 0u;
+                wh[it] = have ? (x & rm) : CV_INVALID;
+                wl[it] = have ? ((x >> rem_nt) & rm) : 0u;
+            }
+        }
+        const uint4* sb = reinterpret_cast<const uint4*>(pp.ent + ((sc + c) & 1u) * CV_STAGE);
         const uint32_t ng = (min((uint32_t)CV_STAGE, n_ent - c * CV_STAGE) + CV_GROUP - 1) / CV_GROUP;
         const uint32_t ebase = ls + c * CV_STAGE;
         uint32_t g = 0;
@@ -781,12 +867,12 @@ __device__ __forceinline__ uint32_t cv_tile(const SearchParams& p, const uint2* 
             if (gn < 32) break;
             do {  // warp-uniform; at most 31 + 32 * ITEMS items are queued here
                 gn -= 32;
-                cv_flush_items(p, gwin, gq + gn, 32, q, qn);
+                cv_flush_items(p, pp.gwin, gq + gn, 32);
             } while (gn >= 32);
         }
-        __syncwarp();  // every lane is done with this buffer before stage c+2 lands in it
+        __syncwarp();  // every lane is done with this buffer before a later stage lands in it
     }
-#undef CV_ISSUE
+    sc += n_stage;
     return gn;
 }
 
@@ -797,7 +883,6 @@ __device__ __forceinline__ uint32_t cv_tile(const SearchParams& p, const uint2* 
 // then needs ONE descriptor load per tile instead of walking the two directories with dependent
 // loads, and carries no slot-walk state in registers (the walking version spilled 240 bytes per
 // thread at 64 registers: ncu counted 1.3e9 local-memory load requests, 3x its global loads).
-#define CV_WTILE (32 * CV_ITEMS)
 __global__ void __launch_bounds__(256) k_ctile_count(const uint32_t* __restrict__ gdir, const uint32_t* __restrict__ dir,
                                                      uint32_t n_slots, uint32_t* __restrict__ tile_start,
                                                      unsigned long long* __restrict__ cand_out) {
@@ -844,105 +929,59 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
                                                                       const uint32_t* __restrict__ n_tiles_ptr,
                                                                       uint32_t* __restrict__ work, uint32_t slice,
                                                                       uint32_t frac_lo, uint32_t frac_hi) {
-    __shared__ uint4 s_q[CV_WARPS][CV_WQ];
-    __shared__ uint4 s_gq[CV_WARPS][CV_GQ];
-    __shared__ __align__(16) uint2 s_ent[CV_WARPS][2 * CV_STAGE];
-    __shared__ uint32_t s_qn[CV_WARPS];
+    // per warp: the item queue, two bucket stages, two tiles of window words, two descriptors + slots
+    extern __shared__ __align__(16) uint4 cv_smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint4* gq = s_gq[warp];
-    uint2* sbuf = s_ent[warp];
+    uint4* gq = cv_smem + warp * (CV_WARP_SMEM / 16);                   // [CV_GQ]
+    uint4* s_desc = gq + CV_GQ;                                         // [2]
+    uint2* s_ent = reinterpret_cast<uint2*>(s_desc + 2);                // [2 * CV_STAGE]
+    uint32_t* s_win = reinterpret_cast<uint32_t*>(s_ent + 2 * CV_STAGE);  // [2 * CV_WTILE]
+    uint32_t* s_dslot = s_win + 2 * CV_WTILE;                           // [2] (+2 pad)
     uint32_t gn = 0;  // queued items of this warp (warp-uniform; survives across tiles)
-    uint4* q = s_q[warp];
-    uint32_t* qn = &s_qn[warp];
-    if (lane == 0) *qn = 0;
-    __syncwarp();
+    CvPipe pp;
+    pp.ent = s_ent; pp.win = s_win; pp.desc = s_desc; pp.dslot = s_dslot;
+    pp.gwin = gwin; pp.ent_hl = p.ent_hl; pp.tile_desc = tile_desc; pp.tile_slot = tile_slot;
     const uint32_t n_tiles = *n_tiles_ptr;
     const uint32_t n_chunks = (n_tiles + CV_CHUNK_TILES - 1) / CV_CHUNK_TILES;
     const uint32_t ch_lo = (uint32_t)(((unsigned long long)n_chunks * frac_lo) >> 16);
     const uint32_t ch_hi = (uint32_t)(((unsigned long long)n_chunks * frac_hi) >> 16);
+    uint32_t sc = 0;  // running bucket-stage counter
     for (;;) {
         uint32_t ch = 0;
         if (lane == 0) ch = ch_lo + atomicAdd(work + slice, 1u);
         ch = __shfl_sync(0xffffffffu, ch, 0);
         if (ch >= ch_hi) break;
         const uint32_t t_end = min((ch + 1) * CV_CHUNK_TILES, n_tiles);
-        // Software pipeline over the tiles of the chunk: the descriptor of tile t+2 and the window
-        // records of tile t+1 are in flight while tile t is verified (ncu on the unpipelined loop at
-        // 10-nt keys, ~95 windows x 19 entries per tile: long scoreboard 6.1 warps per issue, the
-        // record loads and the cp.async wait were the top stall sites, XU pipe 58 %).
         uint32_t t = ch * CV_CHUNK_TILES;
-        uint4 d_cur = __ldg(tile_desc + t);
-        uint32_t slot_cur = __ldg(tile_slot + t);
-        uint4 d_nxt = d_cur;
-        uint32_t slot_nxt = slot_cur;
-        if (CV_PREFETCH && t + 1 < t_end) {
-            d_nxt = __ldg(tile_desc + t + 1);
-            slot_nxt = __ldg(tile_slot + t + 1);
-        }
-        uint32_t x_cur[CV_ITEMS];
-#pragma unroll
-        for (int it = 0; it < CV_ITEMS; it++) {
-            const uint32_t off = it * 32 + lane;
-            x_cur[it] = off < (d_cur.y & 0xffu) ? __ldcs(&gwin[d_cur.x + off].y) : 0u;
+        // prologue of the chunk: the only exposed latency chain (descriptor, then its data)
+        {
+            const uint4 d0 = __ldg(tile_desc + t);
+            if (lane == 0) {
+                pp.desc[t & 1u] = d0;
+                pp.dslot[t & 1u] = __ldg(tile_slot + t);
+            }
+            cv_issue_windows(pp, t, d0, lane);
+            cv_issue_stage(pp, d0.z, d0.w, 0, sc, lane);
+            if (t + 1 < t_end) cv_issue_desc(pp, t + 1, lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            __syncwarp();
         }
         for (; t < t_end; t++) {
-            // issue the loads of the following tiles before this one is touched
-            uint32_t x_nxt[CV_ITEMS];
-            uint4 d_nn = d_nxt;
-            uint32_t slot_nn = slot_nxt;
-            if (CV_PREFETCH) {
-                if (t + 1 < t_end) {
-#pragma unroll
-                    for (int it = 0; it < CV_ITEMS; it++) {
-                        const uint32_t off = it * 32 + lane;
-                        x_nxt[it] = off < (d_nxt.y & 0xffu) ? __ldcs(&gwin[d_nxt.x + off].y) : 0u;
-                    }
-                }
-                if (t + 2 < t_end) {
-                    d_nn = __ldg(tile_desc + t + 2);
-                    slot_nn = __ldg(tile_slot + t + 2);
-                }
-            }
-            const uint32_t n_win = d_cur.y & 0xffu, c = d_cur.y >> 8;
-            const uint32_t rem_nt = p.combo[c].rem_nt, rm = (1u << rem_nt) - 1u;
-            uint32_t wh[CV_ITEMS], wl[CV_ITEMS];
-#pragma unroll
-            for (int it = 0; it < CV_ITEMS; it++) {
-                const bool have = it * 32 + lane < n_win;
-                wh[it] = have ? (x_cur[it] & rm) : CV_INVALID;
-                wl[it] = have ? ((x_cur[it] >> rem_nt) & rm) : 0u;
-            }
-            switch ((n_win + 31u) / 32u) {
-                case 1: gn = cv_tile<K, 1>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
-                case 2: gn = cv_tile<K, 2>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
-                case 3: gn = cv_tile<K, 3>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
-                default: gn = cv_tile<K, 4>(p, gwin, wh, wl, d_cur.z, d_cur.w, d_cur.x, slot_cur, sbuf, gq, gn, q, qn); break;
-            }
-            cv_drain(p, gwin, q, qn, lane);
-            if (CV_PREFETCH) {
-                d_cur = d_nxt; slot_cur = slot_nxt;
-                d_nxt = d_nn; slot_nxt = slot_nn;
-#pragma unroll
-                for (int it = 0; it < CV_ITEMS; it++) x_cur[it] = x_nxt[it];
-            } else if (t + 1 < t_end) {
-                d_cur = __ldg(tile_desc + t + 1);
-                slot_cur = __ldg(tile_slot + t + 1);
-#pragma unroll
-                for (int it = 0; it < CV_ITEMS; it++) {
-                    const uint32_t off = it * 32 + lane;
-                    x_cur[it] = off < (d_cur.y & 0xffu) ? __ldcs(&gwin[d_cur.x + off].y) : 0u;
-                }
+            const uint4 d_cur = pp.desc[t & 1u];
+            const uint32_t slot_cur = pp.dslot[t & 1u];
+            switch (((d_cur.y & 0xffu) + 31u) / 32u) {
+                case 1: gn = cv_tile<K, 1>(p, pp, t, t_end, d_cur, slot_cur, sc, gq, gn); break;
+                case 2: gn = cv_tile<K, 2>(p, pp, t, t_end, d_cur, slot_cur, sc, gq, gn); break;
+                case 3: gn = cv_tile<K, 3>(p, pp, t, t_end, d_cur, slot_cur, sc, gq, gn); break;
+                default: gn = cv_tile<K, 4>(p, pp, t, t_end, d_cur, slot_cur, sc, gq, gn); break;
             }
         }
     }
     while (gn) {  // up to CV_GQ - 1 items are still queued
         const uint32_t take = min(gn, 32u);
         gn -= take;
-        cv_flush_items(p, gwin, gq + gn, take, q, qn);
+        cv_flush_items(p, gwin, gq + gn, take);
     }
-    __syncwarp();
-    const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
-    if (nq) cv_resolve(p, gwin, q, nq);
 }
 
 // Second level + hit resolution as a kernel of their own: every warp takes batches of 32 items of
@@ -958,15 +997,16 @@ __global__ void __launch_bounds__(CV_THREADS, 4) k_cfinish(const __grid_constant
     if (lane == 0) *qn = 0;
     __syncwarp();
     const unsigned long long queued = p.count[4];
+    if (queued > p.item_cap && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(p.count + 5, queued);  // batches were dropped: bc_search retries
     const unsigned long long n_items = queued < p.item_cap ? queued : p.item_cap;  // whole batches of 32; item_cap is a multiple of 32
     const unsigned long long n_warps = (unsigned long long)gridDim.x * CV_WARPS;
     for (unsigned long long b0 = ((unsigned long long)blockIdx.x * CV_WARPS + warp) * 32ull; b0 < n_items; b0 += n_warps * 32ull) {
         const uint32_t n = (uint32_t)min(32ull, n_items - b0);
-        cv_resolve_groups(p, gwin, p.items + b0, n, q, qn);
+        cv_resolve_groups(p, gwin, p.items + b0, n, q, qn, CV_ITEM_POS != 0);
     }
     __syncwarp();
     const uint32_t nq = min(*qn, (uint32_t)CV_WQ);
-    if (nq) cv_resolve(p, gwin, q, nq);
+    if (nq) cv_resolve(p, gwin, q, nq, CV_ITEM_POS != 0);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -1077,6 +1117,18 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
     return cudaSuccess;
 }
 
+// CTAs of k_cverify per SM: CV_MINBLOCKS fills the register file; BC_VERIFY_CTAS (environment, experiments only)
+// lowers it
+static uint32_t cv_ctas_per_sm() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BC_VERIFY_CTAS");
+        v = e ? atoi(e) : CV_MINBLOCKS;
+        if (v < 1 || v > CV_MINBLOCKS) v = CV_MINBLOCKS;
+    }
+    return (uint32_t)v;
+}
+
 cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t dir_slots, uint32_t n_bins, int sm_count,
                             cudaStream_t st, uint32_t* launches, HitSink* sink) {
     const uint32_t launches0 = bc_launch_counter;
@@ -1146,18 +1198,19 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         ws.scan_tmp_cap = tmp_words;
     }
     if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, BC_SINK_SLICES * sizeof(uint32_t)));
-    // global item queue between k_cverify and k_cfinish: about one item per candidate pair; sized from the
-    // hit buffer (a full queue only means the verify kernel resolves the overflow itself)
+    // global item queue between k_cverify and k_cfinish: about one item per candidate pair.  Sized from the hit
+    // buffer, or from the demand a previous attempt measured (ws.item_want, set by bc_search after an overflow)
     {
         uint64_t want = 2 * p.cap + (1ull << 16);
         if (want > (1ull << 29)) want = 1ull << 29;
-        want &= ~31ull;
+        if (ws.item_want > want) want = ws.item_want;
+        want = (want + 31ull) & ~31ull;
         if (want > ws.item_cap) {
             if (ws.d_items) cudaFree(ws.d_items);
             ws.d_items = nullptr;
             ws.item_cap = 0;
-            if (cudaMalloc(&ws.d_items, want * sizeof(uint4)) == cudaSuccess) ws.item_cap = want;
-            else (void)cudaGetLastError();  // no queue: everything is resolved inside the verify kernel
+            JCK(cudaMalloc(&ws.d_items, want * sizeof(uint4)));
+            ws.item_cap = want;
         }
     }
     // tile list: at most one ragged tile per non-empty slot plus the full ones
@@ -1182,7 +1235,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     }
     SearchParams pv = p;
     pv.items = ws.d_items;
-    pv.item_cap = CV_FINISH_KERNEL ? ws.item_cap : 0;
+    pv.item_cap = ws.item_cap;
 
     CBucketParams gp;
     memset(&gp, 0, sizeof gp);
@@ -1198,6 +1251,10 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     gp.P = p.P; gp.pam_dir = p.pam_dir;
     for (int i = 0; i < 8; i++) gp.pam_sets[i] = p.pam_sets[i];
 
+    JCK(cudaFuncSetAttribute(k_cverify<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_WARPS * CV_WARP_SMEM));
+    JCK(cudaFuncSetAttribute(k_cverify<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_WARPS * CV_WARP_SMEM));
+    JCK(cudaFuncSetAttribute(k_cverify<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_WARPS * CV_WARP_SMEM));
+    JCK(cudaFuncSetAttribute(k_cverify<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_WARPS * CV_WARP_SMEM));
     if (!ws.d_lut) JCK(cudaMalloc(&ws.d_lut, (size_t)BC_MAX_COMBOS * CJ_LUT_WORDS * sizeof(uint32_t)));
     k_clut_build<<<(p.n_combos * CJ_LUT_WORDS + 255) / 256, 256, 0, st>>>(gp, ws.d_lut);
     JCK(cudaGetLastError());
@@ -1260,21 +1317,19 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
             const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));
-            const uint32_t dgrid = (uint32_t)sm_count * CV_MINBLOCKS, lo = n_slices == 1 ? 0u : f_lo;
+            const uint32_t dgrid = (uint32_t)sm_count * cv_ctas_per_sm(), lo = n_slices == 1 ? 0u : f_lo;
             JCK(cudaMemsetAsync(p.count + 4, 0, sizeof(unsigned long long), st));
-            switch (p.k) {
-                case 0: k_cverify<0><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
-                case 1: k_cverify<1><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
-                case 2: k_cverify<2><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
-                default: k_cverify<3><<<dgrid, CV_THREADS, 0, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+            switch (p.k) {  // (the dynamic shared-memory opt-in was set once, above)
+                case 0: k_cverify<0><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+                case 1: k_cverify<1><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+                case 2: k_cverify<2><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+                default: k_cverify<3><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
             }
             JCK(cudaGetLastError());
             if (s + 1 == n_slices) JCK(cudaEventRecord(ws.ev_k[4], st));  // end of the (last) first-level kernel
-            if (pv.item_cap) {
-                k_cfinish<<<(uint32_t)sm_count * 4u, CV_THREADS, 0, st>>>(pv, d_win);
-                JCK(cudaGetLastError());
-                bc_launch_counter += 1;
-            }
+            k_cfinish<<<(uint32_t)sm_count * 4u, CV_THREADS, 0, st>>>(pv, d_win);
+            JCK(cudaGetLastError());
+            bc_launch_counter += 1;
             if (sink) {
                 JCK(cudaMemcpyAsync(sink->h_counts + s, p.count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
                 JCK(cudaEventRecord(sink->ev[s], st));

@@ -253,11 +253,13 @@ static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t 
         const long long a = right ? (long long)pos + L : (long long)pos - (long long)p.P;
         if (a >= (long long)cs && a + (long long)p.P <= (long long)ce) {
             uint32_t codes = 0, amb = 0, ok = 1;
+            // the P bases of the site as one funnel-shifted window per plane: six independent loads, then bit
+            // operations only (base by base the loop was a chain of dependent loads: B, then H and Lo, P times)
+            const uint32_t wB = bc_window(p.B, (uint32_t)a), wH = bc_window(p.H, (uint32_t)a), wL = bc_window(p.Lo, (uint32_t)a);
             for (uint32_t i = 0; i < p.P; i++) {
-                uint32_t d = (uint32_t)a + (strand ? p.P - 1 - i : i);
-                uint32_t w = d >> 5, s = d & 31u;
-                if ((p.B[w] >> s) & 1u) { amb = 1; continue; }
-                uint32_t code = (((p.H[w] >> s) & 1u) << 1) | ((p.Lo[w] >> s) & 1u);
+                const uint32_t s = strand ? p.P - 1 - i : i;
+                if ((wB >> s) & 1u) { amb = 1; continue; }
+                uint32_t code = (((wH >> s) & 1u) << 1) | ((wL >> s) & 1u);
                 if (strand) code = 3u - code;
                 codes |= code << (2 * i);
                 if (!((p.pam_sets[i] >> code) & 1u)) ok = 0;

@@ -18,6 +18,7 @@ struct JoinWorkspace {
     uint64_t tile_cap = 0, tile_start_cap = 0;
     uint4* d_items = nullptr;        // compact join: {window, entry group} items handed from k_cverify to k_cfinish
     uint64_t item_cap = 0;
+    uint64_t item_want = 0;  // item-queue demand measured by an attempt that overflowed (bc_search)
     uint32_t* d_lut = nullptr;       // compact join: byte-wise bit-permutation tables, one per combination
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     cudaEvent_t ev_k[6] = {nullptr};  // compact join: per-kernel split

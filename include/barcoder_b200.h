@@ -118,6 +118,8 @@ typedef struct {
     float ms_win_bin;         /* compact join: ... of radix pass A                    */
     float ms_win_place;       /* compact join: ... of radix pass B                    */
     float ms_finish;          /* compact join: ... of k_cfinish (part of ms_scan_kernel; 0 when streaming) */
+    uint32_t search_attempts; /* passes bc_search needed: 1, +1 per hit-buffer or verify-item-queue overflow */
+    uint32_t reserved0;
 } bc_stats;
 
 int bc_abi_version(void);

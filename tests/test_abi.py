@@ -42,7 +42,7 @@ def test_no_cpu_fallback_without_device():
 
 def test_stats_struct_size_matches_header():
     # 2*u64 + 6*u32 + 3*u64 + 5*f32 + 8*u32 with natural alignment
-    assert ctypes.sizeof(_native.BcStats) == 16 + 24 + 24 + 20 + 32 + 4
+    assert ctypes.sizeof(_native.BcStats) == 16 + 24 + 24 + 20 + 32 + 4 + 8
 
 
 def test_constants_match_header():

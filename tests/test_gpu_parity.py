@@ -368,6 +368,22 @@ def test_cjoin_hit_sink_and_overflow():
         assert s.stats()["path"] == 3
 
 
+def test_cjoin_item_queue_overflow_retries():
+    """The verify kernel has no slow path: when the global item queue between k_cverify and k_cfinish is too small
+    batches are dropped, the demand is counted and bc_search repeats the search with a queue of that size."""
+    genome, off = synth.random_genome(300000, seed=181, n_contigs=3, n_fraction=0.01, n_run=5)
+    lib = synth.random_library(300_000, 12, seed=182)
+    synth.plant(lib, genome, 0.05, 1, seed=183)
+    ref = run_oracle(genome, off, lib, 1, pam="NGG")
+    # 1024-record hit buffer -> item queue of 2 * 1024 + 65536 entries; this job queues several 10^5 items
+    gpu, st = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=3, hit_cap=1024)
+    assert st["path"] == 3 and st["search_attempts"] >= 2
+    assert_same(gpu, ref)
+    gpu, st = run_gpu(genome, off, lib, 1, pam="NGG", blocks=2, path=3)
+    assert st["search_attempts"] == 1
+    assert_same(gpu, ref)
+
+
 @pytest.mark.parametrize("index_sort", [1, 2])
 def test_cjoin_index_builders_agree(index_sort):
     """The compact path's library index can be built by the two radix passes (default) or by the
