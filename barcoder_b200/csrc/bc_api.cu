@@ -444,7 +444,7 @@ static bool finish_scheme(Scheme* s, uint32_t L, uint64_t n_entries) {
         while (top < kb && top < 10 && (kb - top) + rem2 > 32) top++;
         if (top > 10) top = 10;
         const uint32_t low = kb - top;
-        if (low > 12 || low + rem2 > 32 || L - knt > 16) s->compact_ok = false;
+        if (low > 12 || low + rem2 > 32 || L - knt > 16 || L > 22) s->compact_ok = false;  // (22: two 11-bit permutation tables)
         cd.top_bits = (uint8_t)top;
         cd.bin_off = bins;
         bins += 1u << top;

@@ -55,19 +55,33 @@ struct CBucketParams {
 // instructions for 1.2e9 records); done through a byte-wise lookup table they cost ~10 per plane.
 // lut[c][b][v] = contribution of byte b (value v) of a plane word to the PERMUTED word of
 // combination c: key positions packed above the rem positions, both in ascending order.
-#define CJ_LUT_WORDS 1024
+// Round 2: two tables of 2^11 entries instead of four of 2^8 (the compact path only takes spacers of
+// at most 22 nt): two look-ups per plane instead of three.  Pass A is bound by its shared-memory
+// traffic (ncu: l1tex 79 %), and a random-index look-up costs ~3.4 wavefronts.
+#ifndef CJ_LUT_BITS
+#define CJ_LUT_BITS 11
+#endif
+#define CJ_LUT_TABS (CJ_LUT_BITS == 8 ? 4 : 2)
+#define CJ_LUT_WORDS (CJ_LUT_TABS << CJ_LUT_BITS)
 __global__ void k_clut_build(const __grid_constant__ CBucketParams gp, uint32_t* __restrict__ lut) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= gp.n_combos * CJ_LUT_WORDS) return;
-    const ComboDesc& cd = gp.combo[g >> 10];
-    const uint32_t word = (g & 255u) << (8u * ((g >> 8) & 3u));
+    const ComboDesc& cd = gp.combo[g / CJ_LUT_WORDS];
+    const uint32_t w = g % CJ_LUT_WORDS;
+    const uint32_t word = (w & ((1u << CJ_LUT_BITS) - 1u)) << (CJ_LUT_BITS * (w >> CJ_LUT_BITS));
     lut[g] = (bc_combo_gather_key(cd, word) << cd.rem_nt) | bc_combo_rem(cd, word);
 }
 
+// v = an L-bit plane word (bits above L are zero)
 __device__ __forceinline__ uint32_t cj_perm(const uint32_t* s_lut, uint32_t v, bool wide) {
+#if CJ_LUT_BITS == 8
     uint32_t out = s_lut[v & 255u] | s_lut[256u + ((v >> 8) & 255u)] | s_lut[512u + ((v >> 16) & 255u)];
     if (wide) out |= s_lut[768u + (v >> 24)];  // spacers longer than 24 nt
     return out;
+#else
+    (void)wide;
+    return s_lut[v & ((1u << CJ_LUT_BITS) - 1u)] | s_lut[(1u << CJ_LUT_BITS) + (v >> CJ_LUT_BITS)];
+#endif
 }
 
 // ------------------------------------------------------------------------------------- count
@@ -131,6 +145,155 @@ __global__ void k_cbin_init(const __grid_constant__ CBucketParams gp, const uint
     bin_start[g] = v;
     bin_cursor[g] = v;
     bin_combo[g] = (uint8_t)c;
+}
+
+// ------------------------------------------------------------ counting without a RED per record
+// k_ccount<win> costs one global RED per (window, combination): 1.5e9 of them at cfg 4 = 7.3 ms at
+// the L2 atomic rate (ncu: lts 87 %), 13 % of the step - only to learn where every bin and slot
+// starts.  Round 2 counts in shared memory instead, in two places:
+//   k_cbincount   before pass A: per combination a shared-memory histogram over its <= 1024 bins,
+//                 flushed once per (CTA, combination).  When the bin is a function of the H plane
+//                 alone (top_bits <= key_nt, nothing pruned or sharded away) only that plane is
+//                 permuted.  A thread walks 32 consecutive positions with one pair of words per plane.
+//   k_cslotcount  after pass A: the records of a bin are contiguous, so the slot histogram of a piece of
+//                 a bin (<= 65536 records) is a shared-memory histogram over the bin's sub-slots, flushed
+//                 with one RED per non-empty (piece, sub-slot): ~2.5e7 REDs instead of 1.5e9.
+#define CB_THREADS 512
+__global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_constant__ CBucketParams gp,
+                                                             const uint32_t* __restrict__ lut,
+                                                             uint32_t* __restrict__ bin_count) {
+    __shared__ uint32_t s_lut[CJ_LUT_WORDS];
+    __shared__ uint32_t s_hist[CJ_MAX_BINS];
+    const uint32_t lm = bc_lmask(gp.L);
+    const uint32_t tid = threadIdx.x;
+    PamGate gate;
+    bc_gate_init(gate, gp.P, gp.L, gp.pam_dir, gp.pam_sets);
+    // static split of the plane words [w_lo, w_hi) over the CTAs
+    const uint32_t w_lo = gp.pos_begin >> 5, w_hi = (gp.pos_end + 31u) >> 5;
+    const uint32_t per = (w_hi - w_lo + gridDim.x - 1) / gridDim.x;
+    const uint32_t my_lo = w_lo + blockIdx.x * per, my_hi = min(w_hi, my_lo + per);
+    for (uint32_t c = 0; c < gp.n_combos; c++) {
+        const ComboDesc& cd = gp.combo[c];
+        if (!bc_combo_in_range(cd, gp.slot_lo, gp.slot_hi)) continue;  // block-uniform
+        const uint32_t n_bins = 1u << cd.top_bits, key_nt = cd.key_nt, rem_nt = cd.rem_nt;
+        const uint32_t low = 2u * key_nt - cd.top_bits;
+        const bool whole = cd.dir_off >= gp.slot_lo && cd.dir_off + (1u << (2u * key_nt)) <= gp.slot_hi;
+        const bool h_only = cd.top_bits <= key_nt && whole && !gp.prune;
+        __syncthreads();
+        for (uint32_t j = tid; j < n_bins; j += CB_THREADS) s_hist[j] = 0;
+        for (uint32_t j = tid; j < CJ_LUT_WORDS; j += CB_THREADS) s_lut[j] = lut[c * CJ_LUT_WORDS + j];
+        __syncthreads();
+        for (uint32_t w = my_lo + tid; w < my_hi; w += CB_THREADS) {
+            const uint32_t wn = min(w + 1u, gp.n_words - 1u);  // the planes are padded: the clamp only guards the very last word
+            const uint32_t b0 = gp.B[w], b1 = gp.B[wn], h0 = gp.H[w], h1 = gp.H[wn];
+            const uint32_t l0 = h_only ? 0u : gp.Lo[w], l1 = h_only ? 0u : gp.Lo[wn];
+#pragma unroll 4
+            for (uint32_t o = 0; o < 32; o++) {
+                const uint32_t pos = (w << 5) + o;
+                if (pos < gp.pos_begin || pos >= gp.pos_end) continue;
+                if (__funnelshift_r(b0, b1, o) & lm) continue;
+                if (gp.gate_first && !bc_gate_window(gate, gp.H, gp.Lo, gp.B, pos)) continue;
+                const uint32_t ph = cj_perm(s_lut, __funnelshift_r(h0, h1, o) & lm, false);
+                uint32_t bin;
+                if (h_only) {
+                    bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
+                } else {
+                    const uint32_t pl = cj_perm(s_lut, __funnelshift_r(l0, l1, o) & lm, false);
+                    const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
+                    const uint32_t slot = cd.dir_off + key;
+                    if (slot < gp.slot_lo || slot >= gp.slot_hi) continue;
+                    if (gp.prune && gp.lib_dir[slot] == gp.lib_dir[slot + 1]) continue;
+                    bin = key >> low;
+                }
+                atomicAdd(&s_hist[bin], 1u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < n_bins; j += CB_THREADS) {
+            const uint32_t v = s_hist[j];
+            if (v) atomicAdd(&bin_count[cd.bin_off + j], v);
+        }
+    }
+}
+
+// bin_start = the scanned bin counts (+ end sentinel), bin_combo[g] = combination of bin g
+__global__ void k_cbin_init2(const __grid_constant__ CBucketParams gp, uint32_t n_bins, const uint32_t* __restrict__ bin_cursor,
+                             uint32_t* __restrict__ bin_start, uint8_t* __restrict__ bin_combo) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_bins) return;
+    bin_start[g] = bin_cursor[g];
+    if (g == n_bins) return;
+    uint32_t c = 0;
+    while (c + 1 < gp.n_combos && gp.combo[c + 1].bin_off <= g) c++;
+    bin_combo[g] = (uint8_t)c;
+}
+
+#define CS_THREADS 512
+#define CS_SEG 65536u
+__global__ void __launch_bounds__(CS_THREADS, 2) k_cslotcount(const __grid_constant__ CBucketParams gp,
+                                                              const uint2* __restrict__ tmp,
+                                                              const uint32_t* __restrict__ bin_start,
+                                                              const uint8_t* __restrict__ bin_combo, uint32_t n_bins,
+                                                              uint32_t* __restrict__ gdir, uint32_t* __restrict__ work) {
+    extern __shared__ __align__(16) uint32_t cj_smem[];
+    uint32_t* s_hist = cj_smem;  // [max_sub]
+    __shared__ uint32_t s_unit;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_rec = bin_start[n_bins];
+    const uint32_t n_units = (uint32_t)(((uint64_t)n_rec + CS_SEG - 1) / CS_SEG);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= n_units) break;
+        const uint32_t r0 = u * CS_SEG, r1 = r0 + min(CS_SEG, n_rec - r0);
+        uint32_t g;
+        {
+            uint32_t lo = 0, hi = n_bins;  // bin_start[lo] <= r0 < bin_start[hi]
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(bin_start + mid) <= r0) lo = mid; else hi = mid;
+            }
+            g = lo;
+        }
+        uint32_t seg = r0;
+        while (seg < r1) {
+            while (g + 1 < n_bins && __ldg(bin_start + g + 1) <= seg) g++;  // skip empty bins
+            const uint32_t s1 = min(r1, __ldg(bin_start + g + 1));
+            const ComboDesc& cd = gp.combo[__ldg(bin_combo + g)];
+            const uint32_t low = 2u * cd.key_nt - cd.top_bits, rem2 = 2u * cd.rem_nt;
+            const uint32_t n_sub = 1u << low;
+            const uint32_t slot0 = cd.dir_off + ((g - cd.bin_off) << low);
+            if (low == 0) {  // the bin is one slot
+                if (tid == 0) atomicAdd(&gdir[slot0], s1 - seg);
+                seg = s1;
+                continue;
+            }
+            __syncthreads();
+            for (uint32_t j = tid; j < n_sub; j += CS_THREADS) s_hist[j] = 0;
+            __syncthreads();
+            // 8 independent loads per thread before the first one is used: with one load in flight per thread the kernel
+            // ran at 2.5 TB/s (latency bound)
+            for (uint32_t i0 = seg; i0 < s1; i0 += 8u * CS_THREADS) {
+                uint32_t y[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t i = i0 + tid + (uint32_t)j * CS_THREADS;
+                    y[j] = i < s1 ? __ldcs(&tmp[i].y) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (i0 + tid + (uint32_t)j * CS_THREADS < s1) atomicAdd(&s_hist[y[j] >> rem2], 1u);
+            }
+            __syncthreads();
+            for (uint32_t j = tid; j < n_sub; j += CS_THREADS) {
+                const uint32_t v = s_hist[j];
+                if (v) atomicAdd(&gdir[slot0 + j], v);
+            }
+            seg = s1;
+        }
+    }
 }
 
 // exclusive scan of CJ_THREADS values, one per thread; s_warp: CJ_THREADS / 32 words
@@ -522,6 +685,8 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
                     uint32_t sum = 0;
                     for (uint32_t j = 0; j < per; j++) sum += j0 + j < n_sub ? s_hist[j0 + j] : 0u;
                     uint32_t run = cj_block_scan(sum, s_warp);
+                    // (holding the atomics' results in registers until the records are grouped, so that the cursors
+                    // answer meanwhile, measured slower: 9.80 against 9.58 ms, 112 registers)
                     for (uint32_t j = 0; j < per && j0 + j < n_sub; j++) {
                         const uint32_t cnt = s_hist[j0 + j];
                         s_lstart[j0 + j] = run;
@@ -1090,6 +1255,7 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
     uint8_t* d_bin_combo = reinterpret_cast<uint8_t*>(d_chunk_bin + max_chunks);
     if (!ws.d_lut) JCK(cudaMalloc(&ws.d_lut, (size_t)BC_MAX_COMBOS * CJ_LUT_WORDS * sizeof(uint32_t)));
     if (!ws.d_work) JCK(cudaMalloc(&ws.d_work, BC_SINK_SLICES * sizeof(uint32_t)));
+    if (CJ_LUT_BITS != 8 && ip.L > 2 * CJ_LUT_BITS) return cudaErrorInvalidValue;  // choose_scheme keeps such spacers off this path
     k_clut_build<<<(n_combos * CJ_LUT_WORDS + 255) / 256, 256, 0, st>>>(gp, ws.d_lut);
     JCK(cudaGetLastError());
     uint32_t gx = (ip.n_entries + 255) / 256;
@@ -1115,6 +1281,17 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
                               ws.d_work, max_sub, smem_b, sm_count, st));
     bc_launch_counter += 7;
     return cudaSuccess;
+}
+
+// BC_WIN_COUNT=red (environment, A/B runs only): count the windows per slot with one global RED per record
+// (k_ccount, the round-1 form) instead of k_cbincount + k_cslotcount
+static bool cj_red_count() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BC_WIN_COUNT");
+        v = (e && !strcmp(e, "red")) ? 1 : 0;
+    }
+    return v != 0;
 }
 
 // CTAs of k_cverify per SM: CV_MINBLOCKS fills the register file; BC_VERIFY_CTAS (environment, experiments only)
@@ -1256,6 +1433,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     JCK(cudaFuncSetAttribute(k_cverify<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_WARPS * CV_WARP_SMEM));
     JCK(cudaFuncSetAttribute(k_cverify<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_WARPS * CV_WARP_SMEM));
     if (!ws.d_lut) JCK(cudaMalloc(&ws.d_lut, (size_t)BC_MAX_COMBOS * CJ_LUT_WORDS * sizeof(uint32_t)));
+    if (CJ_LUT_BITS != 8 && p.L > 2 * CJ_LUT_BITS) return cudaErrorInvalidValue;
     k_clut_build<<<(p.n_combos * CJ_LUT_WORDS + 255) / 256, 256, 0, st>>>(gp, ws.d_lut);
     JCK(cudaGetLastError());
     bc_launch_counter += 1;
@@ -1276,26 +1454,49 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         if (gx > maxb) gx = maxb;
         JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
         JCK(cudaEventRecord(ws.ev_c, st));
-        k_ccount<false><<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_lut, ws.d_gdir);
-        JCK(cudaGetLastError());
-        JCK(cudaEventRecord(ws.ev_k[0], st));  // end of the count kernel
-        JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
-        if (!one_pass) JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
-        k_cbin_init<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, ws.d_gdir, n_bins, n_slots, d_bin_start, d_bin_cursor, d_bin_combo);
-        JCK(cudaGetLastError());
         uint32_t bx = (npos + CJ_CHUNK - 1) / CJ_CHUNK;
         if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
+        const bool red_count = cj_red_count();
+        if (red_count) {  // round-1 form: one global RED per (window, combination), kept for A/B runs (BC_WIN_COUNT=red)
+            k_ccount<false><<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_lut, ws.d_gdir);
+            JCK(cudaGetLastError());
+            JCK(cudaEventRecord(ws.ev_k[0], st));  // end of the count kernel
+            JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
+            if (!one_pass) JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
+            k_cbin_init<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, ws.d_gdir, n_bins, n_slots, d_bin_start, d_bin_cursor, d_bin_combo);
+            JCK(cudaGetLastError());
+        } else {          // bin totals from shared-memory histograms; the slot histogram follows pass A
+            JCK(cudaMemsetAsync(d_bin_cursor, 0, (n_bins + 1) * sizeof(uint32_t), st));
+            k_cbincount<<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
+            JCK(cudaGetLastError());
+            JCK(cudaEventRecord(ws.ev_k[0], st));  // end of the bin count
+            JCK(bc_exclusive_scan(d_bin_cursor, (uint64_t)n_bins + 1, ws.d_scan_tmp, st));
+            k_cbin_init2<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, n_bins, d_bin_cursor, d_bin_start, d_bin_combo);
+            JCK(cudaGetLastError());
+        }
         JCK(cudaEventRecord(ws.ev_k[1], st));  // start of pass A
         k_cbin<false><<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, one_pass ? d_win : d_tmp);
         JCK(cudaGetLastError());
         JCK(cudaEventRecord(ws.ev_k[2], st));  // end of pass A
         bc_launch_counter += 3;
+        const uint32_t* n_rec_ptr = red_count ? ws.d_gdir + n_slots : d_bin_start + n_bins;
+        if (!red_count) {   // slot histogram of the binned records, then the slot starts
+            JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
+            JCK(cudaFuncSetAttribute(k_cslotcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_sub * sizeof(uint32_t))));
+            k_cslotcount<<<(uint32_t)sm_count * 2u, CS_THREADS, max_sub * sizeof(uint32_t), st>>>(gp, one_pass ? d_win : d_tmp, d_bin_start, d_bin_combo, n_bins,
+                                                                                            ws.d_gdir, ws.d_work);
+            JCK(cudaGetLastError());
+            JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
+            JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
+            bc_launch_counter += 1;
+        }
+        JCK(cudaEventRecord(ws.ev_k[5], st));  // end of the slot count (start of pass B)
         if (!one_pass) {
-            k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, ws.d_gdir + n_slots, d_chunk_bin);
+            k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, n_rec_ptr, d_chunk_bin);
             JCK(cudaGetLastError());
             JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
             JCK(cj_launch_place<false>(gp, d_tmp, d_bin_start, d_bin_combo, d_chunk_bin, n_bins, ws.d_gcursor, d_win, nullptr,
-                                       ws.d_gdir + n_slots, ws.d_work, max_sub, smem_b, sm_count, st));
+                                       n_rec_ptr, ws.d_work, max_sub, smem_b, sm_count, st));
             bc_launch_counter += 2;
         }
         JCK(cudaEventRecord(ws.ev_k[3], st));      // end of pass B
@@ -1348,7 +1549,8 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         // figures are those of the last slice, i.e. of the whole stage when nothing is streamed
         JCK(cudaEventElapsedTime(&ms, ws.ev_c, ws.ev_k[0])); ws.ms_kernel[0] += ms;
         JCK(cudaEventElapsedTime(&ms, ws.ev_k[1], ws.ev_k[2])); ws.ms_kernel[1] += ms;
-        JCK(cudaEventElapsedTime(&ms, ws.ev_k[2], ws.ev_k[3])); ws.ms_kernel[2] += ms;
+        JCK(cudaEventElapsedTime(&ms, ws.ev_k[2], ws.ev_k[5])); ws.ms_kernel[0] += ms;  // slot count: part of "count"
+        JCK(cudaEventElapsedTime(&ms, ws.ev_k[5], ws.ev_k[3])); ws.ms_kernel[2] += ms;
         JCK(cudaEventElapsedTime(&ms, ws.ev_k[3], ws.ev_a)); ws.ms_kernel[3] += ms;
         if (n_slices == 1) {
             JCK(cudaEventElapsedTime(&ms, ws.ev_a, ws.ev_k[4])); ws.ms_kernel[4] += ms;
