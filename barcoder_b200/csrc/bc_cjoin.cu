@@ -20,6 +20,7 @@
 //   k_cverify<K>  slot-aligned warp-tiles of <= 128 windows against the slot's library bucket
 #include "bc_join.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -159,6 +160,7 @@ __global__ void k_cbin_init(const __grid_constant__ CBucketParams gp, const uint
 //                 a bin (<= 65536 records) is a shared-memory histogram over the bin's sub-slots, flushed
 //                 with one RED per non-empty (piece, sub-slot): ~2.5e7 REDs instead of 1.5e9.
 #define CB_THREADS 512
+template <bool LIB>
 __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_constant__ CBucketParams gp,
                                                              const uint32_t* __restrict__ lut,
                                                              uint32_t* __restrict__ bin_count) {
@@ -178,12 +180,33 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
         const uint32_t n_bins = 1u << cd.top_bits, key_nt = cd.key_nt, rem_nt = cd.rem_nt;
         const uint32_t low = 2u * key_nt - cd.top_bits;
         const bool whole = cd.dir_off >= gp.slot_lo && cd.dir_off + (1u << (2u * key_nt)) <= gp.slot_hi;
-        const bool h_only = cd.top_bits <= key_nt && whole && !gp.prune;
+        const bool h_only = cd.top_bits <= key_nt && whole && (LIB || !gp.prune);
         __syncthreads();
         for (uint32_t j = tid; j < n_bins; j += CB_THREADS) s_hist[j] = 0;
         for (uint32_t j = tid; j < CJ_LUT_WORDS; j += CB_THREADS) s_lut[j] = lut[c * CJ_LUT_WORDS + j];
         __syncthreads();
-        for (uint32_t w = my_lo + tid; w < my_hi; w += CB_THREADS) {
+        if (LIB) {  // library entries (index build): planes qh / ql, an entry whose key touches a non-ACGT character is skipped
+            for (uint32_t e = blockIdx.x * CB_THREADS + tid; e < gp.n_entries; e += gridDim.x * CB_THREADS) {
+                if (gp.lib_has_n) {
+                    uint32_t nm = gp.sn[e >> 1];
+                    if (e & 1u) nm = bc_rev_bits(nm, gp.L);
+                    if (nm & cd.key_mask) continue;
+                }
+                const uint32_t ph = cj_perm(s_lut, gp.qh[e], false);
+                uint32_t bin;
+                if (h_only) {
+                    bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
+                } else {
+                    const uint32_t pl = cj_perm(s_lut, gp.ql[e], false);
+                    const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
+                    const uint32_t slot = cd.dir_off + key;
+                    if (slot < gp.slot_lo || slot >= gp.slot_hi) continue;
+                    bin = key >> low;
+                }
+                atomicAdd(&s_hist[bin], 1u);
+            }
+        }
+        for (uint32_t w = my_lo + tid; !LIB && w < my_hi; w += CB_THREADS) {
             const uint32_t wn = min(w + 1u, gp.n_words - 1u);  // the planes are padded: the clamp only guards the very last word
             const uint32_t b0 = gp.B[w], b1 = gp.B[wn], h0 = gp.H[w], h1 = gp.H[wn];
             const uint32_t l0 = h_only ? 0u : gp.Lo[w], l1 = h_only ? 0u : gp.Lo[wn];
@@ -374,6 +397,10 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
             const uint32_t low = 2u * cd.key_nt - cd.top_bits, rem_nt = cd.rem_nt;
             const uint32_t n_bins = 1u << cd.top_bits, key_nt = cd.key_nt;
             const uint32_t rm = (1u << rem_nt) - 1u, low_mask = (1u << low) - 1u;
+            // the common case - key bits split evenly between the passes, nothing sharded or pruned away - needs
+            // neither the assembled key nor the range / prune tests (pass A is issue- and shared-memory bound)
+            const bool even = low == key_nt && (LIB || !gp.prune) && cd.dir_off >= gp.slot_lo &&
+                              cd.dir_off + (1u << (2u * key_nt)) <= gp.slot_hi;
             for (uint32_t j = tid; j < n_bins; j += CJ_THREADS) s_hist[j] = 0;
             for (uint32_t j = tid; j < CJ_LUT_WORDS; j += CJ_THREADS) s_lut[j] = lut[c * CJ_LUT_WORDS + j];
             __syncthreads();
@@ -398,11 +425,17 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
                     wl = gp.ql[e];
                 }
                 const uint32_t ph = cj_perm(s_lut, wh, wide), pl = cj_perm(s_lut, wl, wide);
-                const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
-                if (cd.dir_off + key < gp.slot_lo || cd.dir_off + key >= gp.slot_hi) continue;
-                if (!LIB && gp.prune && gp.lib_dir[cd.dir_off + key] == gp.lib_dir[cd.dir_off + key + 1]) continue;
-                const uint32_t bin = key >> low;
-                x[i] = ((key & low_mask) << (2u * rem_nt)) | ((pl & rm) << rem_nt) | (ph & rm);
+                uint32_t bin;
+                if (even) {  // block-uniform: the bin is the H half of the key, and x = pl << rem_nt | Rh as it stands
+                    bin = ph >> rem_nt;
+                    x[i] = (pl << rem_nt) | (ph & rm);
+                } else {
+                    const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
+                    if (cd.dir_off + key < gp.slot_lo || cd.dir_off + key >= gp.slot_hi) continue;
+                    if (!LIB && gp.prune && gp.lib_dir[cd.dir_off + key] == gp.lib_dir[cd.dir_off + key + 1]) continue;
+                    bin = key >> low;
+                    x[i] = ((key & low_mask) << (2u * rem_nt)) | ((pl & rm) << rem_nt) | (ph & rm);
+                }
                 rb[i] = atomicAdd(&s_hist[bin], 1u) | (bin << 16);
             }
             __syncthreads();
@@ -437,13 +470,17 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
 static_assert(CJ_MAX_BINS == 2 * CJ_THREADS, "k_cbin scans two bins per thread");
 static_assert(CJ_CHUNK <= 65536, "k_cbin packs the local rank into 16 bits");
 
-// chunk_bin[ch] = bin that holds record ch * CJ_CHUNK of the pass-A output
+#ifndef CJ_PLACE_FORM
+#define CJ_PLACE_FORM 1   // pass B: 0 staged (LDG), 1 bulk-async with 4096-record chunks and 2 CTAs per SM, 2 bulk-async with 8192-record chunks (7.80 / 8.05 ms at cfg 4)
+#endif
+#define CJ_PLACE_CHUNK (CJ_PLACE_FORM == 1 ? CJ_CHUNK / 2 : CJ_CHUNK)  // records per pass-B chunk
+// chunk_bin[ch] = bin that holds record ch * CJ_PLACE_CHUNK of the pass-A output
 __global__ void k_cchunk_bins(const uint32_t* __restrict__ bin_start, uint32_t n_bins, const uint32_t* __restrict__ n_rec_ptr,
                               uint32_t* __restrict__ chunk_bin) {
     const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_rec = *n_rec_ptr;
-    if ((uint64_t)ch * CJ_CHUNK >= n_rec) return;
-    const uint32_t r = ch * CJ_CHUNK;
+    if ((uint64_t)ch * CJ_PLACE_CHUNK >= n_rec) return;
+    const uint32_t r = ch * CJ_PLACE_CHUNK;
     uint32_t lo = 0, hi = n_bins;  // bin_start[lo] <= r < bin_start[hi]
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -600,6 +637,7 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
                                                                              const uint2* __restrict__ tmp,
                                                                              const uint32_t* __restrict__ bin_start,
                                                                              const uint8_t* __restrict__ bin_combo,
+                                                                             const uint32_t* __restrict__ chunk_bin,
                                                                              uint32_t n_bins, uint32_t* __restrict__ gcursor,
                                                                              uint2* __restrict__ gwin, uint32_t* __restrict__ out_id,
                                                                              const uint32_t* __restrict__ n_rec_ptr,
@@ -612,7 +650,7 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
     uint32_t* s_delta = s_lstart + max_sub;                      // [max_sub]
     uint32_t* s_warp = s_delta + max_sub;                        // [CJ_THREADS / 32]
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_chunk[2];
+    __shared__ uint32_t s_chunk[2], s_cbin[2];
     const uint32_t tid = threadIdx.x;
     const uint32_t n_rec = *n_rec_ptr;
     const uint32_t n_chunks = (uint32_t)(((uint64_t)n_rec + CH - 1) / CH);
@@ -622,6 +660,7 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t ch = atomicAdd(work, 1u);
         s_chunk[0] = ch;
+        if (CH == CJ_PLACE_CHUNK && ch < n_chunks) s_cbin[0] = __ldg(chunk_bin + ch);
         if (ch < n_chunks) {
             const uint32_t r0 = ch * CH, cnt = min(CH, n_rec - r0);
             pl_bulk_load(s_buf, tmp + r0, (cnt * 8u + 15u) & ~15u, &s_bar[0]);
@@ -638,15 +677,20 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
             if (nx < n_chunks) {
                 const uint32_t r0n = nx * CH, cntn = min(CH, n_rec - r0n);
                 pl_bulk_load(s_buf + (cur ^ 1u) * CH, tmp + r0n, (cntn * 8u + 15u) & ~15u, &s_bar[cur ^ 1u]);
+                if (CH == CJ_PLACE_CHUNK) s_cbin[cur ^ 1u] = __ldg(chunk_bin + nx);
             }
         }
         pl_mbar_wait(&s_bar[cur], cur ? parity1 : parity0);
         if (cur) parity1 ^= 1u; else parity0 ^= 1u;
         uint2* buf = s_buf + cur * CH;
         const uint32_t r0 = ch * CH, r1 = r0 + min(CH, n_rec - r0);
-        // bin of the chunk's first record (one thread searches; chunks mostly lie inside one bin)
+        // bin of the chunk's first record: from the chunk table (k_cchunk_bins), fetched together with the chunk by the
+        // elected thread.  (Every warp searching bin_start itself - 14 dependent loads per chunk - was the top stall
+        // site of this kernel: ncu, 15.8 % of the samples.)
         uint32_t g;
-        {
+        if (CH == CJ_PLACE_CHUNK) {
+            g = s_cbin[cur];
+        } else {
             uint32_t lo = 0, hi = n_bins;  // bin_start[lo] <= r0 < bin_start[hi]
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
@@ -889,7 +933,7 @@ __device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint
 // costs no registers: while tile t is verified, the window words and the first bucket stage of tile
 // t+1 and the descriptor of tile t+2 are in flight; the switch to the next tile is three LDS.
 #ifndef CV_ALU_PAIRS
-#define CV_ALU_PAIRS 1
+#define CV_ALU_PAIRS 0   // (round 1's dense kernel saturated the XU pipe and won 3 % from this; the pipelined kernel does not: 11.9 vs 12.1 ms)
 #endif
 #define CV_WTILE (32 * CV_ITEMS)
 #ifndef CV_TILE_INLINE
@@ -946,6 +990,35 @@ __device__ __forceinline__ void cv_issue_stage(const CvPipe& pp, uint32_t ls, ui
     }
 }
 
+// One group: UNITS x 2 entries (one 16-byte broadcast LDS each) against the ITEMS windows of the lane; pass[it] = some
+// entry of the group is within K mismatches of window it.  In a full group one pair in eight goes to the ALU pipe
+// (CV_ALU_PAIRS).
+template <int K, int ITEMS, int UNITS>
+__device__ __forceinline__ void cv_group(const uint4* sg, const uint32_t (&wh)[ITEMS], const uint32_t (&wl)[ITEMS], bool (&pass)[ITEMS]) {
+    int best_[ITEMS];
+    uint32_t rest_[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) { best_[it] = 33; rest_[it] = 1u; }
+#pragma unroll
+    for (int j = 0; j < UNITS; j++) {
+        const uint4 e2 = sg[j];
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            best_[it] = min(best_[it], __popc((wh[it] ^ e2.x) | (wl[it] ^ e2.y)));
+            if (CV_ALU_PAIRS && UNITS == CV_GROUP / 2 && j == UNITS - 1) {
+                uint32_t m = (wh[it] ^ e2.z) | (wl[it] ^ e2.w);
+#pragma unroll
+                for (int cc = 0; cc < K; cc++) m &= m - 1u;
+                rest_[it] = m;
+            } else {
+                best_[it] = min(best_[it], __popc((wh[it] ^ e2.z) | (wl[it] ^ e2.w)));
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) pass[it] = best_[it] <= K || rest_[it] == 0u;
+}
+
 // Verifies tile t (descriptor d, slot) whose window words and first bucket stage were requested
 // earlier; before its last stage is computed the loads of tile t+1 (and descriptor t+2) are issued.
 // sc = running stage counter (selects the bucket stage buffer); returns the queue fill.
@@ -988,41 +1061,30 @@ static __device__ CV_TILE_INLINE uint32_t cv_tile(const SearchParams& p, const C
             }
         }
         const uint4* sb = reinterpret_cast<const uint4*>(pp.ent + ((sc + c) & 1u) * CV_STAGE);
-        const uint32_t ng = (min((uint32_t)CV_STAGE, n_ent - c * CV_STAGE) + CV_GROUP - 1) / CV_GROUP;
+        // groups of CV_GROUP entries; the last group of a bucket is tested in units of two entries (one LDS.128) instead
+        // of being padded to eight: buckets hold ~19 entries at cfg 4, so padding cost 16 % of all POPCs
+        const uint32_t n_here = min((uint32_t)CV_STAGE, n_ent - c * CV_STAGE);
+        const uint32_t n_full = n_here / CV_GROUP, tail_units = ((n_here % CV_GROUP) + 1u) / 2u;
+        const uint32_t ng = n_full + (tail_units ? 1u : 0u);
         const uint32_t ebase = ls + c * CV_STAGE;
         uint32_t g = 0;
         for (;;) {
             for (; g < ng && gn < 32; g++) {
-                int best_[ITEMS];
-                uint32_t rest_[ITEMS];
-#pragma unroll
-                for (int it = 0; it < ITEMS; it++) { best_[it] = 33; rest_[it] = 1u; }
-#pragma unroll
-                for (int j = 0; j < CV_GROUP / 2; j++) {
-                    const uint4 e2 = sb[g * (CV_GROUP / 2) + j];
-#pragma unroll
-                    for (int it = 0; it < ITEMS; it++) {
-                        best_[it] = min(best_[it], __popc((wh[it] ^ e2.x) | (wl[it] ^ e2.y)));
-                        if (CV_ALU_PAIRS && j == CV_GROUP / 2 - 1) {
-                            uint32_t m = (wh[it] ^ e2.z) | (wl[it] ^ e2.w);
-#pragma unroll
-                            for (int cc = 0; cc < K; cc++) m &= m - 1u;
-                            rest_[it] = m;
-                        } else {
-                            best_[it] = min(best_[it], __popc((wh[it] ^ e2.z) | (wl[it] ^ e2.w)));
-                        }
-                    }
-                }
+                bool pass_[ITEMS];
+                const uint4* sg = sb + g * (CV_GROUP / 2);
+                if (g < n_full || tail_units == CV_GROUP / 2) cv_group<K, ITEMS, CV_GROUP / 2>(sg, wh, wl, pass_);
+                else if (tail_units == 1) cv_group<K, ITEMS, 1>(sg, wh, wl, pass_);
+                else if (tail_units == 2) cv_group<K, ITEMS, 2>(sg, wh, wl, pass_);
+                else cv_group<K, ITEMS, 3>(sg, wh, wl, pass_);
 #pragma unroll
                 for (int it = 0; it < ITEMS; it++) {
-                    const bool pass_ = best_[it] <= K || rest_[it] == 0u;
 #ifdef CV_DEBUG_NO_SECOND  // timing experiment only: first level alone (no hits are produced)
-                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_) & (first == 0xffffffffu ? 1u : 0u);
+                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_[it]) & (first == 0xffffffffu ? 1u : 0u);
 #else
-                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_);
+                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_[it]);
 #endif
                     if (hit_) {  // warp-uniform
-                        if (pass_)
+                        if (pass_[it])
                             gq[gn + __popc(hit_ & lt_mask)] =
                                 make_uint4(wh[it] | (wl[it] << 16), first + it * 32 + lane, ebase + g * CV_GROUP, slot);
                         gn += __popc(hit_);
@@ -1175,10 +1237,25 @@ __global__ void __launch_bounds__(CV_THREADS, 4) k_cfinish(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------ host
-#define JCK(call)                           \
-    do {                                    \
-        cudaError_t e__ = (call);           \
-        if (e__ != cudaSuccess) return e__; \
+// BC_WIN_COUNT=red (environment, A/B runs only): count the windows per slot with one global RED per record
+// (k_ccount, the round-1 form) instead of k_cbincount + k_cslotcount
+static bool cj_red_count() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BC_WIN_COUNT");
+        v = (e && !strcmp(e, "red")) ? 1 : 0;
+    }
+    return v != 0;
+}
+
+
+#define JCK(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            if (getenv("BC_DEBUG")) fprintf(stderr, "bc_cjoin.cu:%d: %s\n", __LINE__, cudaGetErrorString(e__)); \
+            return e__;                                                                             \
+        }                                                                                           \
     } while (0)
 
 static cudaError_t cj_ensure_bins(JoinWorkspace& ws, uint32_t n_bins, uint64_t max_chunks) {
@@ -1193,9 +1270,7 @@ static cudaError_t cj_ensure_bins(JoinWorkspace& ws, uint32_t n_bins, uint64_t m
     return cudaSuccess;
 }
 
-#ifndef CJ_PLACE_FORM
-#define CJ_PLACE_FORM 2   // pass B: 0 staged (LDG), 1 bulk-async with 4096-record chunks, 2 bulk-async with 8192-record chunks
-#endif
+
 template <bool LIB>
 static cudaError_t cj_launch_place(const CBucketParams& gp, const uint2* tmp, const uint32_t* bin_start, const uint8_t* bin_combo,
                                    const uint32_t* chunk_bin, uint32_t n_bins, uint32_t* gcursor, uint2* out, uint32_t* out_id,
@@ -1208,12 +1283,12 @@ static cudaError_t cj_launch_place(const CBucketParams& gp, const uint2* tmp, co
     } else if (CJ_PLACE_FORM == 1) {
         const size_t smem = 2 * (size_t)CJ_THREADS * 8 * 8 + (3 * (size_t)max_sub + CJ_THREADS / 32) * 4;
         JCK(cudaFuncSetAttribute(k_cplace_bulk<LIB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_cplace_bulk<LIB, 8><<<(uint32_t)sm_count * 2u, CJ_THREADS, smem, st>>>(gp, tmp, bin_start, bin_combo, n_bins, gcursor, out, out_id,
+        k_cplace_bulk<LIB, 8><<<(uint32_t)sm_count * 2u, CJ_THREADS, smem, st>>>(gp, tmp, bin_start, bin_combo, chunk_bin, n_bins, gcursor, out, out_id,
                                                                               n_rec_ptr, work, max_sub);
     } else {
         const size_t smem = 2 * (size_t)CJ_THREADS * 16 * 8 + (3 * (size_t)max_sub + CJ_THREADS / 32) * 4;
         JCK(cudaFuncSetAttribute(k_cplace_bulk<LIB, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_cplace_bulk<LIB, 16><<<(uint32_t)sm_count, CJ_THREADS, smem, st>>>(gp, tmp, bin_start, bin_combo, n_bins, gcursor, out, out_id,
+        k_cplace_bulk<LIB, 16><<<(uint32_t)sm_count, CJ_THREADS, smem, st>>>(gp, tmp, bin_start, bin_combo, chunk_bin, n_bins, gcursor, out, out_id,
                                                                            n_rec_ptr, work, max_sub);
     }
     return cudaGetLastError();
@@ -1247,7 +1322,7 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
         const uint32_t low = 2u * gp.combo[c].key_nt - gp.combo[c].top_bits;
         if (low > max_low) max_low = low;
     }
-    const uint64_t max_chunks = ((uint64_t)ip.n_entries * n_combos + CJ_CHUNK - 1) / CJ_CHUNK + 1;
+    const uint64_t max_chunks = ((uint64_t)ip.n_entries * n_combos + CJ_PLACE_CHUNK - 1) / CJ_PLACE_CHUNK + 1;
     JCK(cj_ensure_bins(ws, n_bins, max_chunks));
     uint32_t* d_bin_cursor = ws.d_bin_cursor;
     uint32_t* d_bin_start = d_bin_cursor + (n_bins + 2);
@@ -1258,40 +1333,49 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
     if (CJ_LUT_BITS != 8 && ip.L > 2 * CJ_LUT_BITS) return cudaErrorInvalidValue;  // choose_scheme keeps such spacers off this path
     k_clut_build<<<(n_combos * CJ_LUT_WORDS + 255) / 256, 256, 0, st>>>(gp, ws.d_lut);
     JCK(cudaGetLastError());
-    uint32_t gx = (ip.n_entries + 255) / 256;
-    if (gx > (uint32_t)sm_count * 8u) gx = (uint32_t)sm_count * 8u;
-    k_ccount<true><<<dim3(gx, n_combos), 256, 0, st>>>(gp, ws.d_lut, d_dir);
-    JCK(cudaGetLastError());
-    JCK(bc_exclusive_scan(d_dir, dir_slots, d_scan_tmp, st));
-    JCK(cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    k_cbin_init<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, d_dir, n_bins, n_slots, d_bin_start, d_bin_cursor, d_bin_combo);
-    JCK(cudaGetLastError());
     const size_t smem_a = cj_smem_a();
     const uint32_t max_sub = 1u << max_low;
     const size_t smem_b = (3 * (size_t)max_sub + CJ_THREADS / 32) * 4 + (size_t)CJ_CHUNK * 8;
     JCK(cudaFuncSetAttribute(k_cbin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
     uint32_t bx = (ip.n_entries + CJ_CHUNK - 1) / CJ_CHUNK;
     if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
-    k_cbin<true><<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, tmp);
-    JCK(cudaGetLastError());
-    k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, d_dir + n_slots, d_chunk_bin);
+    const uint32_t* n_rec_ptr;
+    if (cj_red_count()) {  // round-1 form: one global RED per (entry, combination)
+        uint32_t gx = (ip.n_entries + 255) / 256;
+        if (gx > (uint32_t)sm_count * 8u) gx = (uint32_t)sm_count * 8u;
+        k_ccount<true><<<dim3(gx, n_combos), 256, 0, st>>>(gp, ws.d_lut, d_dir);
+        JCK(cudaGetLastError());
+        JCK(bc_exclusive_scan(d_dir, dir_slots, d_scan_tmp, st));
+        JCK(cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        k_cbin_init<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, d_dir, n_bins, n_slots, d_bin_start, d_bin_cursor, d_bin_combo);
+        JCK(cudaGetLastError());
+        k_cbin<true><<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, tmp);
+        JCK(cudaGetLastError());
+        n_rec_ptr = d_dir + n_slots;
+    } else {               // bin totals and the slot histogram from shared-memory histograms (see k_cbincount)
+        JCK(cudaMemsetAsync(d_bin_cursor, 0, (n_bins + 1) * sizeof(uint32_t), st));
+        k_cbincount<true><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
+        JCK(cudaGetLastError());
+        JCK(bc_exclusive_scan(d_bin_cursor, (uint64_t)n_bins + 1, d_scan_tmp, st));
+        k_cbin_init2<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, n_bins, d_bin_cursor, d_bin_start, d_bin_combo);
+        JCK(cudaGetLastError());
+        k_cbin<true><<<bx, CJ_THREADS, smem_a, st>>>(gp, ws.d_lut, d_bin_cursor, tmp);
+        JCK(cudaGetLastError());
+        JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
+        k_cslotcount<<<(uint32_t)sm_count * 2u, CS_THREADS, max_sub * sizeof(uint32_t), st>>>(gp, tmp, d_bin_start, d_bin_combo, n_bins, d_dir,
+                                                                                        ws.d_work);
+        JCK(cudaGetLastError());
+        JCK(bc_exclusive_scan(d_dir, dir_slots, d_scan_tmp, st));
+        JCK(cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        n_rec_ptr = d_bin_start + n_bins;
+    }
+    k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, n_rec_ptr, d_chunk_bin);
     JCK(cudaGetLastError());
     JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
-    JCK(cj_launch_place<true>(gp, tmp, d_bin_start, d_bin_combo, d_chunk_bin, n_bins, d_cursor, ent_hl, ent_id, d_dir + n_slots,
+    JCK(cj_launch_place<true>(gp, tmp, d_bin_start, d_bin_combo, d_chunk_bin, n_bins, d_cursor, ent_hl, ent_id, n_rec_ptr,
                               ws.d_work, max_sub, smem_b, sm_count, st));
     bc_launch_counter += 7;
     return cudaSuccess;
-}
-
-// BC_WIN_COUNT=red (environment, A/B runs only): count the windows per slot with one global RED per record
-// (k_ccount, the round-1 form) instead of k_cbincount + k_cslotcount
-static bool cj_red_count() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("BC_WIN_COUNT");
-        v = (e && !strcmp(e, "red")) ? 1 : 0;
-    }
-    return v != 0;
 }
 
 // CTAs of k_cverify per SM: CV_MINBLOCKS fills the register file; BC_VERIFY_CTAS (environment, experiments only)
@@ -1351,7 +1435,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         ws.gwin_cap = want;
     }
     // per-bin tables live in the bin cursor allocation: cursor | start (+1) | chunk table | combination bytes
-    const uint64_t max_chunks = (chunk * p.n_combos + CJ_CHUNK - 1) / CJ_CHUNK + 1;
+    const uint64_t max_chunks = (chunk * p.n_combos + CJ_PLACE_CHUNK - 1) / CJ_PLACE_CHUNK + 1;
     JCK(cj_ensure_bins(ws, n_bins, max_chunks));
     uint32_t* d_bin_cursor = ws.d_bin_cursor;
     uint32_t* d_bin_start = d_bin_cursor + (n_bins + 2);
@@ -1467,7 +1551,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             JCK(cudaGetLastError());
         } else {          // bin totals from shared-memory histograms; the slot histogram follows pass A
             JCK(cudaMemsetAsync(d_bin_cursor, 0, (n_bins + 1) * sizeof(uint32_t), st));
-            k_cbincount<<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
+            k_cbincount<false><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
             JCK(cudaGetLastError());
             JCK(cudaEventRecord(ws.ev_k[0], st));  // end of the bin count
             JCK(bc_exclusive_scan(d_bin_cursor, (uint64_t)n_bins + 1, ws.d_scan_tmp, st));
@@ -1482,7 +1566,6 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         const uint32_t* n_rec_ptr = red_count ? ws.d_gdir + n_slots : d_bin_start + n_bins;
         if (!red_count) {   // slot histogram of the binned records, then the slot starts
             JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
-            JCK(cudaFuncSetAttribute(k_cslotcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_sub * sizeof(uint32_t))));
             k_cslotcount<<<(uint32_t)sm_count * 2u, CS_THREADS, max_sub * sizeof(uint32_t), st>>>(gp, one_pass ? d_win : d_tmp, d_bin_start, d_bin_combo, n_bins,
                                                                                             ws.d_gdir, ws.d_work);
             JCK(cudaGetLastError());
