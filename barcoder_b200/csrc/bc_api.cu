@@ -61,6 +61,9 @@ struct bc_ctx {
     uint64_t ent_cap = 0, dir_cap = 0, scan_tmp_cap = 0;
     uint32_t* d_pdir = nullptr;       // probe path: packed directory (bc_launch_dir_pack)
     uint64_t pdir_cap = 0;
+    uint32_t* d_ent_h = nullptr;      // probe path: H planes of the index entries (bc_launch_ent_h_pack)
+    uint64_t ent_h_cap = 0;
+    bool have_ent_h = false;
     bool packed_dir = false;
 
     // join workspace
@@ -153,6 +156,7 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     dfree(ctx->d_dir); dfree(ctx->d_cursor); dfree(ctx->d_scan_tmp); dfree(ctx->d_ent_id); dfree(ctx->d_ent_hl);
     dfree(ctx->d_ent_tmp); dfree(ctx->d_coarse_cursor);
     dfree(ctx->d_pdir);
+    dfree(ctx->d_ent_h);
     dfree(ctx->d_hits); dfree(ctx->d_count);
     dfree(ctx->d_sort_scratch); dfree(ctx->d_sort_hist); dfree(ctx->d_sort_tmp); dfree(ctx->d_sort_orand);
     bc_join_free(ctx->join);
@@ -528,12 +532,12 @@ static double scheme_cost(const bc_ctx* ctx, const Scheme& s, uint32_t path) {
         while (!radix && slots_per_combo > 65536.0) { c_sort += 6.0; slots_per_combo *= 0.5; }
         return (c_sort + c_rec) * records + 0.25 * cands + common + 5.0 * (double)s.dir_slots + 1.0e8;
     }
-    // compact join (measured at cfg 4, 9- and 10-nt designs): sort 17-18 ps per record, index 20 ps per
-    // (entry, combination) with the radix builder, first-level verify 0.25 ps per candidate plus ~5 ps
-    // per record of tile overhead when the slots are small (< 256 windows)
-    const double c_sort = s.key_nt_max <= 5 ? 10.0 : 17.5;
+    // compact join (measured at cfg 4, 9- and 10-nt designs, round-2 kernels): sort 14 ps per record (bin count 1.3,
+    // pass A 6.1, slot count 1.3, pass B 5.2), index 18 ps per (entry, combination) with the radix builder, verify +
+    // finish 0.25 ps per candidate plus ~5 ps per record of tile overhead when the slots are small (< 256 windows)
+    const double c_sort = s.key_nt_max <= 5 ? 9.0 : 14.2;
     const double c_tile = windows / slots_per_combo >= 256.0 ? 1.0 : 5.0;
-    return (c_sort + c_tile) * records + 0.25 * cands + 20.0 * entries + 10.0 * (double)s.dir_slots + 1.2e8;
+    return (c_sort + c_tile) * records + 0.25 * cands + 18.0 * entries + 10.0 * (double)s.dir_slots + 1.2e8;
 }
 
 static int choose_scheme(bc_ctx* ctx, uint32_t k, Scheme* best, uint32_t* path_out) {
@@ -664,6 +668,19 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
         CK(bc_launch_dir_pack(ctx->d_dir, (uint32_t)(s.dir_slots - 1), ctx->d_pdir, ctx->sm_count, ctx->stream));
         ctx->packed_dir = true;
     }
+    ctx->have_ent_h = false;
+    if (path == 1 && ctx->par_compact_dir != 1) {
+        // probe path: H planes of the entries as a dense array (tested first; halves the L2 working set of the entries)
+        if (ent_needed + 4 > ctx->ent_h_cap) {
+            dfree(ctx->d_ent_h);
+            ctx->ent_h_cap = 0;
+            CK(cudaMalloc(&ctx->d_ent_h, (ent_needed + 4) * sizeof(uint32_t)));
+            ctx->ent_h_cap = ent_needed + 4;
+        }
+        CK(cudaMemsetAsync(ctx->d_ent_h + ent_needed, 0, 4 * sizeof(uint32_t), ctx->stream));
+        CK(bc_launch_ent_h_pack(ctx->d_ent_hl, ent_needed, ctx->d_ent_h, ctx->sm_count, ctx->stream));
+        ctx->have_ent_h = true;
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev0, ctx->ev1));
@@ -697,6 +714,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->ent_id = ctx->d_ent_id;
     p->dir_entries = 2ull * ctx->n * ctx->n_combos;
     p->pdir = ctx->packed_dir ? ctx->d_pdir : nullptr;
+    p->ent_h = ctx->have_ent_h ? ctx->d_ent_h : nullptr;
     p->P = ctx->P;
     p->pam_dir = ctx->pam_dir;
     p->pam_flags = ctx->pam_flags;

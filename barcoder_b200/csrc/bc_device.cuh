@@ -65,6 +65,7 @@ struct SearchParams {
     const uint32_t* ent_id;
     unsigned long long dir_entries;  // index entries over all combinations
     const uint32_t* pdir;            // probe path: packed directory (start | count << 26), one load per probe; or null
+    const uint32_t* ent_h;           // probe path: H planes of the entries (ent_hl[e].x) as a dense array, padded to 4; or null
     // PAM
     uint32_t P, pam_dir, pam_flags;
     uint32_t pam_sets[8];       // per PAM position: allowed set over {A=1,C=2,G=4,T=8}

@@ -320,6 +320,20 @@ cudaError_t bc_launch_dir_pack(const uint32_t* dir, uint32_t n_slots, uint32_t* 
     return cudaGetLastError();
 }
 
+// H planes of the index entries as an array of their own (probe path).  A candidate is first tested on its H plane
+// alone - popc(wh ^ qh) <= popc((wh ^ qh) | (wl ^ ql)), so nothing is lost - and only survivors fetch the Lo plane:
+// the entry working set that has to stay in L2 halves (cfg 5: 48 -> 24 MB next to 38 MB of directories; ncu had 36 %
+// of the probe kernel's sectors coming from HBM), and four consecutive entries arrive with one 16-byte load.
+__global__ void __launch_bounds__(256) k_ent_h_pack(const uint2* __restrict__ ent_hl, uint64_t n, uint32_t* __restrict__ ent_h) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) ent_h[i] = ent_hl[i].x;
+}
+
+cudaError_t bc_launch_ent_h_pack(const uint2* ent_hl, uint64_t n, uint32_t* ent_h, int sm_count, cudaStream_t st) {
+    k_ent_h_pack<<<(unsigned)sm_count * 8u, 256, 0, st>>>(ent_hl, n, ent_h);
+    bc_launch_counter += 1;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------ K3-probe
 // Streams the genome planes tile by tile through shared memory; every thread owns one window
 // per step, builds the seed keys of each combination, looks the bucket up in the directory and
@@ -351,17 +365,17 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
     __shared__ HitStage stage;
     __shared__ uint16_t s_l1[PROBE_WARPS][PROBE_THREADS];   // surviving windows of the warp (tile-local)
     __shared__ uint4 s_l2[PROBE_WARPS][PROBE_L2_CAP];       // non-empty buckets of the warp
-    __shared__ uint32_t s_n2[PROBE_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     if (threadIdx.x == 0) stage.n = 0;
-    if (lane == 0) s_n2[warp] = 0;
     const uint32_t lm = bc_lmask(p.L);
     PamGate gate;
     bc_gate_init(gate, p.P, p.L, p.pam_dir, p.pam_sets);
     const int k = (int)p.k;
     uint16_t* l1 = s_l1[warp];
     uint4* l2 = s_l2[warp];
-    uint32_t* n2p = &s_n2[warp];
+    uint32_t n2 = 0;  // buckets in the warp's list (warp-uniform register; a shared counter bumped with one atomic per
+                      // bucket cost 5e9 serialised shared-memory wavefronts at cfg 5 - as many as all global loads)
     unsigned long long cand = 0, probes = 0;
 
     // Tiles are handed out through an atomic counter (p.count[3], zeroed with the other counters):
@@ -401,7 +415,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
         __syncwarp();
 
         // ---- phase B (+ C whenever the bucket list fills up)
-        for (uint32_t r = 0; r < n1 || *n2p; r += 32) {  // warp-uniform: n1 and *n2p are shared by the warp
+        for (uint32_t r = 0; r < n1 || n2; r += 32) {  // warp-uniform
             if (r < n1) {
                 const bool have = r + lane < n1;
                 const uint32_t t = have ? l1[r + lane] : 0;
@@ -431,43 +445,60 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
                     }
                     if (have) probes += min((uint32_t)PROBE_BATCH, p.n_combos - c0);
 #pragma unroll
-                    for (int j = 0; j < PROBE_BATCH; j++) {
-                        if (eb[j] < ee[j]) {
-                            const uint32_t s2 = atomicAdd(n2p, 1u);  // < PROBE_L2_CAP: drained below before it can fill
-                            l2[s2] = make_uint4(t, c0 + j, eb[j], ee[j]);
-                        }
+                    for (int j = 0; j < PROBE_BATCH; j++) {  // ballot compaction: < PROBE_L2_CAP, drained below before it can fill
+                        const bool ne = eb[j] < ee[j];
+                        const uint32_t bal = __ballot_sync(0xffffffffu, ne);
+                        if (ne) l2[n2 + __popc(bal & lt_mask)] = make_uint4(t, c0 + j, eb[j], ee[j]);
+                        n2 += __popc(bal);
                     }
                     __syncwarp();
-                    if (*n2p + 32 * PROBE_BATCH <= PROBE_L2_CAP && (c0 + PROBE_BATCH < p.n_combos || r + 32 < n1))
+                    if (n2 + 32 * PROBE_BATCH <= PROBE_L2_CAP && (c0 + PROBE_BATCH < p.n_combos || r + 32 < n1))
                         continue;  // room for another batch: keep collecting
                     // ---- phase C: one bucket per lane
-                    const uint32_t n2 = *n2p;
                     for (uint32_t b0 = 0; b0 < n2; b0 += 32) {
                         if (b0 + lane < n2) {
                             const uint4 it = l2[b0 + lane];
                             const uint32_t its = it.x + 32;
                             const uint32_t bh = bc_window(sH, its) & lm, bl = bc_window(sL, its) & lm;
                             cand += it.w - it.z;
-                            for (uint32_t e = it.z; e < it.w; e++) {
-                                const uint2 q = __ldg(p.ent_hl + e);
-                                const uint32_t m = (bh ^ q.x) | (bl ^ q.y);
-                                if (__popc(m) <= k) {
-                                    uint4 rec;
-                                    if (bc_make_hit(p, it.y, tile_pos + it.x, p.ent_id[e], m, &rec))
-                                        bc_stage_hit(p, &stage, rec);
+                            if (p.ent_h) {
+                                // H planes first, four consecutive entries per 16-byte load; the Lo plane only for survivors
+                                for (uint32_t e4 = it.z & ~3u; e4 < it.w; e4 += 4) {
+                                    const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(p.ent_h + e4));
+                                    const uint32_t qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                                    for (uint32_t u = 0; u < 4; u++) {
+                                        const uint32_t e = e4 + u, mh = bh ^ qq[u];
+                                        if (e >= it.z && e < it.w && __popc(mh) <= k) {
+                                            const uint32_t m = mh | (bl ^ __ldg(&p.ent_hl[e].y));
+                                            if (__popc(m) <= k) {
+                                                uint4 rec;
+                                                if (bc_make_hit(p, it.y, tile_pos + it.x, p.ent_id[e], m, &rec))
+                                                    bc_stage_hit(p, &stage, rec);
+                                            }
+                                        }
+                                    }
+                                }
+                            } else {
+                                for (uint32_t e = it.z; e < it.w; e++) {
+                                    const uint2 q = __ldg(p.ent_hl + e);
+                                    const uint32_t m = (bh ^ q.x) | (bl ^ q.y);
+                                    if (__popc(m) <= k) {
+                                        uint4 rec;
+                                        if (bc_make_hit(p, it.y, tile_pos + it.x, p.ent_id[e], m, &rec))
+                                            bc_stage_hit(p, &stage, rec);
+                                    }
                                 }
                             }
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) *n2p = 0;
-                    __syncwarp();
+                    n2 = 0;
                 }
             } else {
                 // nothing left to probe but buckets are pending (cannot happen with the drain rule
                 // above; kept so the loop condition is always safe)
-                if (lane == 0) *n2p = 0;
-                __syncwarp();
+                n2 = 0;
             }
         }
         bc_flush_hits(p, &stage);

@@ -72,3 +72,4 @@ size_t bc_sort_hist_words(uint64_t n);
 
 // probe path: packed directory, one 4-byte load per probe (start | count << 26)
 cudaError_t bc_launch_dir_pack(const uint32_t* dir, uint32_t n_slots, uint32_t* pdir, int sm_count, cudaStream_t st);
+cudaError_t bc_launch_ent_h_pack(const uint2* ent_hl, uint64_t n, uint32_t* ent_h, int sm_count, cudaStream_t st);

@@ -122,6 +122,22 @@ def int_peak(device):
     return {"popc_per_s": popc.value, "verify_atom_per_s": atom.value, "sm_count": sms.value}
 
 
+def gather_peak(device, table_mb):
+    """Divergent 4-byte loads per second an SM array can retire from an L2-resident table (bench_kernels/int_peak.cu):
+    the bound of the probe kernel, whose directory probes and bucket reads touch one 128-byte line per lane."""
+    import ctypes
+    so = os.path.join(ROOT, "bench_kernels", "libbc_ubench.so")
+    if not os.path.exists(so):
+        return None
+    lib = ctypes.CDLL(so)
+    if not hasattr(lib, "ub_gather_peak"):
+        return None
+    rate = ctypes.c_double()
+    if lib.ub_gather_peak(int(device), int(table_mb), ctypes.byref(rate)) != 0:
+        return None
+    return rate.value
+
+
 def source_hash():
     """Hash of the kernel sources: profiles/traffic.json is only trusted for the code it was captured from."""
     import glob
@@ -649,9 +665,33 @@ def main():
                         "peak_source": "bench_kernels/int_peak.cu measured in this run (POPC: 16/clk/SM)",
                         "note": "peak = one POPC per candidate pair (1 pair in 8 is tested on the ALU pipe instead); "
                                 "pairs_vs_k_plus_1 = candidates / what the classic k+1-seed filter would verify"}
-    # `roofline` = the bound that binds the dominant stage: the POPC pipe for verification, HBM otherwise
+    roofline_gather = None
+    if st["path"] == 1 and acc["ms_scan_kernel"] > 0:
+        # probe kernel: divergent loads (directory probes + bucket entries, one 128-byte line per lane each) per second
+        # against the rate measured by the gather microbenchmark on an L2-resident table of the directories' size
+        s.set_param(_native.BC_PARAM_COUNT_CANDIDATES, 1)
+        s.search(k)
+        stc = s.stats()
+        s.set_param(_native.BC_PARAM_COUNT_CANDIDATES, 0)
+        gathers = float(stc["probes"] + stc["candidates"])
+        table_mb = 64
+        gpk = gather_peak(local_rank, table_mb)
+        if gpk:
+            rate = gathers / (parts[verify_key] / 1e3)
+            roofline_gather = {"bound": "l1_gather", "kernel": names[verify_key], "achieved": rate / 1e9, "peak": gpk / 1e9,
+                               "unit": "G divergent loads/s", "frac": rate / gpk, "probes": stc["probes"],
+                               "bucket_entries_read": stc["candidates"], "traffic": traffic if dominant == verify_key else None,
+                               "share_of_step": parts[verify_key] / max(ms_per_step, 1e-9),
+                               "peak_source": f"bench_kernels/int_peak.cu k_gather measured in this run ({table_mb} MB table, "
+                                              "8 independent loads in flight per thread)",
+                               "note": "every window costs one directory probe per seed combination plus one load per entry "
+                                       "of a non-empty bucket; each is its own L1TEX wavefront"}
+    # `roofline` = the bound that binds the dominant stage: the POPC pipe for verification, the divergent-load rate for
+    # the probe kernel, HBM otherwise
     if dominant == verify_key and roofline_int:
         roofline = dict(roofline_int, hbm_view=roofline_hbm)
+    elif dominant == verify_key and roofline_gather:
+        roofline = dict(roofline_gather, hbm_view=roofline_hbm)
     else:
         roofline = dict(roofline_hbm, int_view=roofline_int)
     roofline["stage_ms"] = {k2: round(v, 4) for k2, v in parts.items()}

@@ -86,3 +86,61 @@ extern "C" int ub_int_peak(int device, double* popc_per_s, double* atom_per_s, i
     if (sm_count_out) *sm_count_out = prop.multiProcessorCount;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------- random gathers
+// The probe kernel (k_scan_probe, cfg 1/2/5) is bound by how many DIVERGENT global loads an SM can
+// retire: every lane of a directory probe or bucket read touches its own 128-byte line, and the L1TEX
+// unit works such a load off one line (wavefront) at a time.  This measures that rate: every thread
+// issues independent 4-byte loads at hashed addresses of a table that stays resident in L2 (table_mb
+// megabytes; 64 MB ~ the cfg-5 directories), UNROLL loads in flight per thread.
+#define GATHER_UNROLL 8
+__global__ void __launch_bounds__(256) k_gather(const uint32_t* __restrict__ table, uint32_t mask, uint32_t iters, uint32_t seed,
+                                                uint32_t* out) {
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + seed;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; it++) {
+        uint32_t v[GATHER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; u++) {
+            x ^= x << 13; x ^= x >> 17; x ^= x << 5;  // xorshift32: independent of the loaded values
+            v[u] = __ldg(table + (x & mask));
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_UNROLL; u++) acc += v[u];
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+extern "C" int ub_gather_peak(int device, int table_mb, double* gathers_per_s) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    size_t words = 1;
+    while (words * 4 * 2 <= (size_t)table_mb << 20) words <<= 1;  // largest power of two that fits
+    uint32_t *d_table = nullptr, *d_out = nullptr;
+    if (cudaMalloc(&d_table, words * 4) != cudaSuccess) return -1;
+    if (cudaMalloc(&d_out, 64) != cudaSuccess) return -1;
+    cudaMemset(d_table, 1, words * 4);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int grid = prop.multiProcessorCount * 8;
+    const uint32_t iters = 256;
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(a);
+        k_gather<<<grid, 256>>>(d_table, (uint32_t)(words - 1), iters, 99u + rep, d_out);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) return -2;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double rate = (double)grid * 256.0 * iters * GATHER_UNROLL / (ms * 1e-3);
+        if (rep >= 2 && rate > best) best = rate;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_table);
+    cudaFree(d_out);
+    *gathers_per_s = best;
+    return 0;
+}

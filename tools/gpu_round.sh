@@ -37,13 +37,13 @@ if has full; then
   # full-set capture of the step's kernels (first launches of each: index build + one search), exported to CSV on
   # the box; the .ncu-rep itself only travels back when it is small (gpurun_out/ is capped at 64 MiB)
   timeout 1500 ncu --set full --clock-control none --import-source on \
-    -k regex:"k_cverify|k_cfinish|k_cbin|k_cplace|k_ccount|k_ctile" -c ${NCU_COUNT:-10} \
+    -k regex:"^(k_cverify|k_cfinish|k_cbin|k_cplace_bulk|k_cbincount|k_cslotcount)$" -c ${NCU_COUNT:-10} \
     -o gpurun_out/full_cfg4 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e \
     > gpurun_out/full_cfg4.out 2>&1
   echo "full rc=$?"
   ncu -i gpurun_out/full_cfg4.ncu-rep --page raw --csv > gpurun_out/full_cfg4_raw.csv 2>/dev/null
-  for kn in k_cverify k_cfinish k_cbin k_cplace_bulk; do
-    ncu -i gpurun_out/full_cfg4.ncu-rep --page source --csv --kernel-name regex:$kn > gpurun_out/full_cfg4_src_$kn.csv 2>/dev/null
+  for kn in k_cverify k_cfinish k_cbin k_cplace_bulk k_cbincount k_cslotcount; do
+    ncu -i gpurun_out/full_cfg4.ncu-rep --page source --csv --kernel-name regex:"^$kn\$" > gpurun_out/full_cfg4_src_$kn.csv 2>/dev/null
   done
   sz=$(du -m gpurun_out/full_cfg4.ncu-rep | cut -f1); echo "rep MiB: $sz"
   if [ "$sz" -gt 30 ]; then rm -f gpurun_out/full_cfg4.ncu-rep; fi
