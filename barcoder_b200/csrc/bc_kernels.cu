@@ -357,6 +357,10 @@ cudaError_t bc_launch_ent_h_pack(const uint2* ent_hl, uint64_t n, uint32_t* ent_
 #ifndef PROBE_MINBLOCKS
 #define PROBE_MINBLOCKS 4
 #endif
+// SINGLE: all combinations fit one batch (every k+1-seed block scheme with k <= 3): the batch loop runs once with
+// c0 = 0, so the combination descriptors are read at fixed constant-bank offsets instead of through an index register
+// (phase B was 44 % of the kernel's instructions at cfg 5).
+template <bool SINGLE>
 __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(const __grid_constant__ SearchParams p,
                                                               uint32_t n_tiles) {
     // plane words [w0 - 1, w0 + 66): the tile, the word before it (PAM left of the first window)
@@ -421,14 +425,15 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
                 const uint32_t t = have ? l1[r + lane] : 0;
                 const uint32_t ts = t + 32;
                 const uint32_t wh = bc_window(sH, ts) & lm, wl = bc_window(sL, ts) & lm;
+                const uint32_t n_combos = SINGLE ? min(p.n_combos, (uint32_t)PROBE_BATCH) : p.n_combos;
 #pragma unroll 1
-                for (uint32_t c0 = 0; c0 < p.n_combos; c0 += PROBE_BATCH) {
+                for (uint32_t c0 = 0; c0 < (SINGLE ? 1u : n_combos); c0 += PROBE_BATCH) {
                     // all directory reads of the batch are issued before the first one is consumed
                     uint32_t eb[PROBE_BATCH], ee[PROBE_BATCH];
 #pragma unroll
                     for (int j = 0; j < PROBE_BATCH; j++) {
                         eb[j] = ee[j] = 0;
-                        if (have && c0 + j < p.n_combos) {
+                        if (have && c0 + j < n_combos) {
                             const uint32_t slot = p.combo[c0 + j].dir_off + bc_combo_key(p.combo[c0 + j], wh, wl);
                             if (slot >= p.slot_lo && slot < p.slot_hi) {  // slot-range sharding
                                 if (p.pdir) {
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
                             }
                         }
                     }
-                    if (have) probes += min((uint32_t)PROBE_BATCH, p.n_combos - c0);
+                    if (have) probes += min((uint32_t)PROBE_BATCH, n_combos - c0);
 #pragma unroll
                     for (int j = 0; j < PROBE_BATCH; j++) {  // ballot compaction: < PROBE_L2_CAP, drained below before it can fill
                         const bool ne = eb[j] < ee[j];
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
                         n2 += __popc(bal);
                     }
                     __syncwarp();
-                    if (n2 + 32 * PROBE_BATCH <= PROBE_L2_CAP && (c0 + PROBE_BATCH < p.n_combos || r + 32 < n1))
+                    if (n2 + 32 * PROBE_BATCH <= PROBE_L2_CAP && ((!SINGLE && c0 + PROBE_BATCH < n_combos) || r + 32 < n1))
                         continue;  // room for another batch: keep collecting
                     // ---- phase C: one bucket per lane
                     for (uint32_t b0 = 0; b0 < n2; b0 += 32) {
@@ -462,7 +467,10 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
                             const uint32_t bh = bc_window(sH, its) & lm, bl = bc_window(sL, its) & lm;
                             cand += it.w - it.z;
                             if (p.ent_h) {
-                                // H planes first, four consecutive entries per 16-byte load; the Lo plane only for survivors
+                                // H planes first, four consecutive entries per 16-byte load; the Lo plane only for survivors.
+                                // (Fetching the first group with cp.async the moment the directory answers, so that it is in
+                                // flight while the warp still probes, measured slower: 95.1 against 90.3 ms at cfg 5;
+                                // 5 CTAs per SM at 51 registers spill: 168 ms.)
                                 for (uint32_t e4 = it.z & ~3u; e4 < it.w; e4 += 4) {
                                     const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(p.ent_h + e4));
                                     const uint32_t qq[4] = {q4.x, q4.y, q4.z, q4.w};
@@ -544,7 +552,8 @@ cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int 
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
     }
-    k_scan_probe<<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
+    if (p.n_combos <= PROBE_BATCH) k_scan_probe<true><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
+    else k_scan_probe<false><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
     cudaError_t e = cudaGetLastError();
     if (pin) {
         cudaStreamAttrValue attr;
