@@ -1593,15 +1593,18 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             bc_launch_counter += 2;
         }
         JCK(cudaEventRecord(ws.ev_a, st));
-        // Streamed delivery: the slices halve (1/2, 1/4, ... and the last one repeated).  Short verify
-        // stages (a slot-range shard of an 8-GPU job runs ~3 ms) get fewer slices: every slice costs a
-        // launch tail and a host round trip
+        // Streamed delivery.  Short verify stages (a slot-range shard of an 8-GPU job runs ~3 ms) get fewer slices:
+        // every slice costs a launch tail and a host round trip
         const double est_rec = (double)npos * p.n_combos * ((double)(p.slot_hi - p.slot_lo) / (double)(n_slots ? n_slots : 1));
-        const uint32_t n_slices = !sink ? 1u : est_rec > 6e8 ? (uint32_t)BC_SINK_SLICES : est_rec > 1.5e8 ? 3u : 2u;
+        // Equal slices: at cfg 4 the verify + finish kernels (18 ms) take as long as the D2H copy of their 0.95 GB of
+        // records, so every slice's copy hides behind the next slice's kernels and only the last one (1/8) is exposed.
+        // (Round 1 halved the slices - 1/2, 1/4, ... - when verification took four times longer than the copy; with the
+        // round-2 kernels the first half's copy alone outlasted the rest of the search: +8 ms end to end.)
+        const uint32_t n_slices = !sink ? 1u : est_rec > 6e8 ? (uint32_t)BC_SINK_SLICES : est_rec > 1.5e8 ? 4u : 2u;
         JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
-            const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));
-            const uint32_t dgrid = (uint32_t)sm_count * cv_ctas_per_sm(), lo = n_slices == 1 ? 0u : f_lo;
+            const uint32_t f_lo = 65536u * s / n_slices, f_hi = 65536u * (s + 1) / n_slices;
+            const uint32_t dgrid = (uint32_t)sm_count * cv_ctas_per_sm(), lo = f_lo;
             JCK(cudaMemsetAsync(p.count + 4, 0, sizeof(unsigned long long), st));
             switch (p.k) {  // (the dynamic shared-memory opt-in was set once, above)
                 case 0: k_cverify<0><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;

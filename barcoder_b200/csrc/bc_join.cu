@@ -796,7 +796,7 @@ cudaError_t bc_join_search(JoinWorkspace& ws, const SearchParams& p, uint64_t di
         // Streamed delivery: the slices halve (1/2, 1/4, ... and the last one repeated), so most
         // of the result is on its way early, only 1/2^(S-1) of it is still to be copied when the
         // last kernel ends, and there are few launch tails to pay for.
-        const uint32_t n_slices = sink ? BC_SINK_SLICES : 1;
+        const uint32_t n_slices = sink ? 5u : 1u;  // halving slices (<= BC_SINK_SLICES)
         JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
             const uint32_t f_lo = 65536u - (65536u >> s), f_hi = s + 1 == n_slices ? 65536u : 65536u - (65536u >> (s + 1));

@@ -31,7 +31,7 @@ struct JoinWorkspace {
 // Streamed result delivery (bc_set_hit_sink / bc_set_slice_callback): while the verify kernels of
 // later slices run, the hit records of finished slices are copied to the caller's host buffer on
 // a second stream and/or reported to the caller's callback.
-#define BC_SINK_SLICES 5
+#define BC_SINK_SLICES 8
 struct HitSink {
     bc_slice_fn fn = nullptr;          // bc_set_slice_callback: told about every finished part of the buffer
     void* fn_user = nullptr;

@@ -357,10 +357,10 @@ cudaError_t bc_launch_ent_h_pack(const uint2* ent_hl, uint64_t n, uint32_t* ent_
 #ifndef PROBE_MINBLOCKS
 #define PROBE_MINBLOCKS 4
 #endif
-// SINGLE: all combinations fit one batch (every k+1-seed block scheme with k <= 3): the batch loop runs once with
-// c0 = 0, so the combination descriptors are read at fixed constant-bank offsets instead of through an index register
-// (phase B was 44 % of the kernel's instructions at cfg 5).
-template <bool SINGLE>
+// NC > 0: all combinations fit one batch (every k+1-seed block scheme with k <= 3): the batch loop runs once with
+// c0 = 0 and exactly NC unrolled probes, so the combination descriptors are read at fixed constant-bank offsets instead
+// of through an index register (phase B was 44 % of the kernel's instructions at cfg 5: 90.3 -> 80.5 ms).
+template <int NC>  // NC = 1..PROBE_BATCH: exactly NC combinations, one batch; 0 = any number, batches of PROBE_BATCH
 __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(const __grid_constant__ SearchParams p,
                                                               uint32_t n_tiles) {
     // plane words [w0 - 1, w0 + 66): the tile, the word before it (PAM left of the first window)
@@ -425,13 +425,15 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
                 const uint32_t t = have ? l1[r + lane] : 0;
                 const uint32_t ts = t + 32;
                 const uint32_t wh = bc_window(sH, ts) & lm, wl = bc_window(sL, ts) & lm;
-                const uint32_t n_combos = SINGLE ? min(p.n_combos, (uint32_t)PROBE_BATCH) : p.n_combos;
+                constexpr bool SINGLE = NC > 0;
+                constexpr int BATCH = SINGLE ? NC : PROBE_BATCH;
+                const uint32_t n_combos = SINGLE ? (uint32_t)NC : p.n_combos;
 #pragma unroll 1
-                for (uint32_t c0 = 0; c0 < (SINGLE ? 1u : n_combos); c0 += PROBE_BATCH) {
+                for (uint32_t c0 = 0; c0 < (SINGLE ? 1u : n_combos); c0 += BATCH) {
                     // all directory reads of the batch are issued before the first one is consumed
-                    uint32_t eb[PROBE_BATCH], ee[PROBE_BATCH];
+                    uint32_t eb[BATCH], ee[BATCH];
 #pragma unroll
-                    for (int j = 0; j < PROBE_BATCH; j++) {
+                    for (int j = 0; j < BATCH; j++) {
                         eb[j] = ee[j] = 0;
                         if (have && c0 + j < n_combos) {
                             const uint32_t slot = p.combo[c0 + j].dir_off + bc_combo_key(p.combo[c0 + j], wh, wl);
@@ -448,16 +450,16 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
                             }
                         }
                     }
-                    if (have) probes += min((uint32_t)PROBE_BATCH, n_combos - c0);
+                    if (have) probes += min((uint32_t)BATCH, n_combos - c0);
 #pragma unroll
-                    for (int j = 0; j < PROBE_BATCH; j++) {  // ballot compaction: < PROBE_L2_CAP, drained below before it can fill
+                    for (int j = 0; j < BATCH; j++) {  // ballot compaction: < PROBE_L2_CAP, drained below before it can fill
                         const bool ne = eb[j] < ee[j];
                         const uint32_t bal = __ballot_sync(0xffffffffu, ne);
                         if (ne) l2[n2 + __popc(bal & lt_mask)] = make_uint4(t, c0 + j, eb[j], ee[j]);
                         n2 += __popc(bal);
                     }
                     __syncwarp();
-                    if (n2 + 32 * PROBE_BATCH <= PROBE_L2_CAP && ((!SINGLE && c0 + PROBE_BATCH < n_combos) || r + 32 < n1))
+                    if (n2 + 32 * BATCH <= PROBE_L2_CAP && ((!SINGLE && c0 + BATCH < n_combos) || r + 32 < n1))
                         continue;  // room for another batch: keep collecting
                     // ---- phase C: one bucket per lane
                     for (uint32_t b0 = 0; b0 < n2; b0 += 32) {
@@ -552,8 +554,13 @@ cudaError_t bc_launch_scan_probe(const SearchParams& p, uint64_t dir_bytes, int 
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
     }
-    if (p.n_combos <= PROBE_BATCH) k_scan_probe<true><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
-    else k_scan_probe<false><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles);
+    switch (p.n_combos) {
+        case 1: k_scan_probe<1><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles); break;
+        case 2: k_scan_probe<2><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles); break;
+        case 3: k_scan_probe<3><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles); break;
+        case 4: k_scan_probe<4><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles); break;
+        default: k_scan_probe<0><<<grid, PROBE_THREADS, 0, st>>>(p, n_tiles); break;
+    }
     cudaError_t e = cudaGetLastError();
     if (pin) {
         cudaStreamAttrValue attr;
