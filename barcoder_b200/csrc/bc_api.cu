@@ -642,8 +642,25 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     ip.n_entries = (uint32_t)E;
     ip.L = ctx->L;
     ip.lib_has_n = ctx->lib_has_n;
-    ip.slot_lo = (uint32_t)((s.dir_slots - 1) * (uint64_t)ctx->par_slot_rank / (uint64_t)ctx->par_slot_world);
-    ip.slot_hi = (uint32_t)((s.dir_slots - 1) * (uint64_t)(ctx->par_slot_rank + 1) / (uint64_t)ctx->par_slot_world);
+    // slot-range sharding: shard r owns [bound(r), bound(r + 1)).  On the compact join path the bounds are moved down to
+    // a pass-A bin boundary (a multiple of 2^low slots inside their combination; a bin is ~1/15,000 of the directory), so
+    // that "is this record mine" is a test on the bin and the kernels keep their one-plane fast paths in combinations a
+    // shard owns only partly - at 8 shards over 15 combinations that is every shard.
+    auto bound = [&](uint64_t r) -> uint32_t {
+        if (r == 0) return 0u;
+        if (r >= (uint64_t)ctx->par_slot_world) return (uint32_t)(s.dir_slots - 1);
+        uint32_t raw = (uint32_t)((s.dir_slots - 1) * r / (uint64_t)ctx->par_slot_world);
+        if (path == 3) {
+            uint32_t c = 0;
+            while (c + 1 < s.n_combos && s.combo[c + 1].dir_off <= raw) c++;
+            const uint32_t low = 2u * s.combo[c].key_nt - s.combo[c].top_bits;
+            raw = s.combo[c].dir_off + (((raw - s.combo[c].dir_off) >> low) << low);
+        }
+        return raw;
+    };
+    ip.slot_lo = bound((uint64_t)ctx->par_slot_rank);
+    ip.slot_hi = bound((uint64_t)ctx->par_slot_rank + 1);
+    ip.bin_aligned = path == 3 ? 1u : 0u;
     ctx->slot_lo = ip.slot_lo; ctx->slot_hi = ip.slot_hi;
     ip.compact = path == 3 ? 1u : 0u;  // compact join: the index stores the non-key (rem) planes of every entry
     memcpy(ip.combo, ctx->combo, sizeof ip.combo);
@@ -700,6 +717,7 @@ static void fill_params(bc_ctx* ctx, SearchParams* p) {
     p->pos_end = (uint32_t)((uint64_t)ctx->n_pos * (uint64_t)(ctx->par_scan_rank + 1) / (uint64_t)ctx->par_scan_world);
     p->n_contigs = ctx->n_contigs;
     p->slot_lo = ctx->slot_lo; p->slot_hi = ctx->slot_hi;
+    p->bin_aligned = ctx->stats.path == 3 ? 1u : 0u;
     p->own_hash = ctx->par_slot_world > 1 ? 1u : 0u;  // balanced record counts across the slot-range shards
     p->sn = ctx->d_sn;
     p->lib_has_n = ctx->lib_has_n;
@@ -871,6 +889,12 @@ extern "C" int bc_set_hit_sink(bc_ctx* ctx, bc_hit* dst, uint64_t cap) {
     ctx->sink.host = dst;
     ctx->sink.cap = dst ? cap : 0;
     ctx->sink.copied = 0;
+    ctx->sink.is_device = false;
+    if (dst) {  // a device destination (peer merge over NVLink) needs fewer, larger slices than a PCIe copy to the host
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess) ctx->sink.is_device = attr.type == cudaMemoryTypeDevice;
+        else (void)cudaGetLastError();
+    }
     return BC_OK;
 }
 

@@ -35,6 +35,7 @@ struct CBucketParams {
     uint32_t n_words;             // words per plane
     uint32_t L, n_combos, prune, gate_first;
     uint32_t slot_lo, slot_hi;    // slot-range sharding
+    uint32_t bin_aligned;         // slot_lo / slot_hi lie on pass-A bin boundaries: ownership is a test on the bin
     uint32_t P, pam_dir, pam_sets[8];
     // library-side sort (index build): entries instead of genome windows
     const uint32_t* qh;
@@ -180,7 +181,10 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
         const uint32_t n_bins = 1u << cd.top_bits, key_nt = cd.key_nt, rem_nt = cd.rem_nt;
         const uint32_t low = 2u * key_nt - cd.top_bits;
         const bool whole = cd.dir_off >= gp.slot_lo && cd.dir_off + (1u << (2u * key_nt)) <= gp.slot_hi;
-        const bool h_only = cd.top_bits <= key_nt && whole && (LIB || !gp.prune);
+        const bool h_only = cd.top_bits <= key_nt && (whole || gp.bin_aligned) && (LIB || !gp.prune);
+        // bins of this combination the shard owns (exact when the range is bin aligned)
+        const uint32_t bin_lo = (max(gp.slot_lo, cd.dir_off) - cd.dir_off) >> low;
+        const uint32_t bin_hi = (min(gp.slot_hi, cd.dir_off + (1u << (2u * key_nt))) - cd.dir_off) >> low;
         __syncthreads();
         for (uint32_t j = tid; j < n_bins; j += CB_THREADS) s_hist[j] = 0;
         for (uint32_t j = tid; j < CJ_LUT_WORDS; j += CB_THREADS) s_lut[j] = lut[c * CJ_LUT_WORDS + j];
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
                 uint32_t bin;
                 if (h_only) {
                     bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
+                    if (!whole && (bin < bin_lo || bin >= bin_hi)) continue;
                 } else {
                     const uint32_t pl = cj_perm(s_lut, gp.ql[e], false);
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
                 uint32_t bin;
                 if (h_only) {
                     bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
+                    if (!whole && (bin < bin_lo || bin >= bin_hi)) continue;
                 } else {
                     const uint32_t pl = cj_perm(s_lut, __funnelshift_r(l0, l1, o) & lm, false);
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -399,8 +405,10 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
             const uint32_t rm = (1u << rem_nt) - 1u, low_mask = (1u << low) - 1u;
             // the common case - key bits split evenly between the passes, nothing sharded or pruned away - needs
             // neither the assembled key nor the range / prune tests (pass A is issue- and shared-memory bound)
-            const bool even = low == key_nt && (LIB || !gp.prune) && cd.dir_off >= gp.slot_lo &&
-                              cd.dir_off + (1u << (2u * key_nt)) <= gp.slot_hi;
+            const bool whole = cd.dir_off >= gp.slot_lo && cd.dir_off + (1u << (2u * key_nt)) <= gp.slot_hi;
+            const bool even = low == key_nt && (LIB || !gp.prune) && (whole || gp.bin_aligned);
+            const uint32_t bin_lo = (max(gp.slot_lo, cd.dir_off) - cd.dir_off) >> low;
+            const uint32_t bin_hi = (min(gp.slot_hi, cd.dir_off + (1u << (2u * key_nt))) - cd.dir_off) >> low;
             for (uint32_t j = tid; j < n_bins; j += CJ_THREADS) s_hist[j] = 0;
             for (uint32_t j = tid; j < CJ_LUT_WORDS; j += CJ_THREADS) s_lut[j] = lut[c * CJ_LUT_WORDS + j];
             __syncthreads();
@@ -428,6 +436,7 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
                 uint32_t bin;
                 if (even) {  // block-uniform: the bin is the H half of the key, and x = pl << rem_nt | Rh as it stands
                     bin = ph >> rem_nt;
+                    if (!whole && (bin < bin_lo || bin >= bin_hi)) continue;
                     x[i] = (pl << rem_nt) | (ph & rm);
                 } else {
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -1110,27 +1119,29 @@ static __device__ CV_TILE_INLINE uint32_t cv_tile(const SearchParams& p, const C
 // then needs ONE descriptor load per tile instead of walking the two directories with dependent
 // loads, and carries no slot-walk state in registers (the walking version spilled 240 bytes per
 // thread at 64 registers: ncu counted 1.3e9 local-memory load requests, 3x its global loads).
+// (both kernels walk only the slots [s_lo, s_hi) this context owns: under slot-range sharding the rest of the directory
+// is empty here, and walking / scanning all of it was a fixed cost that did not shrink with the number of GPUs)
 __global__ void __launch_bounds__(256) k_ctile_count(const uint32_t* __restrict__ gdir, const uint32_t* __restrict__ dir,
-                                                     uint32_t n_slots, uint32_t* __restrict__ tile_start,
+                                                     uint32_t s_lo, uint32_t s_hi, uint32_t* __restrict__ tile_start,
                                                      unsigned long long* __restrict__ cand_out) {
     unsigned long long cand = 0;
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= n_slots; s += gridDim.x * blockDim.x) {
+    for (uint32_t s = s_lo + blockIdx.x * blockDim.x + threadIdx.x; s <= s_hi; s += gridDim.x * blockDim.x) {
         uint32_t tiles = 0;
-        if (s < n_slots) {
+        if (s < s_hi) {
             const uint32_t n_win = gdir[s + 1] - gdir[s], n_ent = dir[s + 1] - dir[s];
             if (n_win && n_ent) tiles = (n_win + CV_WTILE - 1) / CV_WTILE;
             cand += (unsigned long long)n_win * n_ent;
         }
-        tile_start[s] = tiles;  // scanned in place afterwards; [n_slots] becomes the number of tiles
+        tile_start[s] = tiles;  // scanned in place afterwards; [s_hi] becomes the number of tiles
     }
     if (cand_out && cand) atomicAdd(cand_out, cand);
 }
 
 __global__ void __launch_bounds__(256) k_ctile_fill(const __grid_constant__ CBucketParams gp, const uint32_t* __restrict__ gdir,
-                                                    const uint32_t* __restrict__ dir, uint32_t n_slots,
+                                                    const uint32_t* __restrict__ dir, uint32_t s_lo, uint32_t s_hi,
                                                     const uint32_t* __restrict__ tile_start, uint4* __restrict__ tile_desc,
                                                     uint32_t* __restrict__ tile_slot) {
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+    for (uint32_t s = s_lo + blockIdx.x * blockDim.x + threadIdx.x; s < s_hi; s += gridDim.x * blockDim.x) {
         const uint32_t t0 = tile_start[s], t1 = tile_start[s + 1];
         if (t0 == t1) continue;
         uint32_t c = 0;
@@ -1316,6 +1327,7 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
     gp.L = ip.L;
     gp.n_combos = n_combos;
     gp.slot_lo = ip.slot_lo; gp.slot_hi = ip.slot_hi;
+    gp.bin_aligned = ip.bin_aligned;
     memcpy(gp.combo, ip.combo, sizeof gp.combo);
     uint32_t max_low = 0;
     for (uint32_t c = 0; c < n_combos; c++) {
@@ -1365,8 +1377,11 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
         k_cslotcount<<<(uint32_t)sm_count * 2u, CS_THREADS, max_sub * sizeof(uint32_t), st>>>(gp, tmp, d_bin_start, d_bin_combo, n_bins, d_dir,
                                                                                         ws.d_work);
         JCK(cudaGetLastError());
-        JCK(bc_exclusive_scan(d_dir, dir_slots, d_scan_tmp, st));
-        JCK(cudaMemcpyAsync(d_cursor, d_dir, dir_slots * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        {   // only the owned slot range holds entries (the rest of d_dir stays zero)
+            const uint64_t r_n = (uint64_t)(ip.slot_hi - ip.slot_lo) + 1;
+            JCK(bc_exclusive_scan(d_dir + ip.slot_lo, r_n, d_scan_tmp, st));
+            JCK(cudaMemcpyAsync(d_cursor + ip.slot_lo, d_dir + ip.slot_lo, r_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        }
         n_rec_ptr = d_bin_start + n_bins;
     }
     k_cchunk_bins<<<(uint32_t)((max_chunks + 255) / 256), 256, 0, st>>>(d_bin_start, n_bins, n_rec_ptr, d_chunk_bin);
@@ -1509,6 +1524,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
     gp.prune = p.dir_entries < (dir_slots - 1) * 2 ? 1u : 0u;
     gp.gate_first = p.gate_first;
     gp.slot_lo = p.slot_lo; gp.slot_hi = p.slot_hi;
+    gp.bin_aligned = p.bin_aligned;
     gp.P = p.P; gp.pam_dir = p.pam_dir;
     for (int i = 0; i < 8; i++) gp.pam_sets[i] = p.pam_sets[i];
 
@@ -1536,11 +1552,15 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         uint32_t gx = (npos + 255) / 256;
         const uint32_t maxb = (uint32_t)sm_count * 8u;
         if (gx > maxb) gx = maxb;
-        JCK(cudaMemsetAsync(ws.d_gdir, 0, dir_slots * 4, st));
+        // the slots this context owns (everything unless the directory is sharded): the directory-sized passes below
+        // (clear, scan, cursor copy, tile list) only touch this range (+ its end sentinel)
+        const bool red_count = cj_red_count();
+        const uint32_t r_lo = red_count ? 0u : p.slot_lo, r_hi = red_count ? n_slots : p.slot_hi;
+        const uint64_t r_n = (uint64_t)(r_hi - r_lo) + 1;
+        JCK(cudaMemsetAsync(ws.d_gdir + r_lo, 0, r_n * 4, st));
         JCK(cudaEventRecord(ws.ev_c, st));
         uint32_t bx = (npos + CJ_CHUNK - 1) / CJ_CHUNK;
         if (bx > (uint32_t)sm_count * 2u) bx = (uint32_t)sm_count * 2u;
-        const bool red_count = cj_red_count();
         if (red_count) {  // round-1 form: one global RED per (window, combination), kept for A/B runs (BC_WIN_COUNT=red)
             k_ccount<false><<<dim3(gx, p.n_combos), 256, 0, st>>>(gp, ws.d_lut, ws.d_gdir);
             JCK(cudaGetLastError());
@@ -1569,8 +1589,8 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             k_cslotcount<<<(uint32_t)sm_count * 2u, CS_THREADS, max_sub * sizeof(uint32_t), st>>>(gp, one_pass ? d_win : d_tmp, d_bin_start, d_bin_combo, n_bins,
                                                                                             ws.d_gdir, ws.d_work);
             JCK(cudaGetLastError());
-            JCK(bc_exclusive_scan(ws.d_gdir, dir_slots, ws.d_scan_tmp, st));
-            JCK(cudaMemcpyAsync(ws.d_gcursor, ws.d_gdir, dir_slots * 4, cudaMemcpyDeviceToDevice, st));
+            JCK(bc_exclusive_scan(ws.d_gdir + r_lo, r_n, ws.d_scan_tmp, st));
+            JCK(cudaMemcpyAsync(ws.d_gcursor + r_lo, ws.d_gdir + r_lo, r_n * 4, cudaMemcpyDeviceToDevice, st));
             bc_launch_counter += 1;
         }
         JCK(cudaEventRecord(ws.ev_k[5], st));  // end of the slot count (start of pass B)
@@ -1585,10 +1605,10 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         JCK(cudaEventRecord(ws.ev_k[3], st));      // end of pass B
         {   // tile list of this pass
             const uint32_t tg = (uint32_t)sm_count * 8u;
-            k_ctile_count<<<tg, 256, 0, st>>>(ws.d_gdir, p.dir, n_slots, ws.d_tile_start, p.count_candidates ? p.count + 1 : nullptr);
+            k_ctile_count<<<tg, 256, 0, st>>>(ws.d_gdir, p.dir, r_lo, r_hi, ws.d_tile_start, p.count_candidates ? p.count + 1 : nullptr);
             JCK(cudaGetLastError());
-            JCK(bc_exclusive_scan(ws.d_tile_start, dir_slots, ws.d_scan_tmp, st));
-            k_ctile_fill<<<tg, 256, 0, st>>>(gp, ws.d_gdir, p.dir, n_slots, ws.d_tile_start, ws.d_tile_desc, ws.d_tile_slot);
+            JCK(bc_exclusive_scan(ws.d_tile_start + r_lo, r_n, ws.d_scan_tmp, st));
+            k_ctile_fill<<<tg, 256, 0, st>>>(gp, ws.d_gdir, p.dir, r_lo, r_hi, ws.d_tile_start, ws.d_tile_desc, ws.d_tile_slot);
             JCK(cudaGetLastError());
             bc_launch_counter += 2;
         }
@@ -1600,17 +1620,20 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
         // records, so every slice's copy hides behind the next slice's kernels and only the last one (1/8) is exposed.
         // (Round 1 halved the slices - 1/2, 1/4, ... - when verification took four times longer than the copy; with the
         // round-2 kernels the first half's copy alone outlasted the rest of the search: +8 ms end to end.)
-        const uint32_t n_slices = !sink ? 1u : est_rec > 6e8 ? (uint32_t)BC_SINK_SLICES : est_rec > 1.5e8 ? 4u : 2u;
+        // A device destination (the peer merge: NVLink, ~10x the PCIe rate) gets fewer slices.
+        const uint32_t n_slices = !sink ? 1u
+                                  : (sink->host && sink->is_device && !sink->fn) ? (est_rec > 6e8 ? 4u : 2u)
+                                  : est_rec > 6e8 ? (uint32_t)BC_SINK_SLICES : est_rec > 1e8 ? 4u : 2u;
         JCK(cudaMemsetAsync(ws.d_work, 0, BC_SINK_SLICES * sizeof(uint32_t), st));
         for (uint32_t s = 0; s < n_slices; s++) {
             const uint32_t f_lo = 65536u * s / n_slices, f_hi = 65536u * (s + 1) / n_slices;
             const uint32_t dgrid = (uint32_t)sm_count * cv_ctas_per_sm(), lo = f_lo;
             JCK(cudaMemsetAsync(p.count + 4, 0, sizeof(unsigned long long), st));
             switch (p.k) {  // (the dynamic shared-memory opt-in was set once, above)
-                case 0: k_cverify<0><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
-                case 1: k_cverify<1><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
-                case 2: k_cverify<2><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
-                default: k_cverify<3><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + n_slots, ws.d_work, s, lo, f_hi); break;
+                case 0: k_cverify<0><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + r_hi, ws.d_work, s, lo, f_hi); break;
+                case 1: k_cverify<1><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + r_hi, ws.d_work, s, lo, f_hi); break;
+                case 2: k_cverify<2><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + r_hi, ws.d_work, s, lo, f_hi); break;
+                default: k_cverify<3><<<dgrid, CV_THREADS, CV_WARPS * CV_WARP_SMEM, st>>>(pv, d_win, ws.d_tile_desc, ws.d_tile_slot, ws.d_tile_start + r_hi, ws.d_work, s, lo, f_hi); break;
             }
             JCK(cudaGetLastError());
             if (s + 1 == n_slices) JCK(cudaEventRecord(ws.ev_k[4], st));  // end of the (last) first-level kernel

@@ -51,6 +51,7 @@ struct SearchParams {
     uint32_t n_words;           // words per plane (whole tiles + padding, bc_api.cu)
     uint32_t pos_begin, pos_end;  // window start positions this context scans (genome-range sharding)
     uint32_t slot_lo, slot_hi;    // directory slots this context owns (slot-range sharding; everything = [0, all slots))
+    uint32_t bin_aligned;         // compact join: slot_lo / slot_hi lie on pass-A bin boundaries (bc_build_index)
     uint32_t own_hash;            // ownership order: 0 = combination order, 1 = cyclic from a hash of (position, entry) (bc_owns)
     uint32_t n_contigs;
     // library

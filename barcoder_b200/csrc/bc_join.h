@@ -37,6 +37,7 @@ struct HitSink {
     void* fn_user = nullptr;
     uint64_t reported = 0;             // records already reported to fn in this search
     bc_hit* host = nullptr;            // caller's destination: pinned host memory, or device memory of this / a peer GPU
+    bool is_device = false;            // the destination is device memory (this or a peer GPU: NVLink), not host memory (PCIe)
     uint64_t cap = 0;                  // records the destination can hold
     uint64_t copied = 0;               // records already queued for copy in this search
     cudaStream_t stream = nullptr;     // copy stream

@@ -10,6 +10,7 @@ struct IndexParams {
     uint32_t L;
     uint32_t lib_has_n;
     uint32_t slot_lo, slot_hi;  // slot-range sharding: only entries whose slot is in [slot_lo, slot_hi) are indexed
+    uint32_t bin_aligned;       // compact join: slot_lo / slot_hi lie on pass-A bin boundaries
     uint32_t compact;    // 1: ent_hl holds the non-key (rem) planes {Rh, Rl} instead of the full query planes
     ComboDesc combo[BC_MAX_COMBOS];
 };
