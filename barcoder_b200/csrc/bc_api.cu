@@ -18,6 +18,8 @@ struct bc_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev_i0 = nullptr, ev_i1 = nullptr;  // bc_build_index: enqueued without a host synchronisation, timed lazily
+    bool index_timing_pending = false;
     std::string err;
 
     // genome
@@ -134,6 +136,7 @@ extern "C" int bc_create(bc_ctx** out, int device) {
     cudaDeviceProp prop;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
         cudaStreamCreate(&ctx->stream) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_i0) != cudaSuccess || cudaEventCreate(&ctx->ev_i1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev2) != cudaSuccess ||
         cudaEventCreate(&ctx->ev3) != cudaSuccess ||
         cudaMalloc(&ctx->d_count, 8 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -161,6 +164,8 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
     dfree(ctx->d_sort_scratch); dfree(ctx->d_sort_hist); dfree(ctx->d_sort_tmp); dfree(ctx->d_sort_orand);
     bc_join_free(ctx->join);
     bc_guides_free(ctx->guides);
+    if (ctx->ev_i0) cudaEventDestroy(ctx->ev_i0);
+    if (ctx->ev_i1) cudaEventDestroy(ctx->ev_i1);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -176,8 +181,20 @@ extern "C" void bc_destroy(bc_ctx* ctx) {
 extern "C" const char* bc_last_error(bc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 // ---------------------------------------------------------------------------------------- genome
+// bc_build_index returns as soon as its kernels are enqueued (the search that follows is enqueued behind them on the
+// same stream, so the host never idles between the two: at 8 GPUs a step is ~7 ms and every host round trip shows).
+// Its device time is read here, once something has synchronised with the stream anyway.
+static int resolve_index_timing(bc_ctx* ctx) {
+    if (!ctx->index_timing_pending) return BC_OK;
+    ctx->index_timing_pending = false;
+    CK(cudaEventSynchronize(ctx->ev_i1));
+    CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev_i0, ctx->ev_i1));
+    return BC_OK;
+}
+
 static int set_genome_common(bc_ctx* ctx, const uint8_t* d_ascii, const uint64_t* contig_offsets,
                              uint32_t n_contigs, cudaStream_t st) {
+    { int rc_ = resolve_index_timing(ctx); if (rc_ != BC_OK) return rc_; }  // index kernels may still read the old planes
     uint64_t G = contig_offsets[n_contigs];
     for (uint32_t c = 0; c < n_contigs; c++)
         if (contig_offsets[c + 1] < contig_offsets[c]) return fail(ctx, BC_EINVAL, "contig_offsets must be non-decreasing");
@@ -251,6 +268,7 @@ extern "C" int bc_set_genome(bc_ctx* ctx, const uint8_t* ascii, const uint64_t* 
 
 // --------------------------------------------------------------------------------------- library
 static int set_library_common(bc_ctx* ctx, const uint8_t* d_ascii, uint32_t n, uint32_t L, cudaStream_t st) {
+    { int rc_ = resolve_index_timing(ctx); if (rc_ != BC_OK) return rc_; }  // index kernels may still read the old library
     if (L < 1 || L > 32) return fail(ctx, BC_ELIMIT, "spacer length must be 1..32");
     if (n >= (1u << 31)) return fail(ctx, BC_ELIMIT, "too many spacers");
     ctx->have_library = false;
@@ -587,6 +605,7 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     if (!ctx->have_genome) return fail(ctx, BC_EINVAL, "bc_build_index: no genome loaded");
     if (k < 0 || k > 3) return fail(ctx, BC_ELIMIT, "k must be 0..3 (bowtie -v limit)");
     CK(cudaSetDevice(ctx->device));
+    { int rc_ = resolve_index_timing(ctx); if (rc_ != BC_OK) return rc_; }
     ctx->have_index = false;
     ctx->index_k = k;
     ctx->stats.k = (uint32_t)k;
@@ -665,7 +684,7 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
     ip.compact = path == 3 ? 1u : 0u;  // compact join: the index stores the non-key (rem) planes of every entry
     memcpy(ip.combo, ctx->combo, sizeof ip.combo);
     const uint32_t launches0 = bc_launch_counter;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_i0, ctx->stream));
     if (!ctx->d_coarse_cursor) CK(cudaMalloc(&ctx->d_coarse_cursor, ((size_t)BC_MAX_COMBOS << BC_COARSE_BITS) * 4 + 4));
     if (ip.compact && ctx->par_index_sort != 1)  // the two radix passes of the compact window sort, applied to the entries
         CK(bc_cindex_build(ctx->join, ip, s.n_combos, s.n_bins, ctx->d_dir, s.dir_slots, ctx->d_cursor, ctx->d_scan_tmp,
@@ -698,9 +717,8 @@ extern "C" int bc_build_index(bc_ctx* ctx, int k) {
         CK(bc_launch_ent_h_pack(ctx->d_ent_hl, ent_needed, ctx->d_ent_h, ctx->sm_count, ctx->stream));
         ctx->have_ent_h = true;
     }
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaEventElapsedTime(&ctx->stats.ms_build_index, ctx->ev0, ctx->ev1));
+    CK(cudaEventRecord(ctx->ev_i1, ctx->stream));
+    ctx->index_timing_pending = true;  // no host synchronisation here: see resolve_index_timing
     ctx->stats.index_launches = bc_launch_counter - launches0;
     ctx->have_index = true;
     return BC_OK;
@@ -837,6 +855,7 @@ extern "C" int bc_search(bc_ctx* ctx, int k, uint64_t* n_hits_out) {
         if (attempt == 2) return fail(ctx, BC_ECUDA, "hit buffer kept overflowing");
     }
     ctx->stats.hits = ctx->n_hits;
+    { int rc_ = resolve_index_timing(ctx); if (rc_ != BC_OK) return rc_; }  // (already complete: the stream was synchronised)
     ctx->stats.ms_search = ms_total;
     ctx->stats.ms_scan_kernel = ms_scan;
     ctx->stats.ms_genome_bucket = ms_bucket;
@@ -998,6 +1017,11 @@ extern "C" int bc_hits_device(bc_ctx* ctx, const bc_hit** d_hits, uint64_t* n_hi
 
 extern "C" int bc_get_stats(bc_ctx* ctx, bc_stats* out) {
     if (!ctx || !out) return BC_EINVAL;
+    if (ctx->index_timing_pending) {
+        cudaSetDevice(ctx->device);
+        int rc_ = resolve_index_timing(ctx);
+        if (rc_ != BC_OK) return rc_;
+    }
     *out = ctx->stats;
     return BC_OK;
 }

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
                 uint32_t bin;
                 if (h_only) {
                     bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
-                    if (!whole && (bin < bin_lo || bin >= bin_hi)) continue;
+                    if (bin - bin_lo >= bin_hi - bin_lo) continue;  // (all bins when the shard owns the whole combination)
                 } else {
                     const uint32_t pl = cj_perm(s_lut, gp.ql[e], false);
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
                 uint32_t bin;
                 if (h_only) {
                     bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
-                    if (!whole && (bin < bin_lo || bin >= bin_hi)) continue;
+                    if (bin - bin_lo >= bin_hi - bin_lo) continue;  // (all bins when the shard owns the whole combination)
                 } else {
                     const uint32_t pl = cj_perm(s_lut, __funnelshift_r(l0, l1, o) & lm, false);
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(CJ_THREADS, 2) k_cbin(const __grid_constant__ 
                 uint32_t bin;
                 if (even) {  // block-uniform: the bin is the H half of the key, and x = pl << rem_nt | Rh as it stands
                     bin = ph >> rem_nt;
-                    if (!whole && (bin < bin_lo || bin >= bin_hi)) continue;
+                    if (bin - bin_lo >= bin_hi - bin_lo) continue;  // (all bins when the shard owns the whole combination)
                     x[i] = (pl << rem_nt) | (ph & rm);
                 } else {
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -807,7 +807,15 @@ __device__ __forceinline__ uint32_t cv_combo_of_slot(const SearchParams& p, uint
 // coalesced store of the surviving records.
 // ypos: the queue entries carry the dev position itself (k_cfinish: the verify kernel fetched it when it flushed
 // the item, while the record's sector was still in L2) instead of the record index.
-static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* q, uint32_t n,
+// The second level is inlined into k_cfinish (its only caller now that the verify kernel has no slow path): out of line
+// the SearchParams reference is a generic pointer, and the loops over the combinations (cv_combo_of_slot, bc_owns) and the
+// PAM annotation read every field with a dependent load instead of from the constant bank (ncu: those loops ran 25 million
+// times per launch; k_cfinish 6.35 -> 4.92 ms).
+#ifndef CV_FIN_INLINE
+#define CV_FIN_INLINE __forceinline__
+#define CV_FIN_MAKE_HIT bc_make_hit_inl
+#endif
+static __device__ CV_FIN_INLINE void cv_resolve(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* q, uint32_t n,
                                                bool ypos) {
 #ifdef CV_DEBUG_NO_RESOLVE  // timing experiment only: candidates are found but not turned into records
     if (p.cap != 1) return;
@@ -823,7 +831,7 @@ static __device__ __noinline__ void cv_resolve(const SearchParams& p, const uint
         // DRAM sectors) are fetched - nearly half of the candidates are not owned
         if (p.lib_has_n || bc_owns(p, c, m)) {
             const uint32_t pos = ypos ? qe.x : __ldg(&gwin[qe.x].x), e = __ldg(p.ent_id + qe.z);
-            ok = bc_make_hit(p, c, pos, e, m, &rec);
+            ok = CV_FIN_MAKE_HIT(p, c, pos, e, m, &rec);
         }
     }
     const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
@@ -869,7 +877,7 @@ __device__ __forceinline__ void cv_drain(const SearchParams& p, const uint2* __r
 // position.  (The first version queued whole 4-window groups: at 9-10 nt keys 70-90 % of the groups
 // contain a passing pair somewhere in the warp, and re-reading their records cost 13 GB of random
 // sectors - ncu: 31.7 GB read for 11.5 GB algorithmic.)
-static __device__ __noinline__ void cv_resolve_groups(const SearchParams& p, const uint2* __restrict__ gwin,
+static __device__ CV_FIN_INLINE void cv_resolve_groups(const SearchParams& p, const uint2* __restrict__ gwin,
                                                       const uint4* gq, uint32_t n, uint4* q, uint32_t* qn, bool ypos) {
     const uint32_t lane = threadIdx.x & 31u;
     const int k = (int)p.k;

@@ -228,8 +228,11 @@ __device__ __forceinline__ bool bc_owns(const SearchParams& p, uint32_t c, uint3
 //   pos   dev position of the window
 //   e     library entry (2*spacer + strand)
 //   m     mismatch mask in QUERY orientation (bit j = query/window base j differs)
-static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t c, uint32_t pos, uint32_t e,
-                                                uint32_t m, uint4* out) {
+// (bc_make_hit_inl is the body; bc_make_hit, below, is the out-of-line copy the scan kernels call from their rare paths.
+// Out of line the SearchParams reference is a generic pointer and every field is a load; k_cfinish, whose whole job
+// is this function, inlines the body so that the fields come from the constant bank.)
+static __device__ __forceinline__ bool bc_make_hit_inl(const SearchParams& p, uint32_t c, uint32_t pos, uint32_t e,
+                                                       uint32_t m, uint4* out) {
     const uint32_t L = p.L;
     const uint32_t strand = e & 1u, sid = e >> 1;
     if (p.lib_has_n) {  // non-ACGT spacer characters mismatch everything (oracle.c rule 6)
@@ -274,6 +277,11 @@ static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t 
     }
     *out = make_uint4(sid + p.spacer_id_base, pos - lo, strand ? bc_rev_bits(m, L) : m, meta);
     return true;
+}
+
+static __device__ __noinline__ bool bc_make_hit(const SearchParams& p, uint32_t c, uint32_t pos, uint32_t e,
+                                                uint32_t m, uint4* out) {
+    return bc_make_hit_inl(p, c, pos, e, m, out);
 }
 
 // Hit records are staged per CTA in shared memory and flushed with ONE global atomic per flush:

@@ -403,10 +403,13 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
         }
         __syncthreads();
 
-        // ---- phase A: compact the windows that can still produce a hit
-        uint32_t n1 = 0;
+        // ---- phase A: compact the windows that can still produce a hit.  Without the PAM gate nearly every window
+        // survives (only those touching a non-ACGT base or a contig end do not), so the compaction is skipped and the
+        // validity test moves into phase B ("direct": window r + lane of the warp's 256)
+        const bool direct = !p.gate_first;
+        uint32_t n1 = direct ? PROBE_TILE_POS / PROBE_WARPS : 0u;
 #pragma unroll 1
-        for (uint32_t i = 0; i < PROBE_STEPS; i++) {
+        for (uint32_t i = 0; i < (direct ? 0u : (uint32_t)PROBE_STEPS); i++) {
             const uint32_t t = warp * (PROBE_TILE_POS / PROBE_WARPS) + i * 32 + lane;
             const uint32_t pos = tile_pos + t;
             const uint32_t ts = t + 32;  // position inside the staged words
@@ -421,8 +424,16 @@ __global__ void __launch_bounds__(PROBE_THREADS, PROBE_MINBLOCKS) k_scan_probe(c
         // ---- phase B (+ C whenever the bucket list fills up)
         for (uint32_t r = 0; r < n1 || n2; r += 32) {  // warp-uniform
             if (r < n1) {
-                const bool have = r + lane < n1;
-                const uint32_t t = have ? l1[r + lane] : 0;
+                uint32_t t;
+                bool have;
+                if (direct) {
+                    t = warp * (PROBE_TILE_POS / PROBE_WARPS) + r + lane;
+                    const uint32_t pos = tile_pos + t;
+                    have = pos >= p.pos_begin && pos < p.pos_end && !(bc_window(sB, t + 32) & lm);
+                } else {
+                    have = r + lane < n1;
+                    t = have ? l1[r + lane] : 0;
+                }
                 const uint32_t ts = t + 32;
                 const uint32_t wh = bc_window(sH, ts) & lm, wl = bc_window(sL, ts) & lm;
                 constexpr bool SINGLE = NC > 0;
