@@ -777,7 +777,8 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
 #define CV_WARPS (CV_THREADS / 32)
 #define CV_ITEMS 4          // window records per lane per warp-tile (at most)
 #define CV_WQ 128           // per-warp candidate queue (entries)
-#define CV_GQ 160           // per-warp queue of {window, group} items awaiting re-examination (31 + 4 * 32 + 1)
+#define CV_QROWS 8          // per-warp item queue: CV_QROWS rows of 32 lane-private slots ({window, group} items for k_cfinish)
+#define CV_GQ (32 * CV_QROWS)
 #define CV_STAGE 64         // library entries per shared-memory stage (x2 buffers per warp)
 #define CV_GROUP 8          // entries per group (one ballot per group)
 #ifndef CV_CHUNK_TILES
@@ -904,32 +905,50 @@ static __device__ CV_FIN_INLINE void cv_resolve_groups(const SearchParams& p, co
     cv_drain(p, gwin, q, qn, lane, ypos);
 }
 
-// Hand n <= 32 queue items over to k_cfinish through the global item queue (one atomic, one coalesced
-// 16-byte store per lane).  Re-examining them inside the verify kernel cost it 45 % of its time
+// Hand the queued items of the warp over to k_cfinish through the global item queue.  Re-examining them inside the verify kernel cost it 45 % of its time
 // (timing experiment, cfg 4 at 9-nt keys: first level alone 22.6 ms, + second level 32.9 ms,
 // + hit resolution 39.1 ms): the dependent loads of the slow path stall warps that should be
 // feeding the POPC pipe.  The verify kernel therefore contains no slow path at all - not even as a
 // fallback: a call inside its hot loop made ptxas keep loop state in local memory (324 bytes of
 // spills; with 214 KB of the SM's 256 KB carved out as shared memory those reloads miss L1: ncu put
 // 25 % of the stall samples on the instructions behind them).  If the queue is full the batch is
-// dropped, the demand keeps counting, k_cfinish records it in count[5] and bc_search repeats the
-// search with a queue of the demanded size (like a hit-buffer overflow).
-__device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* gq, uint32_t n) {
+// dropped, the demand keeps counting, k_cfinish records it in count[5] (and processes nothing) and
+// bc_search repeats the search with a queue of the demanded size (like a hit-buffer overflow).
+//
+// The per-warp queue is lane-private (round 2): lane l appends to column l (gq[row * 32 + l], its fill in a register),
+// so queueing an item is four predicated instructions and needs no vote.  The ballot-compacted queue before it cost a
+// VOTE + compare + branch per window and group plus ~12 instructions whenever any lane had an item - 60 % of the time at
+// 10-nt keys: a quarter of all instructions of a kernel that ncu shows issue bound (issue active 78 %, no memory stalls
+// left).  The queue is flushed when some lane could overflow with the next group: a warp prefix sum of the fills, ONE
+// atomic for the warp, every lane copies its own items.
+__device__ __forceinline__ void cv_flush_items(const SearchParams& p, const uint2* __restrict__ gwin, const uint4* gq, uint32_t cnt) {
     const uint32_t lane = threadIdx.x & 31u;
-    unsigned long long base = 0;
     __syncwarp();
-    // always a whole batch of 32 (missing lanes carry a null item), so the accepted batches tile the
-    // queue without holes and k_cfinish can trust every item below min(counter, capacity)
-    if (lane == 0) base = atomicAdd(p.count + 4, 32ull);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // warp-uniform
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(p.count + 4, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + 32ull <= p.item_cap) {
-        uint4 item = lane < n ? gq[lane] : make_uint4(0u, 0u, 0u, 0xffffffffu);
+    if (base + total <= p.item_cap) {  // else: dropped, the demand keeps counting (see above)
+        const unsigned long long dst = base + incl - cnt;
+        const uint32_t rows = __reduce_max_sync(0xffffffffu, cnt);
+        for (uint32_t r = 0; r < rows; r++) {
+            if (r < cnt) {
+                uint4 item = gq[r * 32 + lane];
 #if CV_ITEM_POS
-        // the item leaves with the window's dev position instead of its record index: the record's sector was read a
-        // moment ago (L2 hit), in k_cfinish the same fetch is a random DRAM sector per candidate
-        if (lane < n) item.y = __ldg(&gwin[item.y].x);
+                // the item leaves with the window's dev position instead of its record index: the record's sector was read
+                // a moment ago (L2 hit), in k_cfinish the same fetch is a random DRAM sector per candidate
+                item.y = __ldg(&gwin[item.y].x);
 #endif
-        p.items[base + lane] = item;
+                p.items[dst + r] = item;
+            }
+        }
     }
     __syncwarp();
 }
@@ -1041,9 +1060,8 @@ __device__ __forceinline__ void cv_group(const uint4* sg, const uint32_t (&wh)[I
 // sc = running stage counter (selects the bucket stage buffer); returns the queue fill.
 template <int K, int ITEMS>
 static __device__ CV_TILE_INLINE uint32_t cv_tile(const SearchParams& p, const CvPipe& pp, uint32_t t, uint32_t t_end, const uint4 d,
-                                            uint32_t slot, uint32_t& sc, uint4* gq, uint32_t gn) {
+                                            uint32_t slot, uint32_t& sc, uint4* gq, uint32_t cnt) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t ls = d.z, le = d.w, first = d.x;
     const uint32_t n_ent = le - ls;
     const uint32_t n_stage = (n_ent + CV_STAGE - 1) / CV_STAGE;
@@ -1084,40 +1102,34 @@ static __device__ CV_TILE_INLINE uint32_t cv_tile(const SearchParams& p, const C
         const uint32_t n_full = n_here / CV_GROUP, tail_units = ((n_here % CV_GROUP) + 1u) / 2u;
         const uint32_t ng = n_full + (tail_units ? 1u : 0u);
         const uint32_t ebase = ls + c * CV_STAGE;
-        uint32_t g = 0;
-        for (;;) {
-            for (; g < ng && gn < 32; g++) {
-                bool pass_[ITEMS];
-                const uint4* sg = sb + g * (CV_GROUP / 2);
-                if (g < n_full || tail_units == CV_GROUP / 2) cv_group<K, ITEMS, CV_GROUP / 2>(sg, wh, wl, pass_);
-                else if (tail_units == 1) cv_group<K, ITEMS, 1>(sg, wh, wl, pass_);
-                else if (tail_units == 2) cv_group<K, ITEMS, 2>(sg, wh, wl, pass_);
-                else cv_group<K, ITEMS, 3>(sg, wh, wl, pass_);
+        for (uint32_t g = 0; g < ng; g++) {
+            bool pass_[ITEMS];
+            const uint4* sg = sb + g * (CV_GROUP / 2);
+            if (g < n_full || tail_units == CV_GROUP / 2) cv_group<K, ITEMS, CV_GROUP / 2>(sg, wh, wl, pass_);
+            else if (tail_units == 1) cv_group<K, ITEMS, 1>(sg, wh, wl, pass_);
+            else if (tail_units == 2) cv_group<K, ITEMS, 2>(sg, wh, wl, pass_);
+            else cv_group<K, ITEMS, 3>(sg, wh, wl, pass_);
 #pragma unroll
-                for (int it = 0; it < ITEMS; it++) {
+            for (int it = 0; it < ITEMS; it++) {
 #ifdef CV_DEBUG_NO_SECOND  // timing experiment only: first level alone (no hits are produced)
-                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_[it]) & (first == 0xffffffffu ? 1u : 0u);
-#else
-                    const uint32_t hit_ = __ballot_sync(0xffffffffu, pass_[it]);
+                if (first != 0xffffffffu) pass_[it] = false;
 #endif
-                    if (hit_) {  // warp-uniform
-                        if (pass_[it])
-                            gq[gn + __popc(hit_ & lt_mask)] =
-                                make_uint4(wh[it] | (wl[it] << 16), first + it * 32 + lane, ebase + g * CV_GROUP, slot);
-                        gn += __popc(hit_);
-                    }
+                if (pass_[it]) {  // lane-private column of the queue: no vote, no compaction
+                    gq[cnt * 32 + lane] = make_uint4(wh[it] | (wl[it] << 16), first + it * 32 + lane, ebase + g * CV_GROUP, slot);
+                    cnt++;
                 }
             }
-            if (gn < 32) break;
-            do {  // warp-uniform; at most 31 + 32 * ITEMS items are queued here
-                gn -= 32;
-                cv_flush_items(p, pp.gwin, gq + gn, 32);
-            } while (gn >= 32);
+            // some lane could overflow its column with the next group - of this tile or of the next one, which may hold more
+            // windows per lane: hence CV_ITEMS, not ITEMS
+            if (__any_sync(0xffffffffu, cnt > CV_QROWS - CV_ITEMS)) {
+                cv_flush_items(p, pp.gwin, gq, cnt);
+                cnt = 0;
+            }
         }
         __syncwarp();  // every lane is done with this buffer before a later stage lands in it
     }
     sc += n_stage;
-    return gn;
+    return cnt;
 }
 
 // ------------------------------------------------------------------------------------ tile list
@@ -1183,7 +1195,7 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
     uint2* s_ent = reinterpret_cast<uint2*>(s_desc + 2);                // [2 * CV_STAGE]
     uint32_t* s_win = reinterpret_cast<uint32_t*>(s_ent + 2 * CV_STAGE);  // [2 * CV_WTILE]
     uint32_t* s_dslot = s_win + 2 * CV_WTILE;                           // [2] (+2 pad)
-    uint32_t gn = 0;  // queued items of this warp (warp-uniform; survives across tiles)
+    uint32_t gn = 0;  // items this lane has queued in its column of gq (survives across tiles)
     CvPipe pp;
     pp.ent = s_ent; pp.win = s_win; pp.desc = s_desc; pp.dslot = s_dslot;
     pp.gwin = gwin; pp.ent_hl = p.ent_hl; pp.tile_desc = tile_desc; pp.tile_slot = tile_slot;
@@ -1223,11 +1235,7 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
             }
         }
     }
-    while (gn) {  // up to CV_GQ - 1 items are still queued
-        const uint32_t take = min(gn, 32u);
-        gn -= take;
-        cv_flush_items(p, gwin, gq + gn, take);
-    }
+    cv_flush_items(p, gwin, gq, gn);  // whatever is still queued
 }
 
 // Second level + hit resolution as a kernel of their own: every warp takes batches of 32 items of
@@ -1244,7 +1252,8 @@ __global__ void __launch_bounds__(CV_THREADS, 4) k_cfinish(const __grid_constant
     __syncwarp();
     const unsigned long long queued = p.count[4];
     if (queued > p.item_cap && blockIdx.x == 0 && threadIdx.x == 0) atomicMax(p.count + 5, queued);  // batches were dropped: bc_search retries
-    const unsigned long long n_items = queued < p.item_cap ? queued : p.item_cap;  // whole batches of 32; item_cap is a multiple of 32
+    // after an overflow the queue has holes (a dropped reservation is never written) and the attempt is repeated anyway
+    const unsigned long long n_items = queued <= p.item_cap ? queued : 0ull;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * CV_WARPS;
     for (unsigned long long b0 = ((unsigned long long)blockIdx.x * CV_WARPS + warp) * 32ull; b0 < n_items; b0 += n_warps * 32ull) {
         const uint32_t n = (uint32_t)min(32ull, n_items - b0);
