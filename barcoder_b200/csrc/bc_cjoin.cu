@@ -161,7 +161,7 @@ __global__ void k_cbin_init(const __grid_constant__ CBucketParams gp, const uint
 //                 a bin (<= 65536 records) is a shared-memory histogram over the bin's sub-slots, flushed
 //                 with one RED per non-empty (piece, sub-slot): ~2.5e7 REDs instead of 1.5e9.
 #define CB_THREADS 512
-template <bool LIB>
+template <bool LIB, bool PART>  // PART: the directory is sharded (slot range != everything): bins are range-checked
 __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_constant__ CBucketParams gp,
                                                              const uint32_t* __restrict__ lut,
                                                              uint32_t* __restrict__ bin_count) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
                 uint32_t bin;
                 if (h_only) {
                     bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
-                    if (bin - bin_lo >= bin_hi - bin_lo) continue;  // (all bins when the shard owns the whole combination)
+                    if (PART && bin - bin_lo >= bin_hi - bin_lo) continue;
                 } else {
                     const uint32_t pl = cj_perm(s_lut, gp.ql[e], false);
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) k_cbincount(const __grid_consta
                 uint32_t bin;
                 if (h_only) {
                     bin = (ph >> rem_nt) >> (key_nt - cd.top_bits);
-                    if (bin - bin_lo >= bin_hi - bin_lo) continue;  // (all bins when the shard owns the whole combination)
+                    if (PART && bin - bin_lo >= bin_hi - bin_lo) continue;
                 } else {
                     const uint32_t pl = cj_perm(s_lut, __funnelshift_r(l0, l1, o) & lm, false);
                     const uint32_t key = ((ph >> rem_nt) << key_nt) | (pl >> rem_nt);
@@ -1383,7 +1383,8 @@ cudaError_t bc_cindex_build(JoinWorkspace& ws, const IndexParams& ip, uint32_t n
         n_rec_ptr = d_dir + n_slots;
     } else {               // bin totals and the slot histogram from shared-memory histograms (see k_cbincount)
         JCK(cudaMemsetAsync(d_bin_cursor, 0, (n_bins + 1) * sizeof(uint32_t), st));
-        k_cbincount<true><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
+        if (ip.slot_lo == 0 && ip.slot_hi == n_slots) k_cbincount<true, false><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
+        else k_cbincount<true, true><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
         JCK(cudaGetLastError());
         JCK(bc_exclusive_scan(d_bin_cursor, (uint64_t)n_bins + 1, d_scan_tmp, st));
         k_cbin_init2<<<(n_bins + 256) / 256, 256, 0, st>>>(gp, n_bins, d_bin_cursor, d_bin_start, d_bin_combo);
@@ -1588,7 +1589,8 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             JCK(cudaGetLastError());
         } else {          // bin totals from shared-memory histograms; the slot histogram follows pass A
             JCK(cudaMemsetAsync(d_bin_cursor, 0, (n_bins + 1) * sizeof(uint32_t), st));
-            k_cbincount<false><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
+            if (p.slot_lo == 0 && p.slot_hi == n_slots) k_cbincount<false, false><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
+            else k_cbincount<false, true><<<(uint32_t)sm_count * 2u, CB_THREADS, 0, st>>>(gp, ws.d_lut, d_bin_cursor);
             JCK(cudaGetLastError());
             JCK(cudaEventRecord(ws.ev_k[0], st));  // end of the bin count
             JCK(bc_exclusive_scan(d_bin_cursor, (uint64_t)n_bins + 1, ws.d_scan_tmp, st));

@@ -601,15 +601,16 @@ def main():
         parts = {"k_cverify": acc["ms_scan_kernel"] - acc["ms_finish"], "k_cfinish": acc["ms_finish"],
                  "k_ccount": acc["ms_win_count"], "k_cbin": acc["ms_win_bin"], "k_cplace": acc["ms_win_place"],
                  "index_build": acc["ms_build_index"]}
-        # algorithmic HBM bytes per launch: count reads the planes; pass A reads them and writes every record
-        # (8 B); pass B reads and writes every record; verify reads the records' x word... (all 8 B sectors) and
-        # the index entries (8 B) once; finish writes the hits; the index build moves 8 B records twice and
-        # writes 12 B per entry
-        alg_bytes = {"k_ccount": 3 * G / 8, "k_cbin": 3 * G / 8 + rec_b * records, "k_cplace": 2 * rec_b * records,
+        # algorithmic HBM bytes per launch: count = k_cbincount (planes) + k_cslotcount (every record read once); pass A
+        # reads the planes and writes every record (8 B); pass B reads and writes every record; verify reads the
+        # records' x word... (all 8 B sectors) and the index entries (8 B) once; finish writes the hits; the index
+        # build moves 8 B records three times (write, count, read) and writes 12 B per entry
+        alg_bytes = {"k_ccount": 3 * G / 8 + rec_b * records, "k_cbin": 3 * G / 8 + rec_b * records, "k_cplace": 2 * rec_b * records,
                      "k_cverify": rec_b * records + 8.0 * entries, "k_cfinish": 16.0 * st["hits"],
                      "index_build": (8 + 8 + 8 + 8 + 12) * entries}
         names = {k2: k2 for k2 in parts}
-        names["index_build"] = "k_ccount<lib>+scan+k_cbin<lib>+k_cplace_bulk<lib>"
+        names["k_ccount"] = "k_cbincount<win>+k_cslotcount"
+        names["index_build"] = "k_cbincount<lib>+k_cbin<lib>+k_cslotcount+k_cplace_bulk<lib>"
         verify_key = "k_cverify"
     else:
         parts = {"verify": acc["ms_scan_kernel"], "window_sort": acc["ms_genome_bucket"],
@@ -663,7 +664,8 @@ def main():
                         "traffic": traffic if dominant == verify_key else None,
                         "share_of_step": parts[verify_key] / max(ms_per_step, 1e-9),
                         "peak_source": "bench_kernels/int_peak.cu measured in this run (POPC: 16/clk/SM)",
-                        "note": "peak = one POPC per candidate pair (1 pair in 8 is tested on the ALU pipe instead); "
+                        "note": "peak = one POPC per candidate pair; achieved counts the ALGORITHMIC pairs (windows x entries per "
+                                "slot) - padded lanes of ragged tiles are work the kernel does but is not credited for; "
                                 "pairs_vs_k_plus_1 = candidates / what the classic k+1-seed filter would verify"}
     roofline_gather = None
     if st["path"] == 1 and acc["ms_scan_kernel"] > 0:

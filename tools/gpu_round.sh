@@ -12,6 +12,10 @@ if has tests; then
   echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
   tail -3 gpurun_out/pytest_gpu.log
 fi
+if has smoke; then
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+  echo "smoke rc=$?"; tail -4 gpurun_out/smoke.log
+fi
 if has bench; then
   timeout 600 python bench.py > gpurun_out/bench_cfg4.json 2> gpurun_out/bench_cfg4.err
   echo "bench rc=$?"; tail -c 600 gpurun_out/bench_cfg4.json
