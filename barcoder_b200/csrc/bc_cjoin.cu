@@ -1238,11 +1238,14 @@ __global__ void __launch_bounds__(CV_THREADS, CV_MINBLOCKS) k_cverify(const __gr
     cv_flush_items(p, gwin, gq, gn);  // whatever is still queued
 }
 
+#ifndef CF_MINBLOCKS
+#define CF_MINBLOCKS 4
+#endif
 // Second level + hit resolution as a kernel of their own: every warp takes batches of 32 items of
 // the global queue, one per lane (8 entries each, tested against the item's window), queues the
 // passing pairs and resolves them 32 at a time (ownership, PAM, one atomic per batch).  All of it
 // is dependent random loads; here they overlap across ~10^8 items instead of stalling the POPC loop.
-__global__ void __launch_bounds__(CV_THREADS, 4) k_cfinish(const __grid_constant__ SearchParams p, const uint2* __restrict__ gwin) {
+__global__ void __launch_bounds__(CV_THREADS, CF_MINBLOCKS) k_cfinish(const __grid_constant__ SearchParams p, const uint2* __restrict__ gwin) {
     __shared__ uint4 s_q[CV_WARPS][CV_WQ];
     __shared__ uint32_t s_qn[CV_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1656,7 +1659,7 @@ cudaError_t bc_cjoin_search(JoinWorkspace& ws, const SearchParams& p, uint64_t d
             }
             JCK(cudaGetLastError());
             if (s + 1 == n_slices) JCK(cudaEventRecord(ws.ev_k[4], st));  // end of the (last) first-level kernel
-            k_cfinish<<<(uint32_t)sm_count * 4u, CV_THREADS, 0, st>>>(pv, d_win);
+            k_cfinish<<<(uint32_t)sm_count * CF_MINBLOCKS, CV_THREADS, 0, st>>>(pv, d_win);
             JCK(cudaGetLastError());
             bc_launch_counter += 1;
             if (sink) {
