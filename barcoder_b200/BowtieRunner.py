@@ -42,6 +42,52 @@ from .seqio import reverse_complement, write_fasta
 
 SAM_AUTO_LIMIT = 2_000_000
 
+try:  # string columns of 10^5..10^6 rows: Arrow kernels instead of one Python object per row
+    import pyarrow as _pa
+    import pyarrow.compute as _pc
+except ImportError:  # pragma: no cover - pandas works without it, only slower
+    _pa = _pc = None
+
+
+def _upper_and_lengths(reads):
+    """(upper-cased reads, their lengths as int64).  With pyarrow the first is an Arrow string array, else a list."""
+    if _pa is not None:
+        try:
+            arr = _pa.array(reads, type=_pa.string())
+            return _pc.utf8_upper(arr), _pc.utf8_length(arr).to_numpy(zero_copy_only=False).astype(np.int64)
+        except (_pa.ArrowInvalid, _pa.ArrowTypeError, TypeError):
+            pass
+    up = [r.upper() for r in reads]
+    return up, np.fromiter((len(r) for r in up), dtype=np.int64, count=len(up))
+
+
+def _take_str(values, idx):
+    """values[idx] as a pandas string column; values = an Arrow string array, or any sequence of str."""
+    if _pa is not None:
+        try:
+            arr = values if isinstance(values, (_pa.Array, _pa.ChunkedArray)) else _pa.array(list(values), type=_pa.string())
+            return pd.Series(arr.take(_pa.array(np.asarray(idx, dtype=np.int64))), dtype="str").array
+        except (_pa.ArrowInvalid, _pa.ArrowTypeError, TypeError, ValueError):
+            pass
+    vals = np.asarray(values.to_pylist() if _pa is not None and isinstance(values, (_pa.Array, _pa.ChunkedArray)) else list(values),
+                      dtype=object)
+    return vals[np.asarray(idx, dtype=np.int64)]
+
+
+def _rows_of(upper, idx, L):
+    """The spacers upper[idx] (all of length L) as a uint8 matrix [n, L] for bc_set_library."""
+    if _pa is not None and isinstance(upper, (_pa.Array, _pa.ChunkedArray)):
+        tk = upper.take(_pa.array(np.asarray(idx, dtype=np.int64)))
+        if isinstance(tk, _pa.ChunkedArray):
+            tk = tk.combine_chunks()
+        data = tk.buffers()[2]
+        if tk.offset == 0 and data is not None and data.size >= len(idx) * L:
+            flat = np.frombuffer(data, dtype=np.uint8, count=len(idx) * L)
+            if tk.null_count == 0:
+                return flat.reshape(len(idx), L)
+        return [s for s in tk.to_pylist()]
+    return [upper[i] for i in idx]
+
 
 
 class BowtieError(Exception):
@@ -64,6 +110,7 @@ class BowtieRunner(Logger):
         self._index_path = None
         self._contig_ids, self._contigs = [], []
         self._reads = []
+        self._upper = self._lens = None   # upper-cased reads (Arrow array or list) and their lengths, built by align()
         self._searcher = None
         self._pam = None  # (pam, direction) set explicitly through set_pam()
         self.hits = None
@@ -186,10 +233,9 @@ class BowtieRunner(Logger):
         self.json(["bc_search", "-a", f"-v{k}", f"reads={len(self._reads)}"])
         pam = self._pam_setting()
         reads = self._reads
-        upper = [r.upper() for r in reads]
-        by_len = {}
-        for i, r in enumerate(upper):
-            by_len.setdefault(len(r), []).append(i)
+        upper, lens = _upper_and_lengths(reads)
+        self._upper, self._lens = upper, lens
+        by_len = {int(L): np.nonzero(lens == L)[0] for L in np.unique(lens)}
         parts, self.stats = [], []
         active = self._searchers
         if self.devices == "auto" and num_threads:
@@ -202,7 +248,7 @@ class BowtieRunner(Logger):
                         raise BowtieError(f"spacers longer than 32 nt are not supported (got {L})")
                     continue
                 idx = np.asarray(idx, dtype=np.int64)
-                lib = [upper[i] for i in idx]
+                lib = _rows_of(upper, idx, L)
 
                 def one(srch, rank):
                     srch.set_pam(pam[0] if pam else "", pam[1] if pam else "downstream")
@@ -247,19 +293,19 @@ class BowtieRunner(Logger):
         hits, reads = self.hits, self._reads
         off = np.asarray(self._searcher.contig_offsets, dtype=np.int64)
         self._offsets = off
-        L = np.fromiter((len(r) for r in reads), dtype=np.int64, count=len(reads))
+        if getattr(self, "_upper", None) is None or len(self._lens) != len(reads):
+            self._upper, self._lens = _upper_and_lengths(reads)
+        barcode, L = self._upper, self._lens
         sid = hits["spacer_id"].astype(np.int64)
         ci = np.searchsorted(off[1:], hits["gpos"].astype(np.int64), side="right")
         start = hits["gpos"].astype(np.int64) - off[ci]
-        ids = np.asarray(self._contig_ids, dtype=object)
-        barcode = np.asarray([r.upper() for r in reads], dtype=object)
         df = pd.DataFrame({
-            "Chromosome": ids[ci] if len(hits) else np.zeros(0, dtype=object),
+            "Chromosome": _take_str(self._contig_ids, ci) if len(hits) else np.zeros(0, dtype=object),
             "Start": start,
             "End": start + L[sid] if len(hits) else start,
             "Mapped": np.ones(len(hits), dtype=bool),
-            "Strand": np.where(hits["meta"] & 1, "-", "+"),
-            "Barcode": barcode[sid] if len(hits) else np.zeros(0, dtype=object),
+            "Strand": _take_str(["+", "-"], hits["meta"] & 1) if len(hits) else np.zeros(0, dtype=object),
+            "Barcode": _take_str(barcode, sid) if len(hits) else np.zeros(0, dtype=object),
             "Mismatches": ((hits["meta"] >> 1) & 3).astype(np.int64),
         })
         if self._pam_used:
@@ -277,7 +323,7 @@ class BowtieRunner(Logger):
         if len(missing):  # flag-4 SAM lines: PySamParser reports them with Mismatches "0" (:45)
             um = pd.DataFrame({
                 "Chromosome": None, "Start": -1, "End": None, "Mapped": False, "Strand": "+",
-                "Barcode": barcode[missing], "Mismatches": "0",
+                "Barcode": _take_str(barcode, missing), "Mismatches": "0",
             })
             if self._pam_used:
                 um["PAM"] = ""
@@ -304,29 +350,30 @@ class BowtieRunner(Logger):
             table = np.empty(len(uniq), dtype=object)
             for t, code in enumerate(uniq.tolist()):
                 table[t] = "".join("ACGT"[(code >> (2 * i)) & 3] for i in range(P))
-            pam_str = table[inv] if len(hits) else np.zeros(0, dtype=object)
         else:
-            pam_str = np.full(len(hits), "", dtype=object)
+            table, inv = np.asarray([""], dtype=object), np.zeros(len(hits), dtype=np.int64)
         targeting = (meta & _native.META_PAM_OK) != 0
         lower = any(c != c.upper() for c in self._contigs) if not hasattr(self, "_has_lower") else self._has_lower
         self._has_lower = lower
         slow = ((meta & _native.META_PAM_FULL) == 0) | ((meta & _native.META_PAM_AMB) != 0)
         if lower:
             slow = np.ones(len(hits), dtype=bool)
-        if slow.any():
-            pattern = re.compile(pam.replace("N", "[ATCG]"))
-            minus = (meta & 1) != 0
-            upstream = self._pam_used[1] == "upstream"
-            for j in np.nonzero(slow)[0]:
-                seq = self._contigs[ci[j]]
-                s0, e0 = int(start[j]), int(start[j] + lens[j])
-                if upstream:  # 5' side of the protospacer; a PAM that leaves the contig is no PAM (targets.py:266-307)
-                    if minus[j]:
-                        s = reverse_complement(seq[e0:e0 + P]) if e0 + P <= len(seq) else ""
-                    else:
-                        s = seq[s0 - P:s0] if s0 - P >= 0 else ""
+        if not slow.any():
+            return (_take_str(table, inv) if len(hits) else np.zeros(0, dtype=object)), targeting
+        pam_str = table[inv] if len(hits) else np.zeros(0, dtype=object)
+        pattern = re.compile(pam.replace("N", "[ATCG]"))
+        minus = (meta & 1) != 0
+        upstream = self._pam_used[1] == "upstream"
+        for j in np.nonzero(slow)[0]:
+            seq = self._contigs[ci[j]]
+            s0, e0 = int(start[j]), int(start[j] + lens[j])
+            if upstream:  # 5' side of the protospacer; a PAM that leaves the contig is no PAM (targets.py:266-307)
+                if minus[j]:
+                    s = reverse_complement(seq[e0:e0 + P]) if e0 + P <= len(seq) else ""
                 else:
-                    s = reverse_complement(seq[s0 - P:s0]) if minus[j] else seq[e0:e0 + P]
-                pam_str[j] = s
-                targeting[j] = bool(pattern.search(s))
+                    s = seq[s0 - P:s0] if s0 - P >= 0 else ""
+            else:
+                s = reverse_complement(seq[s0 - P:s0]) if minus[j] else seq[e0:e0 + P]
+            pam_str[j] = s
+            targeting[j] = bool(pattern.search(s))
         return pam_str, targeting

@@ -76,16 +76,20 @@ def overlap_pairs(a, b):
     ones: the expansion stays proportional to the number of real pairs."""
     if len(a) == 0 or len(b) == 0:
         return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
-    li, ri = [], []
+    keys = []  # pairs as (i << 32 | j): one sort of 64-bit keys orders them by (i, j)
     a_chr = a["Chromosome"].to_numpy()
     b_chr = b["Chromosome"].to_numpy()
     a_s, a_e = a["Start"].to_numpy(dtype=np.int64), a["End"].to_numpy(dtype=np.int64)
     b_s, b_e = b["Start"].to_numpy(dtype=np.int64), b["End"].to_numpy(dtype=np.int64)
-    for chrom in pd.unique(a_chr):
-        ia = np.nonzero(a_chr == chrom)[0]
+    chroms = pd.unique(a_chr)
+    for chrom in chroms:
+        ia = np.arange(len(a)) if len(chroms) == 1 else np.nonzero(a_chr == chrom)[0]
         ib_all = np.nonzero(b_chr == chrom)[0]
         if len(ib_all) == 0:
             continue
+        # the a rows in Start order: sorted queries make the binary searches below run through the cache
+        ia = ia[np.argsort(a_s[ia], kind="stable")]
+        qs, qe = a_s[ia], a_e[ia]
         blen = np.maximum(b_e[ib_all] - b_s[ib_all], 1)
         cls = (np.log2(blen) // 2).astype(np.int64)
         for c in np.unique(cls):
@@ -94,8 +98,8 @@ def overlap_pairs(a, b):
             bs, be = b_s[ib], b_e[ib]
             max_len = int((be - bs).max())
             # b rows that can overlap a row: Start in (a.Start - max_len, a.End)
-            lo = np.searchsorted(bs, a_s[ia] - max_len, side="right")
-            hi = np.searchsorted(bs, a_e[ia], side="left")
+            lo = np.searchsorted(bs, qs - max_len, side="right")
+            hi = np.searchsorted(bs, qe, side="left")
             counts = np.maximum(hi - lo, 0)
             total = int(counts.sum())
             if total == 0:
@@ -103,11 +107,9 @@ def overlap_pairs(a, b):
             rep_a = np.repeat(np.arange(len(ia)), counts)
             offs = np.arange(total) - np.repeat(np.cumsum(counts) - counts, counts)
             cand_b = np.repeat(lo, counts) + offs
-            ok = (be[cand_b] > a_s[ia][rep_a]) & (bs[cand_b] < a_e[ia][rep_a])
-            li.append(ia[rep_a[ok]])
-            ri.append(ib[cand_b[ok]])
-    if not li:
+            ok = (be[cand_b] > qs[rep_a]) & (bs[cand_b] < qe[rep_a])
+            keys.append((ia[rep_a[ok]].astype(np.int64) << 32) | ib[cand_b[ok]].astype(np.int64))
+    if not keys:
         return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
-    li, ri = np.concatenate(li), np.concatenate(ri)
-    order = np.lexsort((ri, li))
-    return li[order], ri[order]
+    key = np.sort(np.concatenate(keys))
+    return key >> 32, key & 0xffffffff
