@@ -337,6 +337,40 @@ def test_cjoin_medium_multi_chunk_bins(gate, key_nt, blocks):
     assert_same(gpu2, ref)
 
 
+@pytest.mark.parametrize("path,key_nt", [(3, 10), (3, 9), (1, 0)])
+def test_low_complexity_genome_skewed_bins(path, key_nt):
+    """Homopolymer runs and tandem repeats: a few seed bins / slots hold most of the windows (skewed pass-A bins, slots
+    of thousands of windows against buckets of near-identical spacers, item-queue bursts: whole warps pass at once)."""
+    rng = np.random.default_rng(191)
+    parts = []
+    for i in range(40):
+        kind = i % 4
+        if kind == 0:
+            parts.append(rng.integers(0, 4, 4000))                        # random
+        elif kind == 1:
+            parts.append(np.full(3000, i % 3))                            # homopolymer
+        elif kind == 2:
+            parts.append(np.tile(rng.integers(0, 4, 2 + i % 5), 1500)[:3000])   # short tandem repeat
+        else:
+            parts.append(np.tile(rng.integers(0, 4, 23), 200)[:3000])     # 23-mer repeat
+    codes = np.concatenate(parts)
+    genome = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].copy()
+    off = np.array([0, len(genome) // 2, len(genome)], dtype=np.uint64)
+    lib = synth.random_library(1500, 20, seed=192)
+    # spacers taken from the repeats themselves (with up to 2 edits), plus pure homopolymers
+    for j in range(0, 600):
+        p0 = int(rng.integers(0, len(genome) - 20))
+        lib[j] = genome[p0:p0 + 20]
+        for _ in range(j % 3):
+            lib[j, int(rng.integers(0, 20))] = b"ACGT"[int(rng.integers(0, 4))]
+    lib[600] = ord("A"); lib[601] = ord("C"); lib[602] = ord("T")
+    ref = run_oracle(genome, off, lib, 3, pam="NGG")
+    assert len(ref) > 200_000
+    gpu, st = run_gpu(genome, off, lib, 3, pam="NGG", path=path, key_nt=key_nt)
+    assert st["path"] == path
+    assert_same(gpu, ref)
+
+
 def test_cjoin_dense_slots_duplicates_and_big_buckets():
     """Huge slots and buckets (4-nt keys), duplicate spacers, short spacers."""
     genome, off = synth.random_genome(300000, seed=161, n_contigs=3, n_fraction=0.01, n_run=5)
