@@ -162,7 +162,9 @@ int bc_set_param(bc_ctx* ctx, int key, int64_t value);
  * <= k mismatches on device (0 <= k <= 3).  Both the library and the genome must be loaded: the seed
  * scheme (block scheme or covering design, key length) and the scan path are chosen by a cost model
  * that needs the genome size; a later bc_set_genome / bc_set_library invalidates the index and
- * bc_search rebuilds it. */
+ * bc_search rebuilds it.  The kernels are enqueued on the context's stream and the call returns
+ * without waiting for them (a following bc_search runs behind them; device errors of the build surface
+ * there); bc_stats.ms_build_index is filled in by the next bc_search or bc_get_stats. */
 int bc_build_index(bc_ctx* ctx, int k);
 
 /* Replaces align (BowtieRunner.py:104-141): every ungapped end-to-end alignment of every
