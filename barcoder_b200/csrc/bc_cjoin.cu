@@ -777,9 +777,14 @@ __global__ void __launch_bounds__(CJ_THREADS, ITEMS > 8 ? 1 : 2) k_cplace_bulk(c
 #define CV_WARPS (CV_THREADS / 32)
 #define CV_ITEMS 4          // window records per lane per warp-tile (at most)
 #define CV_WQ 128           // per-warp candidate queue (entries)
-#define CV_QROWS 8          // per-warp item queue: CV_QROWS rows of 32 lane-private slots ({window, group} items for k_cfinish)
+#ifndef CV_QROWS
+#define CV_QROWS 8
+#endif
+// CV_QROWS: per-warp item queue: CV_QROWS rows of 32 lane-private slots ({window, group} items for k_cfinish)
 #define CV_GQ (32 * CV_QROWS)
-#define CV_STAGE 64         // library entries per shared-memory stage (x2 buffers per warp)
+#ifndef CV_STAGE
+#define CV_STAGE 32         // library entries per shared-memory stage (x2 buffers per warp); buckets hold ~19 entries at cfg 4 (64: 11.35 ms, 32: 11.09 ms)
+#endif
 #define CV_GROUP 8          // entries per group (one ballot per group)
 #ifndef CV_CHUNK_TILES
 #define CV_CHUNK_TILES 32   // 128-record units per work chunk
