@@ -298,3 +298,31 @@ def test_targets_rows_vectorised_equal_literal_loop(plasmids, cn32_spacers, pam,
     assert list(fa.columns) == list(fb.columns)
     key = list(fa.columns)
     assert fa.sort_values(key).reset_index(drop=True).astype(str).equals(fb.sort_values(key).reset_index(drop=True).astype(str))
+
+
+@pytest.mark.parametrize("with_arrow", [True, False])
+def test_bowtierunner_string_helpers(with_arrow, monkeypatch):
+    """The Arrow-backed column builders of BowtieRunner and their plain-Python fallbacks give the same values."""
+    import importlib
+    br = importlib.import_module("barcoder_b200.BowtieRunner")
+    if not with_arrow:
+        monkeypatch.setattr(br, "_pa", None)
+        monkeypatch.setattr(br, "_pc", None)
+    elif br._pa is None:
+        pytest.skip("pyarrow not installed")
+    reads = ["acgtACGTacgtACGTacgt", "TTTTTTTTTTTTTTTTTTTT", "GGGGGGGGGGGGGGGGGGGG", "acgtn", "ACGTACGTAC"]
+    upper, lens = br._upper_and_lengths(reads)
+    assert lens.tolist() == [20, 20, 20, 5, 10]
+    as_list = upper.to_pylist() if hasattr(upper, "to_pylist") else list(upper)
+    assert as_list == [r.upper() for r in reads]
+    idx = np.array([2, 0, 0, 1], dtype=np.int64)
+    col = br._take_str(upper, idx)
+    assert [str(x) for x in col] == [reads[i].upper() for i in idx]
+    assert [str(x) for x in br._take_str(["+", "-"], np.array([1, 0, 1]))] == ["-", "+", "-"]
+    rows = br._rows_of(upper, np.array([0, 1, 2]), 20)
+    if isinstance(rows, np.ndarray):
+        assert rows.shape == (3, 20) and bytes(rows[0]).decode() == reads[0].upper()
+    else:
+        assert rows == [r.upper() for r in reads[:3]]
+    df = pd.DataFrame({"Barcode": br._take_str(upper, idx), "n": np.arange(4)})
+    assert df["Barcode"].tolist() == [reads[i].upper() for i in idx]
