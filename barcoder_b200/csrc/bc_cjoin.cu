@@ -14,10 +14,15 @@
 //     A, up to 12 low bits in pass B), with 8192-record chunks so runs stay >= 64 bytes
 //     (bench_kernels/sort_lab.cu: direct 8-byte scatters cost 25 ps per record, staged runs 3-5 ps).
 //
-//   k_ccount      RED histogram of (window, combination) per directory slot         -> gdir (scan)
-//   k_cbin        pass A: windows -> records grouped by bin (top key bits), runs     -> tmp
-//   k_cplace      pass B: bin regions -> final slots (low key bits)                  -> gwin
-//   k_cverify<K>  slot-aligned warp-tiles of <= 128 windows against the slot's library bucket
+//   k_cbincount     bin totals per combination from shared-memory histograms           -> bin_start (scan)
+//   k_cbin          pass A: windows -> records grouped by bin (top key bits), runs      -> tmp
+//   k_cslotcount    slot histogram of the binned records (pieces of a bin in shared mem) -> gdir (scan)
+//   k_cplace_bulk   pass B: bin regions -> final slots (low key bits), bulk-async loads  -> gwin
+//   k_ctile_*       tile list: one descriptor per (slot, <= 128 windows)
+//   k_cverify<K>    first level: pipelined warp-tiles against the slot's library bucket  -> item queue
+//   k_cfinish       second level + hit resolution (ownership, PAM, records)              -> hits
+//   (k_ccount / k_cplace: the round-1 forms - one global RED per record, LDG-staged pass B - kept for A/B runs;
+//    the library index is built with the same passes, template parameter LIB)
 #include "bc_join.h"
 
 #include <stdio.h>
